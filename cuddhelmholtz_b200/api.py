@@ -1,0 +1,500 @@
+"""Host-side mirror of the reference's C++ interface for the solve path (same class / method names, argument
+meaning and error behaviour as cuddh.hpp), implemented as thin wrappers over the C ABI in
+include/cuddh_b200.h. Device vectors are torch CUDA tensors (torch is only the owner of device memory and
+streams here) or raw device addresses (int).
+
+    reference                                  here
+    Mesh2D::uniform_rect / from_vertices       Mesh2D.uniform_rect / Mesh2D.from_vertices
+    QuadratureRule(n, type)                    QuadratureRule(n, type)
+    Basis(n)::eval/deriv                       Basis(n).eval/deriv
+    H1Space(mesh, basis)                       H1Space(mesh, basis)
+    FaceSpace(fem, nf, faces)                  FaceSpace(fem, faces)
+    StiffnessMatrix / MassMatrix / ...         same names; .action(x, y) and .action(c, x, y)
+    gmres(n, x, A, b, [P,] m, maxit, tol,..)   gmres(n, x, A, b, m, maxit, tol, P=None, ...)
+    DDH(omega, h_a, fem, nx, ny)               DDH(omega, h_a, fem, nx, ny, block=16)
+"""
+import ctypes as C
+import numpy as np
+
+from . import capi
+from .capi import check, load
+
+GaussLegendre, GaussLobatto = 0, 1
+
+
+def _ptr(t):
+    """device address of a torch tensor (must be contiguous CUDA) or pass-through of an int / None."""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return t
+    if not t.is_cuda:
+        raise capi.CuddhError("expected a CUDA tensor (every vector argument is a DEVICE pointer)")
+    if not t.is_contiguous():
+        raise capi.CuddhError("expected a contiguous tensor")
+    return t.data_ptr()
+
+
+def _stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream if torch.cuda.is_available() else None
+
+
+def _np(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class QuadratureRule:
+    """include/QuadratureRule.hpp:13-77."""
+    GaussLegendre, GaussLobatto = 0, 1
+
+    def __init__(self, n, type=GaussLobatto):
+        self.n, self.type = n, type
+        self._x = np.zeros(n)
+        self._w = np.zeros(n)
+        check(load().cuddh_b200_quadrature(n, type, _vp(self._x), _vp(self._w)))
+
+    def size(self):
+        return self.n
+
+    def x(self, i=None):
+        return self._x if i is None else self._x[i]
+
+    def w(self, i=None):
+        return self._w if i is None else self._w[i]
+
+    def name(self):
+        return ("legendre" if self.type == GaussLegendre else "lobatto") + "%05d" % self.n
+
+
+class Basis:
+    """include/Basis.hpp:13-63."""
+
+    def __init__(self, n):
+        self.n = n
+        self._h = C.c_void_p()
+        check(load().cuddh_b200_basis_create(n, C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            load().cuddh_b200_basis_destroy(self._h)
+            self._h = None
+
+    def size(self):
+        return self.n
+
+    def eval(self, x):
+        """P with P[j, i] = phi_i(x_j) (the reference's column-major (m, n) array, returned as numpy (m, n))."""
+        x = _np(x, np.float64)
+        P = np.zeros((self.n, len(x)))
+        check(load().cuddh_b200_basis_eval(self._h, len(x), _vp(x), _vp(P)))
+        return P.T.copy()
+
+    def deriv(self, x):
+        x = _np(x, np.float64)
+        D = np.zeros((self.n, len(x)))
+        check(load().cuddh_b200_basis_deriv(self._h, len(x), _vp(x), _vp(D)))
+        return D.T.copy()
+
+    def quadrature(self):
+        x = np.zeros(self.n)
+        w = np.zeros(self.n)
+        check(load().cuddh_b200_basis_nodes(self._h, _vp(x), _vp(w)))
+        return x, w
+
+
+class Mesh2D:
+    """include/Mesh2D.hpp."""
+
+    def __init__(self, handle):
+        self._h = handle
+        s = np.zeros(5, np.int64)
+        check(load().cuddh_b200_mesh_sizes(self._h, _vp(s)))
+        self._sizes = s
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            load().cuddh_b200_mesh_destroy(self._h)
+            self._h = None
+
+    @staticmethod
+    def uniform_rect(nx, ax, bx, ny, ay, by):
+        h = C.c_void_p()
+        check(load().cuddh_b200_mesh_uniform_rect(nx, ax, bx, ny, ay, by, C.byref(h)))
+        return Mesh2D(h)
+
+    @staticmethod
+    def from_vertices(xy, elems):
+        """xy: (nv, 2) coordinates, elems: (nel, 4) CCW corner indices."""
+        xy = _np(xy, np.float64)
+        elems = _np(elems, np.int32)
+        h = C.c_void_p()
+        check(load().cuddh_b200_mesh_from_vertices(len(xy), _vp(xy), len(elems), _vp(elems), C.byref(h)))
+        return Mesh2D(h)
+
+    def n_elem(self):
+        return int(self._sizes[0])
+
+    def n_nodes(self):
+        return int(self._sizes[1])
+
+    def n_edges(self, kind=None):
+        return int(self._sizes[2] if kind is None else self._sizes[3] if kind == "boundary" else self._sizes[4])
+
+    def edges(self):
+        """(n_edges, 8): nodes0, nodes1, el0, el1, side0, side1, delta, is_boundary."""
+        e = np.zeros((self.n_edges(), 8), np.int32)
+        check(load().cuddh_b200_mesh_edges(self._h, _vp(e)))
+        return e
+
+    def boundary_edges(self):
+        b = np.zeros(int(self._sizes[3]), np.int32)
+        check(load().cuddh_b200_mesh_boundary_edges(self._h, _vp(b)))
+        return b
+
+    def min_h(self):
+        a, b = C.c_double(), C.c_double()
+        check(load().cuddh_b200_mesh_h(self._h, C.byref(a), C.byref(b)))
+        return a.value
+
+    def max_h(self):
+        a, b = C.c_double(), C.c_double()
+        check(load().cuddh_b200_mesh_h(self._h, C.byref(a), C.byref(b)))
+        return b.value
+
+
+class H1Space:
+    """include/H1Space.hpp:18-65."""
+
+    def __init__(self, mesh, basis):
+        self._mesh, self._basis = mesh, basis
+        self.n_basis = basis.size()
+        self._h = C.c_void_p()
+        check(load().cuddh_b200_h1space_create(mesh._h, self.n_basis, C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            load().cuddh_b200_h1space_destroy(self._h)
+            self._h = None
+
+    def size(self):
+        return int(load().cuddh_b200_h1space_size(self._h))
+
+    def mesh(self):
+        return self._mesh
+
+    def basis(self):
+        return self._basis
+
+    def global_indices(self):
+        """host copy, numpy (n_elem, nb, nb) with [el, j, i] = I(i, j, el)."""
+        nb = self.n_basis
+        I = np.zeros((self._mesh.n_elem(), nb, nb), np.int32)
+        check(load().cuddh_b200_h1space_global_indices(self._h, _vp(I)))
+        return I
+
+    def physical_coordinates(self):
+        xy = np.zeros((self.size(), 2))
+        check(load().cuddh_b200_h1space_physical_coordinates(self._h, _vp(xy)))
+        return xy
+
+
+class FaceSpace:
+    """include/H1Space.hpp:69-147."""
+
+    def __init__(self, fem, faces):
+        self.fem = fem
+        faces = _np(faces, np.int32)
+        self._nf = len(faces)
+        self._h = C.c_void_p()
+        check(load().cuddh_b200_facespace_create(fem._h, len(faces), _vp(faces), C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            load().cuddh_b200_facespace_destroy(self._h)
+            self._h = None
+
+    def size(self):
+        return int(load().cuddh_b200_facespace_size(self._h))
+
+    def n_faces(self):
+        return self._nf
+
+    def h1_space(self):
+        return self.fem
+
+    def subspace_indices(self):
+        I = np.zeros((self._nf, self.fem.n_basis), np.int32)
+        check(load().cuddh_b200_facespace_subspace_indices(self._h, _vp(I)))
+        return I
+
+    def global_indices(self):
+        p = np.zeros(self.size(), np.int32)
+        check(load().cuddh_b200_facespace_global_indices(self._h, _vp(p)))
+        return p
+
+    def restrict(self, x, y):
+        check(load().cuddh_b200_facespace_restrict(self._h, _ptr(x), _ptr(y), _stream()))
+
+    def prolong(self, x, y):
+        check(load().cuddh_b200_facespace_prolong(self._h, _ptr(x), _ptr(y), _stream()))
+
+    def orth(self, x):
+        check(load().cuddh_b200_facespace_orth(self._h, _ptr(x), _stream()))
+
+
+class Operator:
+    """include/Operator.hpp:6-17: action(c, x, y): y += c*A*x ; action(x, y): y = A*x (device vectors)."""
+
+    _h = None
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            load().cuddh_b200_operator_destroy(self._h)
+            self._h = None
+
+    def action(self, *args):
+        if len(args) == 2:
+            x, y = args
+            check(load().cuddh_b200_operator_apply(self._h, 1.0, 0, _ptr(x), _ptr(y), _stream()))
+        elif len(args) == 3:
+            c, x, y = args
+            check(load().cuddh_b200_operator_apply(self._h, float(c), 1, _ptr(x), _ptr(y), _stream()))
+        else:
+            raise TypeError("action(x, y) or action(c, x, y)")
+
+    def algorithmic_bytes(self):
+        return int(load().cuddh_b200_operator_bytes(self._h))
+
+    # C callback usable by gmres without a Python trampoline
+    def _as_apply(self):
+        return C.cast(load().cuddh_b200_operator_as_apply, C.c_void_p), self._h
+
+
+class StiffnessMatrix(Operator):
+    """include/StiffnessMatrix.hpp:11-38."""
+
+    def __init__(self, fem, quad=None):
+        self.fem = fem
+        self._h = C.c_void_p()
+        nq, qt = (0, GaussLegendre) if quad is None else (quad.size(), quad.type)
+        check(load().cuddh_b200_stiffness_create(fem._h, nq, qt, C.byref(self._h)))
+
+
+class MassMatrix(Operator):
+    """include/MassMatrix.hpp:14-41: MassMatrix(fem) or MassMatrix(a, fem) with `a` a DEVICE nodal vector."""
+
+    def __init__(self, *args, n_quad=0):
+        a, fem = (None, args[0]) if len(args) == 1 else args
+        self.fem, self._a = fem, a
+        self._h = C.c_void_p()
+        check(load().cuddh_b200_mass_create(fem._h, _ptr(a), n_quad, C.byref(self._h)))
+
+
+class DiagInvMassMatrix(Operator):
+    """include/MassMatrix.hpp:44-68."""
+
+    def __init__(self, *args):
+        a, fem = (None, args[0]) if len(args) == 1 else args
+        self.fem = fem
+        self._h = C.c_void_p()
+        check(load().cuddh_b200_diag_inv_mass_create(fem._h, _ptr(a), C.byref(self._h)))
+
+
+class FaceMassMatrix(Operator):
+    """include/FaceMassMatrix.hpp: FaceMassMatrix(fs) or FaceMassMatrix(a, fs); vectors are FaceSpace vectors."""
+
+    def __init__(self, *args, n_quad=0):
+        a, fs = (None, args[0]) if len(args) == 1 else args
+        self.fs = fs
+        self._h = C.c_void_p()
+        check(load().cuddh_b200_facemass_create(fs._h, _ptr(a), n_quad, C.byref(self._h)))
+
+    def action_h1(self, c, x, y):
+        """fused restrict + action + prolong on H1 vectors: y[proj] += c * H * x[proj]."""
+        check(load().cuddh_b200_facemass_apply_h1(self._h, float(c), _ptr(x), _ptr(y), _stream()))
+
+
+class DiagInvFaceMassMatrix(Operator):
+    def __init__(self, *args):
+        a, fs = (None, args[0]) if len(args) == 1 else args
+        self.fs = fs
+        self._h = C.c_void_p()
+        check(load().cuddh_b200_diag_inv_facemass_create(fs._h, _ptr(a), C.byref(self._h)))
+
+
+class Helmholtz(Operator):
+    """examples/Helmholtz.hpp:10-80: x = [u; v] -> [S u - w^2 M u - w H v ; -(S v - w^2 M v + w H u)]."""
+
+    def __init__(self, omega, a2x, ax, fem, fs):
+        self.fem, self.fs, self.omega = fem, fs, omega
+        self._h = C.c_void_p()
+        check(load().cuddh_b200_helmholtz_create(float(omega), _ptr(a2x), _ptr(ax), fem._h, fs._h, C.byref(self._h)))
+
+    def action(self, *args):
+        if len(args) != 2:
+            raise capi.CuddhError("Helmholtz::action(c, x, y) not implemented")
+        x, y = args
+        check(load().cuddh_b200_operator_apply(self._h, 1.0, 0, _ptr(x), _ptr(y), _stream()))
+
+
+class SolverOut:
+    """include/gmres.hpp:14-21 solver_out."""
+
+    def __init__(self, so, res, time):
+        self.success = bool(so.success)
+        self.num_iter = so.num_iter
+        self.num_matvec = so.num_matvec
+        self.res_norm = list(res[:so.n_res])
+        self.time = list(time[:so.n_res])
+
+
+def _callback(A, kind):
+    """(function pointer, ctx, keepalive) for an operator: library objects use the in-library trampoline, any
+    object with .action(x, y) taking raw device addresses is wrapped in a ctypes callback."""
+    if hasattr(A, "_as_apply"):
+        fn, ctx = A._as_apply()
+        return fn, ctx, None
+    proto = capi.APPLY_D if kind == "d" else capi.APPLY_F
+
+    def tramp(_ctx, x, y):
+        A.action(int(x), int(y))
+
+    cb = proto(tramp)
+    return C.cast(cb, C.c_void_p), None, cb
+
+
+def gmres(n, x, A, b, m, maxit, tol=None, P=None, verbose=0, max_seconds=6 * 60 * 60):
+    """include/gmres.hpp:33-36. x, b: device vectors (torch float64 -> FP64 solver, float32 -> FP32 solver).
+    A (and P): operators of this module, or any object with .action(x_ptr, y_ptr) on raw device addresses."""
+    import torch
+    single = isinstance(x, torch.Tensor) and x.dtype == torch.float32
+    cap = maxit + 2
+    res = np.zeros(cap)
+    tim = np.zeros(cap)
+    so = capi.SolverOut()
+    fa, ca, keep_a = _callback(A, "f" if single else "d")
+    if single:
+        if P is not None:
+            raise capi.CuddhError("the FP32 gmres overload has no preconditioner argument (include/gmres.hpp:36)")
+        tol = 1e-4 if tol is None else tol
+        check(load().cuddh_b200_gmres_f(n, _ptr(x), fa, ca, _ptr(b), m, maxit, tol, verbose, float(max_seconds), C.byref(so),
+                                        _vp(res), _vp(tim), cap, _stream()))
+    else:
+        tol = 1e-6 if tol is None else tol
+        fp, cp, keep_p = (None, None, None) if P is None else _callback(P, "d")
+        check(load().cuddh_b200_gmres_d(n, _ptr(x), fa, ca, _ptr(b), fp, cp, m, maxit, tol, verbose, float(max_seconds),
+                                        C.byref(so), _vp(res), _vp(tim), cap, _stream()))
+    return SolverOut(so, res, tim)
+
+
+class DDH:
+    """include/DDH.hpp:21-84 (SinglePrecisionOperator). h_a: HOST nodal coefficient (numpy, length ndof)."""
+
+    def __init__(self, omega, h_a, fem, nx, ny, block=16):
+        self.fem = fem
+        h_a = _np(h_a, np.float64)
+        if len(h_a) != fem.size():
+            raise capi.CuddhError("DDH: coefficient array must have length fem.size()")
+        self._h = C.c_void_p()
+        check(load().cuddh_b200_ddh_create(float(omega), _vp(h_a), fem._h, nx, ny, block, C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            load().cuddh_b200_ddh_destroy(self._h)
+            self._h = None
+
+    def size(self):
+        return int(load().cuddh_b200_ddh_size(self._h))
+
+    def rhs(self, f, b):
+        check(load().cuddh_b200_ddh_rhs(self._h, _ptr(f), _ptr(b), _stream()))
+
+    def action(self, x, y):
+        check(load().cuddh_b200_ddh_action(self._h, _ptr(x), _ptr(y), _stream()))
+
+    def postprocess(self, lam, f, u):
+        check(load().cuddh_b200_ddh_postprocess(self._h, _ptr(lam), _ptr(f), _ptr(u), _stream()))
+
+    def info(self):
+        v = np.zeros(8, np.int64)
+        dt = C.c_double()
+        check(load().cuddh_b200_ddh_info(self._h, _vp(v), C.byref(dt)))
+        keys = ["n_domains", "n_shared", "nt", "mx_dof", "mx_fdof", "mx_elem_per_dom", "n_basis", "block"]
+        d = {k: int(x) for k, x in zip(keys, v)}
+        d["dt"] = dt.value
+        return d
+
+    def array(self, name):
+        cnt = C.c_int64()
+        check(load().cuddh_b200_ddh_get_array(self._h, name.encode(), None, 0, C.byref(cnt)))
+        isf = name in ("m", "gmi", "a", "H", "D", "g", "wh_filter", "cs", "sn")
+        out = np.zeros(cnt.value, np.float32 if isf else np.int32)
+        check(load().cuddh_b200_ddh_get_array(self._h, name.encode(), _vp(out), out.nbytes, C.byref(cnt)))
+        return out
+
+    def flops(self):
+        return float(load().cuddh_b200_ddh_flops(self._h))
+
+    def _as_apply(self):
+        return C.cast(load().cuddh_b200_ddh_as_apply, C.c_void_p), self._h
+
+
+# include/linalg.hpp
+def _lin(name, *a):
+    check(getattr(load(), name)(*a))
+
+
+def dot(n, x, y):
+    import torch
+    if x.dtype == torch.float32:
+        r = C.c_float()
+        _lin("cuddh_b200_dot_f", n, _ptr(x), _ptr(y), C.byref(r), _stream())
+    else:
+        r = C.c_double()
+        _lin("cuddh_b200_dot_d", n, _ptr(x), _ptr(y), C.byref(r), _stream())
+    return r.value
+
+
+def norm(n, x):
+    return float(np.sqrt(dot(n, x, x)))
+
+
+def dist(n, x, y):
+    import torch
+    if x.dtype == torch.float32:
+        r = C.c_float()
+        _lin("cuddh_b200_dist_f", n, _ptr(x), _ptr(y), C.byref(r), _stream())
+    else:
+        r = C.c_double()
+        _lin("cuddh_b200_dist_d", n, _ptr(x), _ptr(y), C.byref(r), _stream())
+    return r.value
+
+
+def _suffix(x):
+    import torch
+    return {torch.float64: "d", torch.float32: "f", torch.int32: "i"}[x.dtype]
+
+
+def axpby(n, a, x, b, y):
+    _lin("cuddh_b200_axpby_" + _suffix(x), n, a, _ptr(x), b, _ptr(y), _stream())
+
+
+def copy(n, x, y):
+    _lin("cuddh_b200_copy_" + _suffix(x), n, _ptr(x), _ptr(y), _stream())
+
+
+def scal(n, a, x):
+    _lin("cuddh_b200_scal_" + _suffix(x), n, a, _ptr(x), _stream())
+
+
+def fill(n, a, x):
+    _lin("cuddh_b200_fill_" + _suffix(x), n, a, _ptr(x), _stream())
+
+
+def launch_count():
+    return int(load().cuddh_b200_launch_count())

@@ -1,0 +1,497 @@
+// extern "C" boundary of libcuddh_b200.so (see include/cuddh_b200.h). Every entry point converts C++
+// exceptions into a status code + last-error string; nothing throws across the ABI.
+#include "../../include/cuddh_b200.h"
+#include "common.hpp"
+#include "ddh.hpp"
+#include "linalg.hpp"
+#include "operators.hpp"
+#include <atomic>
+#include <cstring>
+
+namespace cb200
+{
+    static thread_local std::string g_last_error;
+    void set_last_error(const std::string & msg) { g_last_error = msg; }
+    const char * get_last_error() { return g_last_error.c_str(); }
+    std::atomic<int64_t> g_launches{0};
+} // namespace cb200
+
+using namespace cb200;
+
+#define CB_TRY try {
+#define CB_CATCH                                                                        \
+    }                                                                                   \
+    catch (const cb200::Error & e)                                                      \
+    {                                                                                   \
+        set_last_error(e.what());                                                       \
+        return e.code ? e.code : -1;                                                    \
+    }                                                                                   \
+    catch (const std::exception & e)                                                    \
+    {                                                                                   \
+        set_last_error(e.what());                                                       \
+        return -2;                                                                      \
+    }                                                                                   \
+    return 0;
+
+struct cuddh_mesh_s { std::unique_ptr<Mesh> m; };
+struct cuddh_basis_s { std::unique_ptr<Basis> b; };
+struct cuddh_h1space_s { std::unique_ptr<H1Space> s; };
+struct cuddh_facespace_s { std::unique_ptr<FaceSpace> f; };
+struct cuddh_operator_s
+{
+    std::unique_ptr<VolumeOp> vol;
+    std::unique_ptr<DiagOp> diag;
+    std::unique_ptr<FaceMassOp> face;
+    std::unique_ptr<HelmholtzOp> helm;
+};
+struct cuddh_ddh_s { std::unique_ptr<DDH> d; };
+
+static inline cudaStream_t S(void * s) { return (cudaStream_t)s; }
+
+extern "C" {
+
+int cuddh_b200_version(void) { return 100; }
+const char * cuddh_b200_last_error(void) { return get_last_error(); }
+int64_t cuddh_b200_launch_count(void) { return g_launches.load(); }
+
+// ---- tables ----
+int cuddh_b200_quadrature(int n, int type, double * x, double * w)
+{
+    CB_TRY
+    CB_REQUIRE(type == CUDDH_GAUSS_LEGENDRE || type == CUDDH_GAUSS_LOBATTO, "unknown quadrature type");
+    quadrature_rule(n, type, x, w);
+    CB_CATCH
+}
+int cuddh_b200_basis_create(int n, cuddh_basis_t * out)
+{
+    CB_TRY
+    *out = new cuddh_basis_s{std::unique_ptr<Basis>(new Basis(n))};
+    CB_CATCH
+}
+int cuddh_b200_basis_destroy(cuddh_basis_t b)
+{
+    delete b;
+    return 0;
+}
+int cuddh_b200_basis_eval(cuddh_basis_t b, int m, const double * x, double * P)
+{
+    CB_TRY
+    b->b->eval(m, x, P);
+    CB_CATCH
+}
+int cuddh_b200_basis_deriv(cuddh_basis_t b, int m, const double * x, double * D)
+{
+    CB_TRY
+    b->b->deriv(m, x, D);
+    CB_CATCH
+}
+int cuddh_b200_basis_nodes(cuddh_basis_t b, double * x, double * w)
+{
+    CB_TRY
+    std::memcpy(x, b->b->x.data(), sizeof(double) * b->b->n);
+    std::memcpy(w, b->b->w.data(), sizeof(double) * b->b->n);
+    CB_CATCH
+}
+
+// ---- mesh ----
+int cuddh_b200_mesh_uniform_rect(int nx, double ax, double bx, int ny, double ay, double by, cuddh_mesh_t * out)
+{
+    CB_TRY
+    *out = new cuddh_mesh_s{Mesh::uniform_rect(nx, ax, bx, ny, ay, by)};
+    CB_CATCH
+}
+int cuddh_b200_mesh_from_vertices(int64_t nv, const double * xy, int64_t nel, const int * elems, cuddh_mesh_t * out)
+{
+    CB_TRY
+    *out = new cuddh_mesh_s{Mesh::from_vertices(nv, xy, nel, elems)};
+    CB_CATCH
+}
+int cuddh_b200_mesh_destroy(cuddh_mesh_t m)
+{
+    delete m;
+    return 0;
+}
+int cuddh_b200_mesh_sizes(cuddh_mesh_t m, int64_t * sizes)
+{
+    CB_TRY
+    sizes[0] = m->m->n_elem;
+    sizes[1] = m->m->n_nodes;
+    sizes[2] = m->m->n_edges;
+    sizes[3] = (int64_t)m->m->boundary_edges.size();
+    sizes[4] = (int64_t)m->m->interior_edges.size();
+    CB_CATCH
+}
+int cuddh_b200_mesh_edges(cuddh_mesh_t m, int * e)
+{
+    CB_TRY
+    std::memcpy(e, m->m->edges.data(), sizeof(int) * m->m->edges.size());
+    CB_CATCH
+}
+int cuddh_b200_mesh_boundary_edges(cuddh_mesh_t m, int * l)
+{
+    CB_TRY
+    std::memcpy(l, m->m->boundary_edges.data(), sizeof(int) * m->m->boundary_edges.size());
+    CB_CATCH
+}
+int cuddh_b200_mesh_h(cuddh_mesh_t m, double * min_h, double * max_h)
+{
+    CB_TRY
+    *min_h = m->m->min_h;
+    *max_h = m->m->max_h;
+    CB_CATCH
+}
+
+// ---- H1 space ----
+int cuddh_b200_h1space_create(cuddh_mesh_t mesh, int nb, cuddh_h1space_t * out)
+{
+    CB_TRY
+    *out = new cuddh_h1space_s{std::unique_ptr<H1Space>(new H1Space(mesh->m.get(), nb))};
+    CB_CATCH
+}
+int cuddh_b200_h1space_destroy(cuddh_h1space_t s)
+{
+    delete s;
+    return 0;
+}
+int64_t cuddh_b200_h1space_size(cuddh_h1space_t s) { return s->s->ndof; }
+int cuddh_b200_h1space_global_indices(cuddh_h1space_t s, int * I)
+{
+    CB_TRY
+    std::memcpy(I, s->s->I.data(), sizeof(int) * s->s->I.size());
+    CB_CATCH
+}
+int cuddh_b200_h1space_physical_coordinates(cuddh_h1space_t s, double * xy)
+{
+    CB_TRY
+    std::memcpy(xy, s->s->xy.data(), sizeof(double) * s->s->xy.size());
+    CB_CATCH
+}
+const int * cuddh_b200_h1space_device_indices(cuddh_h1space_t s)
+{
+    try {
+        return s->s->device_I();
+    }
+    catch (const std::exception & e) {
+        set_last_error(e.what());
+        return nullptr;
+    }
+}
+const double * cuddh_b200_h1space_device_coordinates(cuddh_h1space_t s)
+{
+    try {
+        return s->s->device_xy();
+    }
+    catch (const std::exception & e) {
+        set_last_error(e.what());
+        return nullptr;
+    }
+}
+
+// ---- face space ----
+int cuddh_b200_facespace_create(cuddh_h1space_t s, int64_t nf, const int * faces, cuddh_facespace_t * out)
+{
+    CB_TRY
+    *out = new cuddh_facespace_s{std::unique_ptr<FaceSpace>(new FaceSpace(s->s.get(), nf, faces))};
+    CB_CATCH
+}
+int cuddh_b200_facespace_destroy(cuddh_facespace_t f)
+{
+    delete f;
+    return 0;
+}
+int64_t cuddh_b200_facespace_size(cuddh_facespace_t f) { return f->f->fdof; }
+int cuddh_b200_facespace_subspace_indices(cuddh_facespace_t f, int * I)
+{
+    CB_TRY
+    std::memcpy(I, f->f->I.data(), sizeof(int) * f->f->I.size());
+    CB_CATCH
+}
+int cuddh_b200_facespace_global_indices(cuddh_facespace_t f, int * p)
+{
+    CB_TRY
+    std::memcpy(p, f->f->proj.data(), sizeof(int) * f->f->proj.size());
+    CB_CATCH
+}
+int cuddh_b200_facespace_restrict(cuddh_facespace_t f, const double * x, double * y, void * stream)
+{
+    CB_TRY
+    face_restrict(f->f.get(), x, y, S(stream));
+    CB_CATCH
+}
+int cuddh_b200_facespace_prolong(cuddh_facespace_t f, const double * x, double * y, void * stream)
+{
+    CB_TRY
+    face_prolong(f->f.get(), x, y, S(stream));
+    CB_CATCH
+}
+int cuddh_b200_facespace_orth(cuddh_facespace_t f, double * x, void * stream)
+{
+    CB_TRY
+    face_orth(f->f.get(), x, S(stream));
+    CB_CATCH
+}
+
+// ---- operators ----
+int cuddh_b200_stiffness_create(cuddh_h1space_t s, int nq, int quad_type, cuddh_operator_t * out)
+{
+    CB_TRY
+    auto * op = new cuddh_operator_s;
+    std::unique_ptr<cuddh_operator_s> guard(op);
+    op->vol = make_stiffness(s->s.get(), nq, quad_type);
+    *out = guard.release();
+    CB_CATCH
+}
+int cuddh_b200_mass_create(cuddh_h1space_t s, const double * d_a, int nq, cuddh_operator_t * out)
+{
+    CB_TRY
+    std::unique_ptr<cuddh_operator_s> op(new cuddh_operator_s);
+    op->vol = make_mass(s->s.get(), d_a, nq);
+    *out = op.release();
+    CB_CATCH
+}
+int cuddh_b200_diag_inv_mass_create(cuddh_h1space_t s, const double * d_a, cuddh_operator_t * out)
+{
+    CB_TRY
+    std::unique_ptr<cuddh_operator_s> op(new cuddh_operator_s);
+    op->diag = make_diag_inv_mass(s->s.get(), d_a);
+    *out = op.release();
+    CB_CATCH
+}
+int cuddh_b200_facemass_create(cuddh_facespace_t f, const double * d_a, int nq, cuddh_operator_t * out)
+{
+    CB_TRY
+    std::unique_ptr<cuddh_operator_s> op(new cuddh_operator_s);
+    op->face = make_facemass(f->f.get(), d_a, nq);
+    *out = op.release();
+    CB_CATCH
+}
+int cuddh_b200_diag_inv_facemass_create(cuddh_facespace_t f, const double * d_a, cuddh_operator_t * out)
+{
+    CB_TRY
+    std::unique_ptr<cuddh_operator_s> op(new cuddh_operator_s);
+    op->diag = make_diag_inv_facemass(f->f.get(), d_a);
+    *out = op.release();
+    CB_CATCH
+}
+int cuddh_b200_helmholtz_create(double omega, const double * d_a2, const double * d_a, cuddh_h1space_t s, cuddh_facespace_t f,
+                                cuddh_operator_t * out)
+{
+    CB_TRY
+    std::unique_ptr<cuddh_operator_s> op(new cuddh_operator_s);
+    op->helm = make_helmholtz(omega, d_a2, d_a, s->s.get(), f->f.get());
+    *out = op.release();
+    CB_CATCH
+}
+int cuddh_b200_operator_apply(cuddh_operator_t op, double c, int accumulate, const double * x, double * y, void * stream)
+{
+    CB_TRY
+    if (op->vol)
+        op->vol->apply(c, accumulate, x, y, S(stream));
+    else if (op->diag)
+        op->diag->apply(c, accumulate, x, y, S(stream));
+    else if (op->face)
+        op->face->apply(c, accumulate, x, y, S(stream));
+    else if (op->helm) {
+        // examples/Helmholtz.hpp:62-65: action(c, x, y) is not implemented by the reference composite
+        CB_REQUIRE(!accumulate && c == 1.0, "Helmholtz::action(c, x, y) not implemented");
+        op->helm->apply(x, y, S(stream));
+    }
+    else
+        throw Error(-1, "operator_apply: empty operator handle");
+    CB_CATCH
+}
+int cuddh_b200_facemass_apply_h1(cuddh_operator_t op, double c, const double * x, double * y, void * stream)
+{
+    CB_TRY
+    CB_REQUIRE(op->face != nullptr, "facemass_apply_h1: not a FaceMassMatrix handle");
+    op->face->apply_h1(c, x, y, S(stream));
+    CB_CATCH
+}
+int cuddh_b200_operator_destroy(cuddh_operator_t op)
+{
+    delete op;
+    return 0;
+}
+int64_t cuddh_b200_operator_bytes(cuddh_operator_t op)
+{
+    if (op->vol)
+        return (int64_t)op->vol->algorithmic_bytes();
+    if (op->helm) {
+        // fused-read formulation of SURVEY §8(d): 24nqS^2 + 8nqM^2 + 4nb^2 + 32(nb-1)^2 per element
+        const int nb = op->helm->fem->nb, qs = op->helm->S->nq, qm = op->helm->M->nq;
+        return (int64_t)op->helm->fem->n_elem * (24ll * qs * qs + 8ll * qm * qm + 4ll * nb * nb + 32ll * (nb - 1) * (nb - 1));
+    }
+    return 0;
+}
+
+// ---- linalg ----
+#define CB_LINALG2(NAME, T, SUF)                                                                          \
+    int cuddh_b200_axpby_##SUF(int64_t n, T a, const T * x, T b, T * y, void * stream)                    \
+    {                                                                                                     \
+        CB_TRY axpby<T>(n, a, x, b, y, S(stream));                                                        \
+        CB_CATCH                                                                                          \
+    }                                                                                                     \
+    int cuddh_b200_dot_##SUF(int64_t n, const T * x, const T * y, T * r, void * stream)                   \
+    {                                                                                                     \
+        CB_TRY * r = dot<T>(n, x, y, S(stream));                                                          \
+        CB_CATCH                                                                                          \
+    }                                                                                                     \
+    int cuddh_b200_dist_##SUF(int64_t n, const T * x, const T * y, T * r, void * stream)                  \
+    {                                                                                                     \
+        CB_TRY * r = dist<T>(n, x, y, S(stream));                                                         \
+        CB_CATCH                                                                                          \
+    }                                                                                                     \
+    int cuddh_b200_copy_##SUF(int64_t n, const T * x, T * y, void * stream)                               \
+    {                                                                                                     \
+        CB_TRY copy<T>(n, x, y, S(stream));                                                               \
+        CB_CATCH                                                                                          \
+    }                                                                                                     \
+    int cuddh_b200_scal_##SUF(int64_t n, T a, T * x, void * stream)                                       \
+    {                                                                                                     \
+        CB_TRY scal<T>(n, a, x, S(stream));                                                               \
+        CB_CATCH                                                                                          \
+    }                                                                                                     \
+    int cuddh_b200_fill_##SUF(int64_t n, T a, T * x, void * stream)                                       \
+    {                                                                                                     \
+        CB_TRY fill<T>(n, a, x, S(stream));                                                               \
+        CB_CATCH                                                                                          \
+    }
+CB_LINALG2(d, double, d)
+CB_LINALG2(f, float, f)
+int cuddh_b200_copy_i(int64_t n, const int * x, int * y, void * stream)
+{
+    CB_TRY copy<int>(n, x, y, S(stream));
+    CB_CATCH
+}
+int cuddh_b200_fill_i(int64_t n, int a, int * x, void * stream)
+{
+    CB_TRY fill<int>(n, a, x, S(stream));
+    CB_CATCH
+}
+
+// ---- gmres ----
+namespace
+{
+    struct PrecondSystem // source/gmres.cpp:68-89 PreconditionedSystem: y = P (A x)
+    {
+        cuddh_apply_d_fn A, P;
+        void *Actx, *Pctx;
+        double * q;
+        static void apply(void * self, const double * x, double * y)
+        {
+            auto * s = (PrecondSystem *)self;
+            s->A(s->Actx, x, s->q);
+            s->P(s->Pctx, s->q, y);
+        }
+    };
+
+    void fill_out(const GmresResult & r, cuddh_solver_out * out, double * res, double * time, int cap)
+    {
+        if (out) {
+            out->success = r.success ? 1 : 0;
+            out->num_iter = r.num_iter;
+            out->num_matvec = r.num_matvec;
+            out->n_res = (int)std::min<size_t>(r.res_norm.size(), (size_t)std::max(cap, 0));
+        }
+        const int n = (int)std::min<size_t>(r.res_norm.size(), (size_t)std::max(cap, 0));
+        for (int i = 0; i < n; ++i) {
+            if (res)
+                res[i] = r.res_norm[i];
+            if (time)
+                time[i] = r.time[i];
+        }
+    }
+} // namespace
+
+int cuddh_b200_gmres_d(int64_t n, double * x, cuddh_apply_d_fn A, void * A_ctx, const double * b, cuddh_apply_d_fn P, void * P_ctx,
+                       int m, int maxit, double tol, int verbose, double max_seconds, cuddh_solver_out * out, double * res,
+                       double * time, int cap, void * stream)
+{
+    CB_TRY
+    GmresResult r;
+    if (P) { // gmres.cpp:242-251: solve P A x = P b
+        DevBuf<double> q((size_t)n), r0((size_t)n);
+        PrecondSystem sys{A, P, A_ctx, P_ctx, q.p};
+        P(P_ctx, b, r0.p);
+        r = gmres<double>(n, x, &PrecondSystem::apply, &sys, r0.p, m, maxit, tol, verbose, max_seconds, S(stream));
+        CB_CUDA(cudaStreamSynchronize(S(stream)));
+    }
+    else
+        r = gmres<double>(n, x, A, A_ctx, b, m, maxit, tol, verbose, max_seconds, S(stream));
+    fill_out(r, out, res, time, cap);
+    CB_CATCH
+}
+
+int cuddh_b200_gmres_f(int64_t n, float * x, cuddh_apply_f_fn A, void * A_ctx, const float * b, int m, int maxit, float tol,
+                       int verbose, double max_seconds, cuddh_solver_out * out, double * res, double * time, int cap, void * stream)
+{
+    CB_TRY
+    GmresResult r = gmres<float>(n, x, A, A_ctx, b, m, maxit, tol, verbose, max_seconds, S(stream));
+    fill_out(r, out, res, time, cap);
+    CB_CATCH
+}
+
+void cuddh_b200_operator_as_apply(void * h, const double * x, double * y)
+{
+    cuddh_b200_operator_apply((cuddh_operator_t)h, 1.0, 0, x, y, nullptr);
+}
+void cuddh_b200_ddh_as_apply(void * h, const float * x, float * y)
+{
+    cuddh_b200_ddh_action((cuddh_ddh_t)h, x, y, nullptr);
+}
+
+// ---- DDH ----
+int cuddh_b200_ddh_create(double omega, const double * h_a, cuddh_h1space_t s, int nx, int ny, int block, cuddh_ddh_t * out)
+{
+    CB_TRY
+    *out = new cuddh_ddh_s{std::unique_ptr<DDH>(new DDH(omega, h_a, s->s.get(), nx, ny, block))};
+    CB_CATCH
+}
+int cuddh_b200_ddh_destroy(cuddh_ddh_t d)
+{
+    delete d;
+    return 0;
+}
+int64_t cuddh_b200_ddh_size(cuddh_ddh_t d) { return 2 * d->d->n_lambda; }
+int cuddh_b200_ddh_rhs(cuddh_ddh_t d, const double * f, float * b, void * stream)
+{
+    CB_TRY
+    d->d->rhs(f, b, S(stream));
+    CB_CATCH
+}
+int cuddh_b200_ddh_action(cuddh_ddh_t d, const float * x, float * y, void * stream)
+{
+    CB_TRY
+    d->d->action(x, y, S(stream));
+    CB_CATCH
+}
+int cuddh_b200_ddh_postprocess(cuddh_ddh_t d, const float * lambda, const double * f, double * u, void * stream)
+{
+    CB_TRY
+    d->d->postprocess(lambda, f, u, S(stream));
+    CB_CATCH
+}
+int cuddh_b200_ddh_info(cuddh_ddh_t d, int64_t * info, double * dt)
+{
+    CB_TRY
+    const DDH & D = *d->d;
+    info[0] = D.n_domains;
+    info[1] = D.n_shared;
+    info[2] = D.nt;
+    info[3] = D.mx_dof;
+    info[4] = D.mx_fdof;
+    info[5] = D.mx_elem;
+    info[6] = D.nb;
+    info[7] = D.block;
+    *dt = D.dt;
+    CB_CATCH
+}
+int cuddh_b200_ddh_get_array(cuddh_ddh_t d, const char * name, void * h_out, int64_t cap_bytes, int64_t * count)
+{
+    CB_TRY
+    d->d->get_array(name, h_out, cap_bytes, count);
+    CB_CATCH
+}
+double cuddh_b200_ddh_flops(cuddh_ddh_t d) { return d->d->flops(); }
+
+} // extern "C"

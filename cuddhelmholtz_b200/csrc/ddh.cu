@@ -1,0 +1,286 @@
+// DDH action kernel for sm_100a: per-subdomain WaveHoltz local solves + interface-trace update, FP32.
+//
+// Same linear map as the reference kernel ddh_action<NB,NEL> (source/DDH.cpp:111-321; inlined collocated
+// stiffness :60-109): 5 WaveHoltz filter iterations from zero, each integrating the damped wave equation
+// over one period with nt two-stage explicit steps, lumped mass / boundary mass, identical time tables.
+//
+// What changed relative to the reference kernel (all re-association-level in FP32):
+//   * structured addressing: a subdomain is an NEL x NEL block of elements, so its unique DOFs form an
+//     N1 x N1 grid (N1 = NEL*(NB-1)+1). The wave field lives on that grid in shared memory; a node thread
+//     reads its row / column directly — no s_I index loads (the reference does 2*NB shared index loads +
+//     2*NB dependent value loads per gradient).
+//   * the four D rows/columns a thread needs sit in registers (reference: 4*NB shared loads per stiffness).
+//   * assembly is atomic-free and ordered: every element-local node writes its divergence term once, the
+//     canonical copy of each DOF adds the <= 4 copies in a fixed order (reference: shared-memory float
+//     atomicAdd, run-to-run non-deterministic).
+//   * DOF state (p, q, u, v, forcing, 1/m, boundary mass) lives in registers of the canonical thread.
+//   * postprocess() assembles the partition-of-unity sum in a fixed order (reference: FP64 atomicAdd).
+//   * `update` slots that no subdomain writes (cross-point orphans) are zeroed explicitly.
+#include "ddh.hpp"
+#include "linalg.hpp"
+
+namespace cb200
+{
+    namespace
+    {
+        struct DDHArgs
+        {
+            const int * gid;
+            const int * bin;
+            const int * bout;
+            const float * a;
+            const float * m;
+            const float * pou;
+            const float * H;
+            const float * g;   // (3, NB, NB, NEL*NEL, dom)
+            const float * D;   // (NB, NB) column-major
+            const float * whf;
+            const float * cs;
+            const float * sn;
+            const double * x;  // forcing [F; G] (global, FP64) or null
+            double * contrib;  // postprocess contributions (2, nd, dom) or null
+            const float * lambda;
+            float * update;
+            int64_t g_ndof, n_lambda;
+            int nt;
+            float omega, dt;
+        };
+
+        template <int NB, int NEL>
+        __global__ void __launch_bounds__(NB * NB * NEL * NEL)
+        ddh_kernel(const DDHArgs A)
+        {
+            constexpr int MX = NB * NB * NEL * NEL;
+            constexpr int N1 = NEL * (NB - 1) + 1;
+            constexpr int ND = N1 * N1;
+            constexpr int WH_MAXIT = 5; // source/DDH.cpp:136
+
+            __shared__ float s_p[ND];
+            __shared__ float s_fx[MX];
+            __shared__ float s_fy[MX];
+            __shared__ float s_su[MX];
+
+            const int tid = threadIdx.x;
+            const int dom = blockIdx.x;
+            const int k = tid % NB;
+            const int l = (tid / NB) % NB;
+            const int el = tid / (NB * NB);
+            const int ex = el % NEL, ey = el / NEL;
+            const int X = ex * (NB - 1) + k, Y = ey * (NB - 1) + l;
+            const int at = Y * N1 + X;
+            const int row0 = Y * N1 + ex * (NB - 1);        // first node of this thread's element row
+            const int col0 = ey * (NB - 1) * N1 + X;        // first node of this thread's element column
+            const int ebase = el * NB * NB;
+
+            // canonical copy of a shared node: k == 0 / l == 0 side of the right / upper element
+            const bool canon = (k < NB - 1 || ex == NEL - 1) && (l < NB - 1 || ey == NEL - 1);
+            const bool hasL = canon && (k == 0) && (ex > 0);
+            const bool hasB = canon && (l == 0) && (ey > 0);
+            const int cpL = (NB - 1) + NB * (l + NB * (el - 1));
+            const int cpB = k + NB * ((NB - 1) + NB * (el - NEL));
+            const int cpD = (NB - 1) + NB * ((NB - 1) + NB * (el - NEL - 1));
+
+            float Dk[NB], Dl[NB], DTk[NB], DTl[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                Dk[i] = __ldg(A.D + k + NB * i);
+                Dl[i] = __ldg(A.D + l + NB * i);
+                DTk[i] = __ldg(A.D + i + NB * k);
+                DTl[i] = __ldg(A.D + i + NB * l);
+            }
+            const float * gp = A.g + 3 * ((size_t)tid + (size_t)MX * dom);
+            const float gx = __ldg(gp), gy = __ldg(gp + 1), gz = __ldg(gp + 2);
+
+            const float half_dt = 0.5f * A.dt;
+            const float dt = A.dt;
+
+            float ai = 1.0f, inv_mi = 0.0f, Hi = 0.0f, F = 0.0f, G = 0.0f;
+            float u = 0.0f, v = 0.0f, p = 0.0f, q = 0.0f, lambda = 0.0f, mu = 0.0f;
+            int gi = 0;
+            const size_t o = (size_t)at + (size_t)ND * dom;
+            if (canon) {
+                gi = __ldg(A.gid + o);
+                ai = __ldg(A.a + o);
+                const float mi = __ldg(A.m + o);
+                inv_mi = 1.0f / (ai * ai * mi);
+                if (A.x) {
+                    F = (float)A.x[gi];
+                    G = (float)A.x[A.g_ndof + gi];
+                }
+                Hi = __ldg(A.H + o);
+                if (A.lambda) {
+                    const int idx = __ldg(A.bin + o);
+                    if (idx >= 0) {
+                        lambda = A.lambda[idx];
+                        mu = A.lambda[A.n_lambda + idx];
+                        F += Hi * lambda;
+                        G += Hi * mu;
+                    }
+                }
+                Hi *= ai;
+            }
+
+            // z = S * w for the field w held by the canonical threads (value `w` of this thread)
+            auto stiffness = [&](const float w) -> float {
+                if (canon)
+                    s_p[at] = w;
+                __syncthreads();
+                float Ux = 0.0f, Uy = 0.0f;
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    Ux = fmaf(Dk[i], s_p[row0 + i], Ux);
+                    Uy = fmaf(Dl[i], s_p[col0 + i * N1], Uy);
+                }
+                s_fx[tid] = gx * Ux + gy * Uy;
+                s_fy[tid] = gy * Ux + gz * Uy;
+                __syncthreads();
+                float Su = 0.0f;
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    Su = fmaf(DTk[i], s_fx[ebase + i + NB * l], Su);
+                    Su = fmaf(DTl[i], s_fy[ebase + k + NB * i], Su);
+                }
+                s_su[tid] = Su;
+                __syncthreads();
+                float z = Su;
+                if (hasL)
+                    z += s_su[cpL];
+                if (hasB)
+                    z += s_su[cpB];
+                if (hasL && hasB)
+                    z += s_su[cpD];
+                return z;
+            };
+
+            for (int whit = 0; whit < WH_MAXIT; ++whit) {
+                float dK = __ldg(A.whf);
+                p = u;
+                q = v;
+                u *= dK;
+                v *= dK;
+                for (int it = 1; it <= A.nt; ++it) {
+                    float z = stiffness(p) - Hi * q;
+                    float dq = z + __ldg(A.cs + 2 * it - 2) * F;
+                    dq += __ldg(A.sn + 2 * it - 2) * G;
+                    dq *= inv_mi;
+                    const float ph = p - half_dt * q;
+                    const float qh = q + half_dt * dq;
+                    p -= dt * qh;
+
+                    z = stiffness(ph) - Hi * qh;
+                    dq = z + __ldg(A.cs + 2 * it - 1) * F;
+                    dq += __ldg(A.sn + 2 * it - 1) * G;
+                    dq *= inv_mi;
+                    q += dt * dq;
+
+                    dK = __ldg(A.whf + it);
+                    u += dK * p;
+                    v += dK * q;
+                }
+            }
+
+            v *= (1.0f / A.omega);
+
+            if (canon) {
+                if (A.contrib) { // partition of unity weight M = m * g_inv_m (:298-307), ordered sum done afterwards
+                    const float M = __ldg(A.pou + o);
+                    A.contrib[2 * o] = (double)(M * u);
+                    A.contrib[2 * o + 1] = (double)(M * v);
+                }
+                if (A.update) {
+                    const int idx = __ldg(A.bout + o);
+                    if (idx >= 0) {
+                        const float S = 2.0f * ai * A.omega;
+                        A.update[idx] = -lambda - S * v;
+                        A.update[A.n_lambda + idx] = -mu + S * u;
+                    }
+                }
+            }
+        }
+
+        __global__ void pou_gather_kernel(const int64_t g_ndof, const int * __restrict__ ptr, const int * __restrict__ src,
+                                          const double * __restrict__ contrib, double * __restrict__ y)
+        {
+            const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+            if (i >= g_ndof)
+                return;
+            double su = 0.0, sv = 0.0;
+            for (int t = ptr[i]; t < ptr[i + 1]; ++t) {
+                const size_t o = (size_t)src[t];
+                su += contrib[2 * o];
+                sv += contrib[2 * o + 1];
+            }
+            y[i] = su;
+            y[g_ndof + i] = sv;
+        }
+    } // namespace
+
+    void DDH::run(const double * x, double * y, const float * lambda, float * update, cudaStream_t s)
+    {
+        ensure_device();
+        DDHArgs A;
+        A.gid = d_gid.p;
+        A.bin = d_bin.p;
+        A.bout = d_bout.p;
+        A.a = d_a.p;
+        A.m = d_m.p;
+        A.pou = d_pou.p;
+        A.H = d_H.p;
+        A.g = d_g.p;
+        A.D = d_D.p;
+        A.whf = d_whf.p;
+        A.cs = d_cs.p;
+        A.sn = d_sn.p;
+        A.x = x;
+        A.contrib = nullptr;
+        A.lambda = lambda;
+        A.update = update;
+        A.g_ndof = g_ndof;
+        A.n_lambda = n_lambda;
+        A.nt = nt;
+        A.omega = (float)omega;
+        A.dt = (float)dt;
+        if (y) {
+            if (!d_contrib.p)
+                d_contrib.alloc(2 * (size_t)n1 * n1 * n_domains);
+            A.contrib = d_contrib.p;
+        }
+        if (update)
+            CB_CUDA(cudaMemsetAsync(update, 0, sizeof(float) * 2 * (size_t)n_lambda, s));
+
+        const int threads = block * block;
+        if (nb == 4 && block == 16)
+            ddh_kernel<4, 4><<<n_domains, threads, 0, s>>>(A);
+        else if (nb == 8 && block == 16)
+            ddh_kernel<8, 2><<<n_domains, threads, 0, s>>>(A);
+        else if (nb == 4 && block == 32)
+            ddh_kernel<4, 8><<<n_domains, threads, 0, s>>>(A);
+        else if (nb == 8 && block == 32)
+            ddh_kernel<8, 4><<<n_domains, threads, 0, s>>>(A);
+        else
+            throw Error(-1, "DDH::action only supports n_basis == 4 or 8.");
+        CB_LAUNCHED();
+
+        if (y) {
+            pou_gather_kernel<<<(unsigned)((g_ndof + 255) / 256), 256, 0, s>>>(g_ndof, d_asm_ptr.p, d_asm_src.p, d_contrib.p, y);
+            CB_LAUNCHED();
+        }
+    }
+
+    void DDH::action(const float * x, float * y, cudaStream_t s)
+    {
+        // source/DDH.cpp:611-639: update = T(lambda); out = lambda - update
+        run(nullptr, nullptr, x, y, s);
+        axpby<float>(2 * n_lambda, 1.0f, x, -1.0f, y, s);
+    }
+
+    void DDH::rhs(const double * f, float * b, cudaStream_t s)
+    {
+        run(f, nullptr, nullptr, b, s); // :641-667
+    }
+
+    void DDH::postprocess(const float * lambda, const double * f, double * u, cudaStream_t s)
+    {
+        run(f, u, lambda, nullptr, s); // :669-695
+    }
+} // namespace cb200

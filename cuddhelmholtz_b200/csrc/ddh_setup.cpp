@@ -1,0 +1,456 @@
+// Host-side setup of the DDH operator: subdomain maps (EnsembleSpace semantics) and the DDH constructor's
+// index / coefficient tables, then their re-expression in the structured per-subdomain grid layout the
+// sm_100a kernel uses. Compile without FP contraction (-ffp-contract=off).
+//
+// Reference: source/EnsembleSpace.cpp:11-287, source/DDH.cpp:323-609.
+#include "ddh.hpp"
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <unordered_set>
+
+namespace cb200
+{
+    // ---------------------------------------------------------------------------------------------
+    // Ensemble: same first-touch numbering rules as the reference, with flat scratch arrays instead of
+    // per-subdomain hash maps (O(total size), works at 262 144 subdomains).
+    // ---------------------------------------------------------------------------------------------
+    Ensemble::Ensemble(const H1Space & fem, int n_spaces_, const int * labels) : n_spaces(n_spaces_), nb(fem.nb)
+    {
+        const Mesh & mesh = *fem.mesh;
+        const int64_t nel = mesh.n_elem;
+        const int nb2 = nb * nb;
+
+        // elements of each subspace in global element order (:28-71)
+        s_elems.assign(n_spaces, 0);
+        std::vector<int> el2s((size_t)nel);
+        for (int64_t el = 0; el < nel; ++el) {
+            const int p = labels[el];
+            CB_REQUIRE(p >= 0 && p < n_spaces, "EnsembleSpace error: an element was illogically labeled.");
+            el2s[el] = s_elems[p]++;
+        }
+        mx_elems = *std::max_element(s_elems.begin(), s_elems.end());
+        CB_REQUIRE(*std::min_element(s_elems.begin(), s_elems.end()) >= 1, "EnsembleSpace error: atleast one space is empty");
+        elems.assign((size_t)mx_elems * n_spaces, -1);
+        for (int64_t el = 0; el < nel; ++el)
+            elems[(size_t)el2s[el] + (size_t)mx_elems * labels[el]] = (int)el;
+
+        // boundary faces of each subspace in global edge order, tagged with the side (:74-107)
+        s_faces.assign(n_spaces, 0);
+        struct SharedFace { int S0, S1, l0, l1; };
+        std::vector<SharedFace> shared_faces;
+        std::vector<std::array<int, 3>> flist; // (subspace, edge, side) in discovery order
+        for (int64_t e = 0; e < mesh.n_edges; ++e) {
+            const int * rec = &mesh.edges[8 * (size_t)e];
+            const int S0 = labels[rec[2]];
+            if (rec[7]) {
+                flist.push_back({S0, (int)e, 0});
+                s_faces[S0]++;
+            }
+            else {
+                const int S1 = labels[rec[3]];
+                if (S0 != S1) {
+                    flist.push_back({S0, (int)e, 0});
+                    flist.push_back({S1, (int)e, 1});
+                    shared_faces.push_back({S0, S1, s_faces[S0], s_faces[S1]});
+                    s_faces[S0]++;
+                    s_faces[S1]++;
+                }
+            }
+        }
+        mx_faces = *std::max_element(s_faces.begin(), s_faces.end());
+        faces.assign((size_t)mx_faces * n_spaces, -1);
+        face_side.assign((size_t)mx_faces * n_spaces, -1);
+        {
+            std::vector<int> cur(n_spaces, 0);
+            for (auto & f : flist) {
+                const size_t at = (size_t)cur[f[0]]++ + (size_t)mx_faces * f[0];
+                faces[at] = f[1];
+                face_side[at] = f[2];
+            }
+        }
+
+        // subspace DOF numbering: first touch over (el, j, i) (:142-175)
+        sI.assign((size_t)nb2 * mx_elems * n_spaces, -1);
+        s_dof.assign(n_spaces, 0);
+        std::vector<int> local((size_t)fem.ndof, -1);
+        std::vector<std::vector<int>> s2g(n_spaces);
+        for (int p = 0; p < n_spaces; ++p) {
+            auto & lst = s2g[p];
+            for (int el = 0; el < s_elems[p]; ++el) {
+                const int g_el = elems[(size_t)el + (size_t)mx_elems * p];
+                const int * Ie = &fem.I[(size_t)nb2 * g_el];
+                int * sIe = &sI[(size_t)nb2 * (el + (size_t)mx_elems * p)];
+                for (int t = 0; t < nb2; ++t) {
+                    const int g = Ie[t];
+                    if (local[g] < 0) {
+                        local[g] = (int)lst.size();
+                        lst.push_back(g);
+                    }
+                    sIe[t] = local[g];
+                }
+            }
+            s_dof[p] = (int)lst.size();
+            for (int g : lst)
+                local[g] = -1;
+        }
+        mx_ndof = *std::max_element(s_dof.begin(), s_dof.end());
+        gI.assign((size_t)mx_ndof * n_spaces, -1);
+        for (int p = 0; p < n_spaces; ++p)
+            std::copy(s2g[p].begin(), s2g[p].end(), gI.begin() + (size_t)mx_ndof * p);
+
+        // face-space numbering: first touch over (face, i), reversed on side 1 of a flipped edge (:193-234)
+        fI.assign((size_t)nb * mx_faces * n_spaces, -1);
+        s_fdof.assign(n_spaces, 0);
+        std::vector<std::vector<int>> f2s(n_spaces);
+        {
+            std::vector<int> flocal((size_t)mx_ndof, -1);
+            for (int p = 0; p < n_spaces; ++p) {
+                auto & lst = f2s[p];
+                for (int f = 0; f < s_faces[p]; ++f) {
+                    const size_t at = (size_t)f + (size_t)mx_faces * p;
+                    const int * rec = &mesh.edges[8 * (size_t)faces[at]];
+                    const int side = face_side[at];
+                    const int g_el = rec[2 + side];
+                    const int s = rec[4 + side];
+                    const bool reversed = (side == 1 && rec[6] < 0);
+                    const int el = el2s[g_el];
+                    for (int i = 0; i < nb; ++i) {
+                        const int j = reversed ? (nb - 1 - i) : i;
+                        const int mm = (s == 0 || s == 2) ? j : (s == 1 ? nb - 1 : 0);
+                        const int nn = (s == 1 || s == 3) ? j : (s == 2 ? nb - 1 : 0);
+                        const int idx = sI[(size_t)mm + nb * (nn + (size_t)nb * (el + (size_t)mx_elems * p))];
+                        if (flocal[idx] < 0) {
+                            flocal[idx] = (int)lst.size();
+                            lst.push_back(idx);
+                        }
+                        fI[(size_t)i + nb * (f + (size_t)mx_faces * p)] = flocal[idx];
+                    }
+                }
+                s_fdof[p] = (int)lst.size();
+                for (int idx : lst)
+                    flocal[idx] = -1;
+            }
+        }
+        mx_fdof = *std::max_element(s_fdof.begin(), s_fdof.end());
+        pI.assign((size_t)mx_fdof * n_spaces, -1);
+        for (int p = 0; p < n_spaces; ++p)
+            std::copy(f2s[p].begin(), f2s[p].end(), pI.begin() + (size_t)mx_fdof * p);
+
+        // connectivity map: one entry per unique shared face DOF per subspace pair (:254-286); 64-bit keys
+        std::unordered_set<uint64_t> seen;
+        seen.reserve(shared_faces.size() * (size_t)nb * 2);
+        for (auto & sf : shared_faces) {
+            const uint64_t lo = (uint64_t)std::min(sf.S0, sf.S1), hi = (uint64_t)std::max(sf.S0, sf.S1);
+            const uint64_t pair_key = lo + (uint64_t)n_spaces * hi;
+            for (int i = 0; i < nb; ++i) {
+                const int j0 = fI[(size_t)i + nb * (sf.l0 + (size_t)mx_faces * sf.S0)];
+                const int j1 = fI[(size_t)i + nb * (sf.l1 + (size_t)mx_faces * sf.S1)];
+                const uint64_t lkey = (uint64_t)((sf.S0 < sf.S1) ? j0 : j1);
+                if (seen.insert(pair_key * (uint64_t)(mx_fdof + 1) + lkey).second) {
+                    const int rec[4] = {sf.S0, sf.S1, j0, j1};
+                    cmap.insert(cmap.end(), rec, rec + 4);
+                }
+            }
+        }
+        n_shared = (int64_t)cmap.size() / 4;
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // DDH constructor
+    // ---------------------------------------------------------------------------------------------
+    DDH::DDH(double omega_, const double * h_a, H1Space * fem_, int nx, int ny, int block_)
+        : fem(fem_), nb(fem_->nb), block(block_), g_ndof(fem_->ndof), omega(omega_)
+    {
+        const Mesh & mesh = *fem->mesh;
+        CB_REQUIRE(nb == 4 || nb == 8, "DDH error: Only n_basis==4, and n_basis==8 supported.");
+        CB_REQUIRE(block == 16 || block == 32, "DDH error: subdomain block size must be 16 or 32.");
+        CB_REQUIRE((int64_t)nx * ny == mesh.n_elem, "DDH error: nx*ny does not match the mesh (Mesh2D::uniform_rect required).");
+        nel1 = block / nb;
+        n1 = nel1 * (nb - 1) + 1;
+        CB_REQUIRE(nx % nel1 == 0 && ny % nel1 == 0, "Only nx x ny meshes with nx and ny multiples of 32 / n_basis allowed.");
+        const int ndx = nx / nel1, ndy = ny / nel1;
+        n_domains = ndx * ndy;
+
+        std::vector<int> labels((size_t)nx * ny);
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i)
+                labels[(size_t)i + (size_t)nx * j] = (i / nel1) + ndx * (j / nel1);
+        en.reset(new Ensemble(*fem, n_domains, labels.data()));
+        const Ensemble & E = *en;
+
+        // WaveHoltz time grid and filter (:363-386)
+        const double T = (2 * M_PI) / omega;
+        const double h = mesh.min_h;
+        dt = 0.2 * 0.5 * h / (nb * nb);
+        nt = (int)std::ceil(T / dt);
+        dt = T / nt;
+        wh_filter.resize((size_t)nt + 1);
+        for (int k = 0; k <= nt; ++k)
+            wh_filter[k] = (float)(dt * (omega / M_PI) * (std::cos(omega * k * dt) - 0.25));
+        wh_filter[0] *= 0.5;
+        wh_filter[nt] *= 0.5;
+        cs.resize(2 * (size_t)nt + 1);
+        sn.resize(2 * (size_t)nt + 1);
+        for (int k = 0; k <= 2 * nt; ++k) {
+            const double t = 0.5 * k * dt;
+            cs[k] = (float)(-std::cos(omega * t));
+            sn[k] = (float)(std::sin(omega * t));
+        }
+
+        mx_dof = E.mx_ndof;
+        mx_fdof = E.mx_fdof;
+        mx_elem = E.mx_elems;
+        n_shared = E.n_shared;
+        n_lambda = 2 * n_shared;
+        CB_REQUIRE(mx_elem == nel1 * nel1 && mx_dof == n1 * n1, "DDH error: subdomains are not uniform blocks (Mesh2D::uniform_rect required).");
+
+        // lambda index map; later cmap entries overwrite earlier ones at cross points (:425-440)
+        B.assign((size_t)mx_fdof * 2 * n_domains, -1);
+        for (int64_t k = 0; k < n_shared; ++k) {
+            const int S0 = E.cmap[4 * k], S1 = E.cmap[4 * k + 1], j0 = E.cmap[4 * k + 2], j1 = E.cmap[4 * k + 3];
+            B[(size_t)j0 + (size_t)mx_fdof * (0 + 2 * (size_t)S0)] = (int)k;
+            B[(size_t)j0 + (size_t)mx_fdof * (1 + 2 * (size_t)S0)] = (int)(n_shared + k);
+            B[(size_t)j1 + (size_t)mx_fdof * (0 + 2 * (size_t)S1)] = (int)(n_shared + k);
+            B[(size_t)j1 + (size_t)mx_fdof * (1 + 2 * (size_t)S1)] = (int)k;
+        }
+
+        // permutation: face DOFs first (face-space order), then the rest in subspace order (:443-510)
+        const int nb2 = nb * nb;
+        gI.assign((size_t)mx_dof * n_domains, 0);
+        sI.assign((size_t)nb2 * mx_elem * n_domains, 0);
+        {
+            std::vector<int> perm(mx_dof), inv(mx_dof);
+            std::vector<char> isface(mx_dof);
+            for (int p = 0; p < n_domains; ++p) {
+                const int ndof = E.s_dof[p], fdof = E.s_fdof[p];
+                std::fill(isface.begin(), isface.end(), 0);
+                int l = 0;
+                for (; l < fdof; ++l) {
+                    const int j = E.pI[(size_t)l + (size_t)mx_fdof * p];
+                    isface[j] = 1;
+                    perm[l] = j;
+                }
+                for (int i = 0; i < ndof; ++i)
+                    if (!isface[i])
+                        perm[l++] = i;
+                for (int i = 0; i < ndof; ++i)
+                    inv[perm[i]] = i;
+                for (int i = 0; i < ndof; ++i)
+                    gI[(size_t)i + (size_t)mx_dof * p] = E.gI[(size_t)perm[i] + (size_t)mx_dof * p];
+                for (int el = 0; el < E.s_elems[p]; ++el)
+                    for (int t = 0; t < nb2; ++t) {
+                        const size_t at = (size_t)t + (size_t)nb2 * (el + (size_t)mx_elem * p);
+                        sI[at] = inv[E.sI[at]];
+                    }
+            }
+        }
+
+        // 1-D derivative matrix at the GLL nodes, FP32 (:523-528)
+        {
+            std::vector<double> Dd((size_t)nb2);
+            fem->basis->deriv(nb, fem->basis->x.data(), Dd.data());
+            D.resize(nb2);
+            for (int i = 0; i < nb2; ++i)
+                D[i] = (float)Dd[i];
+        }
+
+        // metrics at GLL nodes: Jacobian (source/Element.cpp:21-27), det; geometric factors (:31-58) in FP32
+        const double * q = fem->basis->x.data();
+        const double * qw = fem->basis->w.data();
+        const int64_t g_elem = mesh.n_elem;
+        std::vector<double> detJ((size_t)nb2 * g_elem);
+        g.assign((size_t)3 * nb2 * mx_elem * n_domains, 0.0f);
+        std::vector<float> g_elem3((size_t)3 * nb2 * g_elem);
+        for (int64_t el = 0; el < g_elem; ++el) {
+            double c[8];
+            mesh.corners(el, c);
+            for (int j = 0; j < nb; ++j)
+                for (int i = 0; i < nb; ++i) {
+                    const double xi0 = q[i], xi1 = q[j];
+                    const double X_xi = 0.25 * ((1.0 - xi1) * (c[2] - c[0]) + (1.0 + xi1) * (c[4] - c[6]));
+                    const double Y_xi = 0.25 * ((1.0 - xi1) * (c[3] - c[1]) + (1.0 + xi1) * (c[5] - c[7]));
+                    const double X_eta = 0.25 * ((1.0 - xi0) * (c[6] - c[0]) + (1.0 + xi0) * (c[4] - c[2]));
+                    const double Y_eta = 0.25 * ((1.0 - xi0) * (c[7] - c[1]) + (1.0 + xi0) * (c[5] - c[3]));
+                    const double det = X_xi * Y_eta - Y_xi * X_eta;
+                    const size_t at = (size_t)i + nb * (j + (size_t)nb * el);
+                    detJ[at] = det;
+                    const double W = qw[i] * qw[j];
+                    g_elem3[3 * at + 0] = (float)(W * (Y_eta * Y_eta + X_eta * X_eta) / det);
+                    g_elem3[3 * at + 1] = (float)(-W * (Y_xi * Y_eta + X_xi * X_eta) / det);
+                    g_elem3[3 * at + 2] = (float)(W * (Y_xi * Y_xi + X_xi * X_xi) / det);
+                }
+        }
+        for (int p = 0; p < n_domains; ++p)
+            for (int el = 0; el < E.s_elems[p]; ++el) {
+                const int g_el = E.elems[(size_t)el + (size_t)mx_elem * p];
+                std::memcpy(&g[3 * (size_t)nb2 * (el + (size_t)mx_elem * p)], &g_elem3[3 * (size_t)nb2 * g_el], sizeof(float) * 3 * nb2);
+            }
+
+        // global inverse lumped mass (:556-565)
+        std::vector<double> mi((size_t)g_ndof, 0.0);
+        for (int64_t el = 0; el < g_elem; ++el)
+            for (int j = 0; j < nb; ++j)
+                for (int i = 0; i < nb; ++i) {
+                    const size_t at = (size_t)i + nb * (j + (size_t)nb * el);
+                    mi[fem->I[at]] += qw[i] * qw[j] * detJ[at];
+                }
+        for (int64_t i = 0; i < g_ndof; ++i)
+            mi[i] = 1.0 / mi[i];
+
+        // per-subdomain lumped mass, boundary mass, coefficient, global inverse mass (:567-608); FP32 storage,
+        // each "+=" rounds to float as in the reference's float arrays
+        m.assign((size_t)mx_dof * n_domains, 0.0f);
+        H.assign((size_t)mx_fdof * n_domains, 0.0f);
+        a.assign((size_t)mx_dof * n_domains, 0.0f);
+        gmi.assign((size_t)mx_dof * n_domains, 0.0f);
+        for (int p = 0; p < n_domains; ++p) {
+            for (int el = 0; el < E.s_elems[p]; ++el) {
+                const int g_el = E.elems[(size_t)el + (size_t)mx_elem * p];
+                for (int j = 0; j < nb; ++j)
+                    for (int i = 0; i < nb; ++i) {
+                        const int l = sI[(size_t)i + nb * (j + (size_t)nb * (el + (size_t)mx_elem * p))];
+                        float & ml = m[(size_t)l + (size_t)mx_dof * p];
+                        ml = (float)((double)ml + qw[i] * qw[j] * detJ[(size_t)i + nb * (j + (size_t)nb * g_el)]);
+                    }
+            }
+            for (int i = 0; i < E.s_dof[p]; ++i) {
+                const int gi = gI[(size_t)i + (size_t)mx_dof * p];
+                a[(size_t)i + (size_t)mx_dof * p] = (float)h_a[gi];
+                gmi[(size_t)i + (size_t)mx_dof * p] = (float)mi[gi];
+            }
+            for (int f = 0; f < E.s_faces[p]; ++f) {
+                const double ds = mesh.edge_meas[E.faces[(size_t)f + (size_t)E.mx_faces * p]];
+                for (int i = 0; i < nb; ++i) {
+                    const int l = E.fI[(size_t)i + nb * (f + (size_t)E.mx_faces * p)];
+                    float & Hl = H[(size_t)l + (size_t)mx_fdof * p];
+                    Hl = (float)((double)Hl + ds * qw[i]);
+                }
+            }
+        }
+
+        // -----------------------------------------------------------------------------------------
+        // grid layout for the kernel: unique DOF (X, Y) of subdomain p at p*n1*n1 + Y*n1 + X, where the
+        // element-local node (k, l) of local element (ex, ey) sits at X = ex*(nb-1)+k, Y = ey*(nb-1)+l.
+        // The tables below are the reference-order arrays above seen through that map, so the operator is
+        // the same linear map (including the cross-point quirks of B).
+        // -----------------------------------------------------------------------------------------
+        const int nd = n1 * n1;
+        std::vector<int> h_gid((size_t)nd * n_domains, -1), h_bin((size_t)nd * n_domains, -1), h_bout((size_t)nd * n_domains, -1);
+        std::vector<float> h_a2((size_t)nd * n_domains, 1.0f), h_m((size_t)nd * n_domains, 1.0f), h_pou((size_t)nd * n_domains, 0.0f),
+            h_H((size_t)nd * n_domains, 0.0f);
+        std::vector<int> dof_of_grid(nd);
+        for (int p = 0; p < n_domains; ++p) {
+            std::fill(dof_of_grid.begin(), dof_of_grid.end(), -1);
+            CB_REQUIRE(E.s_elems[p] == mx_elem && E.s_dof[p] == nd, "DDH error: non-uniform subdomain (Mesh2D::uniform_rect required).");
+            for (int el = 0; el < mx_elem; ++el) {
+                const int ex = el % nel1, ey = el / nel1;
+                for (int l = 0; l < nb; ++l)
+                    for (int k = 0; k < nb; ++k) {
+                        const int d = sI[(size_t)k + nb * (l + (size_t)nb * (el + (size_t)mx_elem * p))];
+                        const int at = (ey * (nb - 1) + l) * n1 + ex * (nb - 1) + k;
+                        CB_REQUIRE(dof_of_grid[at] < 0 || dof_of_grid[at] == d, "DDH error: subdomain is not a structured block (Mesh2D::uniform_rect required).");
+                        dof_of_grid[at] = d;
+                    }
+            }
+            for (int at = 0; at < nd; ++at) {
+                const int d = dof_of_grid[at];
+                const size_t o = (size_t)at + (size_t)nd * p;
+                h_gid[o] = gI[(size_t)d + (size_t)mx_dof * p];
+                h_a2[o] = a[(size_t)d + (size_t)mx_dof * p];
+                h_m[o] = m[(size_t)d + (size_t)mx_dof * p];
+                h_pou[o] = m[(size_t)d + (size_t)mx_dof * p] * gmi[(size_t)d + (size_t)mx_dof * p]; // M = mi * g_inv_m (:300)
+                if (d < E.s_fdof[p]) {
+                    h_H[o] = H[(size_t)d + (size_t)mx_fdof * p];
+                    h_bin[o] = B[(size_t)d + (size_t)mx_fdof * (0 + 2 * (size_t)p)];
+                    h_bout[o] = B[(size_t)d + (size_t)mx_fdof * (1 + 2 * (size_t)p)];
+                }
+            }
+        }
+        hg_gid = std::move(h_gid);
+        hg_bin = std::move(h_bin);
+        hg_bout = std::move(h_bout);
+        hg_a = std::move(h_a2);
+        hg_m = std::move(h_m);
+        hg_pou = std::move(h_pou);
+        hg_H = std::move(h_H);
+
+        // transposed map for the ordered partition-of-unity sum in postprocess(): global DOF -> slots (p*nd+at)
+        {
+            std::vector<int> ptr((size_t)g_ndof + 1, 0), src(hg_gid.size());
+            const std::vector<int> & h_gid = hg_gid;
+            for (size_t t = 0; t < h_gid.size(); ++t)
+                ptr[h_gid[t] + 1]++;
+            for (int64_t i = 0; i < g_ndof; ++i)
+                ptr[i + 1] += ptr[i];
+            std::vector<int> cur(ptr.begin(), ptr.end() - 1);
+            for (size_t t = 0; t < h_gid.size(); ++t)
+                src[cur[h_gid[t]]++] = (int)t;
+            h_asm_ptr = std::move(ptr);
+            h_asm_src = std::move(src);
+        }
+    }
+
+    void DDH::ensure_device()
+    {
+        if (on_device)
+            return;
+        d_gid.upload(hg_gid);
+        d_bin.upload(hg_bin);
+        d_bout.upload(hg_bout);
+        d_a.upload(hg_a);
+        d_m.upload(hg_m);
+        d_pou.upload(hg_pou);
+        d_H.upload(hg_H);
+        d_g.upload(g);
+        d_D.upload(D);
+        d_whf.upload(wh_filter);
+        d_cs.upload(cs);
+        d_sn.upload(sn);
+        d_asm_ptr.upload(h_asm_ptr);
+        d_asm_src.upload(h_asm_src);
+        on_device = true;
+    }
+
+    void DDH::get_array(const char * name, void * out, int64_t cap_bytes, int64_t * count) const
+    {
+        const void * src = nullptr;
+        size_t bytes = 0, cnt = 0;
+        auto pick_i = [&](const std::vector<int> & v) { src = v.data(); cnt = v.size(); bytes = cnt * sizeof(int); };
+        auto pick_f = [&](const std::vector<float> & v) { src = v.data(); cnt = v.size(); bytes = cnt * sizeof(float); };
+        const std::string n(name);
+        if (n == "B") pick_i(B);
+        else if (n == "gI") pick_i(gI);
+        else if (n == "sI") pick_i(sI);
+        else if (n == "cmap") pick_i(en->cmap);
+        else if (n == "ens_gI") pick_i(en->gI);
+        else if (n == "ens_sI") pick_i(en->sI);
+        else if (n == "ens_fI") pick_i(en->fI);
+        else if (n == "ens_pI") pick_i(en->pI);
+        else if (n == "ens_faces") pick_i(en->faces);
+        else if (n == "ens_elems") pick_i(en->elems);
+        else if (n == "m") pick_f(m);
+        else if (n == "gmi") pick_f(gmi);
+        else if (n == "a") pick_f(a);
+        else if (n == "H") pick_f(H);
+        else if (n == "D") pick_f(D);
+        else if (n == "g") pick_f(g);
+        else if (n == "wh_filter") pick_f(wh_filter);
+        else if (n == "cs") pick_f(cs);
+        else if (n == "sn") pick_f(sn);
+        else throw Error(-1, "ddh_get_array: unknown array name " + n);
+        if (count)
+            *count = (int64_t)cnt;
+        if (out) {
+            CB_REQUIRE((int64_t)bytes <= cap_bytes, "ddh_get_array: output buffer too small");
+            std::memcpy(out, src, bytes);
+        }
+    }
+
+    double DDH::flops() const
+    {
+        // n_domains * 5 * nt * N_threads * (2(8 nb + 7) + 26)
+        return (double)n_domains * 5.0 * nt * (double)(block * block) * (2.0 * (8.0 * nb + 7.0) + 26.0);
+    }
+} // namespace cb200

@@ -1,0 +1,399 @@
+// H1 space (global-to-local map + nodal coordinates), face space, and the CTA assembly plan.
+//
+// Numbering semantics = reference source/H1Space.cpp:11-127: a node shared between elements belongs to
+// the lowest-numbered element touching it (edge->elements[0] / connected_elements[0]); global ids are
+// handed out in increasing volume index v = i + nb*(j + nb*el) over the owned nodes. That is exactly a
+// first-touch scan, which is how it is computed here (flat per-vertex / per-edge id tables, no hash maps).
+// Nodal coordinates: bilinear map of the GLL tensor nodes (source/Element.cpp:5-19), last writer wins
+// in element order, as in the reference loop (:108-126).
+//
+// Compile without FP contraction (-ffp-contract=off) so xy is bit-identical to the reference's host pass.
+#include "common.hpp"
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+namespace cb200
+{
+    H1Space::H1Space(const Mesh * mesh_, int nb_) : mesh(mesh_), basis(new Basis(nb_)), nb(nb_), n_elem(mesh_->n_elem)
+    {
+        CB_REQUIRE(nb >= 2, "H1Space: n_basis must be >= 2");
+        const int64_t nel = n_elem;
+        const int ne_int = nb - 2;
+        CB_REQUIRE((double)nel * nb * nb < 2.0e9, "H1Space: n_elem * n_basis^2 exceeds 32-bit DOF ids");
+        I.assign((size_t)nb * nb * nel, -1);
+        std::vector<int> vertex_id((size_t)mesh->n_nodes, -1);
+        std::vector<int> edge_id((size_t)mesh->n_edges * (size_t)std::max(ne_int, 0), -1);
+        const int * elems = mesh->elems.data();
+        const int * edges = mesh->edges.data();
+        const int * eledge = mesh->elem_edges.data();
+
+        int next = 0;
+        for (int64_t el = 0; el < nel; ++el) {
+            int * Ie = &I[(size_t)nb * nb * el];
+            for (int j = 0; j < nb; ++j) {
+                const bool jlo = (j == 0), jhi = (j == nb - 1);
+                for (int i = 0; i < nb; ++i) {
+                    const bool ilo = (i == 0), ihi = (i == nb - 1);
+                    int id;
+                    if ((ilo || ihi) && (jlo || jhi)) { // corner -> mesh vertex
+                        const int c = jlo ? (ilo ? 0 : 1) : (ihi ? 2 : 3);
+                        int & vid = vertex_id[elems[4 * el + c]];
+                        if (vid < 0)
+                            vid = next++;
+                        id = vid;
+                    }
+                    else if (ilo || ihi || jlo || jhi) { // edge-interior node
+                        const int s = jlo ? 0 : (ihi ? 1 : (jhi ? 2 : 3));
+                        const int pos = (s == 0 || s == 2) ? i : j;
+                        const int e = eledge[4 * el + s];
+                        const int * rec = edges + 8 * (size_t)e;
+                        const bool first = (rec[2] == (int)el && rec[4] == s);
+                        const int t = (first || rec[6] > 0) ? pos : (nb - 1 - pos);
+                        int & eid = edge_id[(size_t)e * ne_int + (t - 1)];
+                        if (eid < 0)
+                            eid = next++;
+                        id = eid;
+                    }
+                    else
+                        id = next++;
+                    Ie[i + nb * j] = id;
+                }
+            }
+        }
+        ndof = next;
+
+        xy.assign(2 * (size_t)ndof, 0.0);
+        const double * q = basis->x.data();
+        for (int64_t el = 0; el < nel; ++el) {
+            double c[8];
+            mesh->corners(el, c);
+            const int * Ie = &I[(size_t)nb * nb * el];
+            for (int j = 0; j < nb; ++j)
+                for (int i = 0; i < nb; ++i) {
+                    const double xi0 = q[i], xi1 = q[j];
+                    const double b[4] = {0.25 * (1.0 - xi0) * (1.0 - xi1), 0.25 * (1.0 + xi0) * (1.0 - xi1),
+                                         0.25 * (1.0 + xi0) * (1.0 + xi1), 0.25 * (1.0 - xi0) * (1.0 + xi1)};
+                    double x0 = 0.0, x1 = 0.0;
+                    for (int k = 0; k < 4; ++k) {
+                        x0 += c[2 * k] * b[k];
+                        x1 += c[2 * k + 1] * b[k];
+                    }
+                    const size_t idx = (size_t)Ie[i + nb * j];
+                    xy[2 * idx] = x0;
+                    xy[2 * idx + 1] = x1;
+                }
+        }
+    }
+
+    const int * H1Space::device_I()
+    {
+        if (!d_I.p)
+            d_I.upload(I);
+        return d_I.p;
+    }
+    const double * H1Space::device_xy()
+    {
+        if (!d_xy.p)
+            d_xy.upload(xy);
+        return d_xy.p;
+    }
+    const double * H1Space::device_corners()
+    {
+        if (!d_corners.p) {
+            std::vector<double> c(8 * (size_t)n_elem);
+            for (int64_t el = 0; el < n_elem; ++el)
+                mesh->corners(el, &c[8 * (size_t)el]);
+            d_corners.upload(c);
+        }
+        return d_corners.p;
+    }
+    Plan & H1Space::get_plan_host()
+    {
+        if (!plan) {
+            plan.reset(new Plan);
+            build_plan(*this, *plan);
+        }
+        return *plan;
+    }
+    Plan & H1Space::get_plan()
+    {
+        if (!plan) {
+            plan.reset(new Plan);
+            build_plan(*this, *plan);
+        }
+        plan->ensure_device();
+        return *plan;
+    }
+
+    // ---- FaceSpace: reference source/H1Space.cpp:129-187 ----
+    FaceSpace::FaceSpace(H1Space * fem_, int64_t nf, const int * faces_) : fem(fem_), nb(fem_->nb), n_faces(nf)
+    {
+        const Mesh & mesh = *fem->mesh;
+        faces.assign(faces_, faces_ + nf);
+        I.assign((size_t)nb * nf, -1);
+        std::vector<int> seen((size_t)fem->ndof, -1);
+        std::vector<double> meas(nf);
+        for (int64_t f = 0; f < nf; ++f) {
+            const int e = faces[f];
+            CB_REQUIRE(e >= 0 && e < mesh.n_edges, "FaceSpace: face index out of range");
+            const int * rec = &mesh.edges[8 * (size_t)e];
+            const int64_t el = rec[2];
+            const int s = rec[4];
+            meas[f] = mesh.edge_meas[e];
+            for (int i = 0; i < nb; ++i) {
+                const int m = (s == 0 || s == 2) ? i : (s == 1 ? nb - 1 : 0);
+                const int n = (s == 1 || s == 3) ? i : (s == 2 ? nb - 1 : 0);
+                const int g = fem->I[(size_t)m + (size_t)nb * (n + (size_t)nb * el)];
+                if (seen[g] < 0) {
+                    seen[g] = (int)proj.size();
+                    proj.push_back(g);
+                }
+                I[i + (size_t)nb * f] = seen[g];
+            }
+        }
+        fdof = (int64_t)proj.size();
+
+        // DOF-centric incidence lists in (face, k) order: fixed summation order for the face mass action
+        inc_ptr.assign((size_t)fdof + 1, 0);
+        for (size_t k = 0; k < I.size(); ++k)
+            inc_ptr[I[k] + 1]++;
+        for (int64_t d = 0; d < fdof; ++d)
+            inc_ptr[d + 1] += inc_ptr[d];
+        inc.resize(I.size());
+        std::vector<int> cur(inc_ptr.begin(), inc_ptr.end() - 1);
+        for (size_t k = 0; k < I.size(); ++k)
+            inc[cur[I[k]]++] = (int)k;
+
+        h_meas = meas;
+    }
+
+    void FaceSpace::ensure_device()
+    {
+        if (on_device)
+            return;
+        d_I.upload(I);
+        d_proj.upload(proj);
+        d_inc_ptr.upload(inc_ptr);
+        d_inc.upload(inc);
+        d_meas.upload(h_meas);
+        on_device = true;
+    }
+
+    // ---- assembly plan -------------------------------------------------------------------------
+    // Elements are grouped into CTA patches (2-D tiles on uniform_rect meshes, chunks of a Morton-ordered
+    // centroid sort otherwise). Inside a patch the kernel accumulates element results into a patch-local
+    // vector in shared memory, colour by colour (elements of one colour share no DOF), so the summation
+    // order of every DOF is fixed by the plan -> bitwise reproducible without atomics. DOFs touched by a
+    // single patch are written straight to y; DOFs on patch boundaries go to a partial buffer whose slots
+    // are summed in patch order by a second small kernel.
+    namespace
+    {
+        void pick_patch_shape(int nb, int & px, int & py)
+        {
+            switch (nb) {
+            case 2: px = 12; py = 10; break;
+            case 3: px = 12; py = 10; break;
+            case 4: px = 10; py = 6; break;
+            case 5: px = 10; py = 6; break;
+            case 6: px = 6; py = 5; break;
+            case 7: px = 6; py = 5; break;
+            case 8: px = 4; py = 3; break;
+            case 9: px = 4; py = 3; break;
+            default: px = 3; py = 2; break;
+            }
+        }
+
+        uint64_t morton(uint32_t a, uint32_t b)
+        {
+            auto spread = [](uint64_t v) {
+                v &= 0xffffffffull;
+                v = (v | (v << 16)) & 0x0000ffff0000ffffull;
+                v = (v | (v << 8)) & 0x00ff00ff00ff00ffull;
+                v = (v | (v << 4)) & 0x0f0f0f0f0f0f0f0full;
+                v = (v | (v << 2)) & 0x3333333333333333ull;
+                v = (v | (v << 1)) & 0x5555555555555555ull;
+                return v;
+            };
+            return spread(a) | (spread(b) << 1);
+        }
+    } // namespace
+
+    void build_plan(H1Space & fem, Plan & plan)
+    {
+        const Mesh & mesh = *fem.mesh;
+        const int nb = fem.nb, nb2 = nb * nb;
+        const int64_t nel = fem.n_elem;
+        int px, py;
+        pick_patch_shape(nb, px, py);
+        const int PE = px * py;
+        plan.nb = nb;
+        plan.PE = PE;
+
+        // 1. patches -> element lists
+        std::vector<std::vector<int>> pel;
+        if (mesh.nx > 0 && (int64_t)mesh.nx * mesh.ny == nel) {
+            const int tx = (mesh.nx + px - 1) / px, ty = (mesh.ny + py - 1) / py;
+            pel.resize((size_t)tx * ty);
+            for (int j = 0; j < mesh.ny; ++j)
+                for (int i = 0; i < mesh.nx; ++i)
+                    pel[(size_t)(i / px) + (size_t)tx * (j / py)].push_back(i + mesh.nx * j);
+        }
+        else {
+            double lo[2] = {1e300, 1e300}, hi[2] = {-1e300, -1e300};
+            for (int64_t v = 0; v < mesh.n_nodes; ++v)
+                for (int d = 0; d < 2; ++d) {
+                    lo[d] = std::min(lo[d], mesh.xy[2 * v + d]);
+                    hi[d] = std::max(hi[d], mesh.xy[2 * v + d]);
+                }
+            std::vector<std::pair<uint64_t, int>> key(nel);
+            for (int64_t el = 0; el < nel; ++el) {
+                double c[8];
+                mesh.corners(el, c);
+                const double cx = 0.25 * (c[0] + c[2] + c[4] + c[6]), cy = 0.25 * (c[1] + c[3] + c[5] + c[7]);
+                const uint32_t a = (uint32_t)(65535.0 * (cx - lo[0]) / std::max(hi[0] - lo[0], 1e-300));
+                const uint32_t b = (uint32_t)(65535.0 * (cy - lo[1]) / std::max(hi[1] - lo[1], 1e-300));
+                key[el] = {morton(a, b), (int)el};
+            }
+            std::sort(key.begin(), key.end());
+            pel.resize((size_t)((nel + PE - 1) / PE));
+            for (int64_t k = 0; k < nel; ++k)
+                pel[k / PE].push_back(key[k].second);
+        }
+        const int64_t np = (int64_t)pel.size();
+        plan.n_patches = np;
+
+        // 2. greedy colouring inside each patch (vertex-sharing elements get different colours), then
+        //    order the patch's elements by colour
+        plan.hdr.resize(np);
+        plan.slot_elem.assign((size_t)np * PE, -1);
+        plan.color_ptr.clear();
+        {
+            std::vector<uint32_t> vmask((size_t)mesh.n_nodes, 0);
+            std::vector<int> col;
+            for (int64_t p = 0; p < np; ++p) {
+                auto & els = pel[p];
+                col.assign(els.size(), 0);
+                int ncol = 0;
+                for (size_t k = 0; k < els.size(); ++k) {
+                    uint32_t used = 0;
+                    for (int c = 0; c < 4; ++c)
+                        used |= vmask[mesh.elems[4 * (size_t)els[k] + c]];
+                    int cc = 0;
+                    while (used & (1u << cc))
+                        ++cc;
+                    CB_REQUIRE(cc < 32, "assembly plan: more than 32 colours needed in a patch");
+                    col[k] = cc;
+                    ncol = std::max(ncol, cc + 1);
+                    for (int c = 0; c < 4; ++c)
+                        vmask[mesh.elems[4 * (size_t)els[k] + c]] |= (1u << cc);
+                }
+                for (size_t k = 0; k < els.size(); ++k)
+                    for (int c = 0; c < 4; ++c)
+                        vmask[mesh.elems[4 * (size_t)els[k] + c]] = 0;
+                std::vector<int> order(els.size());
+                std::iota(order.begin(), order.end(), 0);
+                std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return col[a] < col[b]; });
+                PatchHdr & h = plan.hdr[p];
+                h.elem_begin = (int)(p * PE);
+                h.n_elem = (int)els.size();
+                h.color_begin = (int)plan.color_ptr.size();
+                h.n_colors = ncol;
+                plan.max_colors = std::max(plan.max_colors, ncol);
+                int pos = 0;
+                for (int c = 0; c < ncol; ++c) {
+                    plan.color_ptr.push_back(pos);
+                    while (pos < (int)order.size() && col[order[pos]] == c)
+                        ++pos;
+                }
+                plan.color_ptr.push_back(pos);
+                for (size_t k = 0; k < order.size(); ++k)
+                    plan.slot_elem[(size_t)p * PE + k] = els[order[k]];
+            }
+        }
+
+        // 3. patch-local DOF lists; a DOF touched by more than one patch is "shared"
+        std::vector<uint8_t> touch((size_t)fem.ndof, 0);
+        std::vector<std::vector<int>> pg(np);
+        for (int64_t p = 0; p < np; ++p) {
+            auto & g = pg[p];
+            g.reserve((size_t)plan.hdr[p].n_elem * nb2);
+            for (int k = 0; k < plan.hdr[p].n_elem; ++k) {
+                const int * Ie = &fem.I[(size_t)nb2 * plan.slot_elem[(size_t)p * PE + k]];
+                g.insert(g.end(), Ie, Ie + nb2);
+            }
+            std::sort(g.begin(), g.end());
+            g.erase(std::unique(g.begin(), g.end()), g.end());
+            for (int v : g)
+                if (touch[v] < 255)
+                    touch[v]++;
+        }
+        // shared DOF table (ascending global id) and CSR of partial slots in patch order
+        std::vector<int> sh_index((size_t)fem.ndof, -1);
+        plan.sh_gid.clear();
+        for (int64_t g = 0; g < fem.ndof; ++g)
+            if (touch[g] > 1) {
+                sh_index[g] = (int)plan.sh_gid.size();
+                plan.sh_gid.push_back((int)g);
+            }
+        plan.n_shared = (int64_t)plan.sh_gid.size();
+        plan.sh_ptr.assign((size_t)plan.n_shared + 1, 0);
+        for (int64_t p = 0; p < np; ++p)
+            for (int v : pg[p])
+                if (sh_index[v] >= 0)
+                    plan.sh_ptr[sh_index[v] + 1]++;
+        for (int64_t s = 0; s < plan.n_shared; ++s)
+            plan.sh_ptr[s + 1] += plan.sh_ptr[s];
+        plan.n_slots_total = plan.sh_ptr[plan.n_shared];
+        std::vector<int> next_slot(plan.sh_ptr.begin(), plan.sh_ptr.end() - 1);
+
+        plan.gid.clear();
+        plan.slot.clear();
+        plan.L.assign((size_t)np * PE * nb2, 0);
+        std::vector<int> local((size_t)fem.ndof, -1);
+        for (int64_t p = 0; p < np; ++p) {
+            PatchHdr & h = plan.hdr[p];
+            auto & g = pg[p];
+            h.pdof_begin = (int)plan.gid.size();
+            h.slot_begin = (int)plan.slot.size();
+            h.n_pdof = (int)g.size();
+            CB_REQUIRE(g.size() < 65535, "assembly plan: patch has too many DOFs for 16-bit local ids");
+            int n = 0;
+            for (int v : g)
+                if (sh_index[v] < 0) {
+                    local[v] = n++;
+                    plan.gid.push_back(v);
+                }
+            h.n_int = n;
+            for (int v : g)
+                if (sh_index[v] >= 0) {
+                    local[v] = n++;
+                    plan.gid.push_back(v);
+                    plan.slot.push_back(next_slot[sh_index[v]]++);
+                }
+            plan.max_pdof = std::max(plan.max_pdof, h.n_pdof);
+            for (int k = 0; k < h.n_elem; ++k) {
+                const int * Ie = &fem.I[(size_t)nb2 * plan.slot_elem[(size_t)p * PE + k]];
+                uint16_t * Le = &plan.L[((size_t)p * PE + k) * nb2];
+                for (int a = 0; a < nb2; ++a)
+                    Le[a] = (uint16_t)local[Ie[a]];
+            }
+        }
+
+    }
+
+    void Plan::ensure_device()
+    {
+        if (on_device)
+            return;
+        d_hdr.upload(hdr);
+        d_gid.upload(gid);
+        d_slot.upload(slot);
+        d_L.upload(L);
+        d_color_ptr.upload(color_ptr);
+        d_slot_elem.upload(slot_elem);
+        d_sh_gid.upload(sh_gid);
+        d_sh_ptr.upload(sh_ptr);
+        on_device = true;
+    }
+} // namespace cb200

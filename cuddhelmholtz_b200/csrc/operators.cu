@@ -1,0 +1,951 @@
+// FP64 matrix-free operator actions for sm_100a (path A): stiffness, mass, face mass.
+//
+// What the reference does (source/StiffnessMatrix.cpp:83-184, source/MassMatrix.cpp:137-211): one CTA of
+// nq*nq threads per element, 1-D tables re-read from global memory by every CTA, 4 barriers, FP64
+// atomicAdd scatter preceded by a cudaMemset. What this file does instead:
+//
+//   * one CTA per PATCH of elements (assembly plan, h1space.cpp). The patch's unique DOFs are gathered once,
+//     coalesced, into shared memory; element results are accumulated into a patch-local vector colour by
+//     colour (fixed order, no atomics) and written back with plain coalesced stores. Only DOFs on patch
+//     boundaries (~12%) take a detour through a partial buffer that a second tiny kernel sums in patch
+//     order. The result is bitwise reproducible and needs no memset.
+//   * inside a patch, a warp processes EPW = 32/NQ elements at a time with NQ lanes per element. Each
+//     lane owns a whole tensor row/column in registers, so the sum-factorised contractions are pure
+//     register DFMA chains whose table operands (P, D) come from the kernel-parameter constant bank
+//     (__grid_constant__): no shared-memory reads for the tables at all. The two transposes an element
+//     needs go through a small per-warp scratch with __syncwarp only.
+//   * the metric data (G for stiffness, a*w*w*detJ for mass) is stored in "lane-major" plan order so that
+//     every load instruction of a warp reads one contiguous run; it is prefetched into registers before
+//     the first contraction, streamed with an evict-first hint.
+//
+// Contraction order. Let U = u[I] (nb x nb), F = metric applied at quadrature points. The reference forms
+//   Su[a][b] = sum_j P(j,b) (sum_i D(i,a) F0[i][j]) + D(j,b) (sum_i P(i,a) F1[i][j]);
+// here the j-sum (local to a lane) is done first and the i-sum second: same flops, one transpose fewer.
+// The difference is floating-point re-association only (tests bound it at 1e-12 relative).
+#include "operators.hpp"
+#include <algorithm>
+#include <cmath>
+
+namespace cb200
+{
+    namespace
+    {
+        constexpr int MAXQ = 32;
+
+        struct PlanDev
+        {
+            const PatchHdr * hdr;
+            const int * gid;
+            const int * slot;
+            const uint16_t * L;
+            const int * color_ptr;
+            int PE;
+        };
+
+        template <int NB, int NQ, bool STIFF>
+        struct Tables
+        {
+            double P[NQ * NB];
+            double D[STIFF ? NQ * NB : 1];
+        };
+
+        __device__ __forceinline__ double ld_stream(const double * p)
+        {
+            return __ldcs(p);
+        }
+
+        // ------------------------------------------------------------------------------------------
+        // main action kernel
+        // ------------------------------------------------------------------------------------------
+        template <int NB, int NQ, bool STIFF>
+        __global__ void __launch_bounds__(256)
+        volume_action_kernel(const __grid_constant__ Tables<NB, NQ, STIFF> tab, const PlanDev plan,
+                             const double * __restrict__ G, const double * __restrict__ x, double * __restrict__ y,
+                             double * __restrict__ partial, const double c, const int accumulate, const int max_pdof)
+        {
+            constexpr int EPW = 32 / NQ;          // elements per warp pass
+            constexpr int LW = EPW * NQ;          // active lanes
+            constexpr int NB2 = NB * NB;
+            constexpr int NK = STIFF ? 3 * NQ : NQ; // metric values per lane
+            constexpr int SCR = (STIFF ? 2 : 1) * NQ * NB; // scratch doubles per element
+
+            extern __shared__ __align__(16) unsigned char smem_raw[];
+            const int PE = plan.PE;
+            const int n_pass_patch = (PE + EPW - 1) / EPW;
+            const int nwarps = blockDim.x >> 5;
+            double * xloc = reinterpret_cast<double *>(smem_raw);
+            double * yloc = xloc + max_pdof;
+            double * su = yloc + max_pdof;
+            double * scratch = su + PE * NB2;
+            uint16_t * Ls = reinterpret_cast<uint16_t *>(scratch + nwarps * EPW * SCR);
+
+            const int tid = threadIdx.x;
+            const int lane = tid & 31;
+            const int warp = tid >> 5;
+            const PatchHdr hdr = plan.hdr[blockIdx.x];
+
+            // ---- A. stage the patch: gather x, zero the accumulator, copy the local map ----
+            for (int d = tid; d < hdr.n_pdof; d += blockDim.x) {
+                xloc[d] = __ldg(x + __ldg(plan.gid + hdr.pdof_begin + d));
+                yloc[d] = 0.0;
+            }
+            {
+                const uint16_t * Lg = plan.L + (size_t)hdr.elem_begin * NB2;
+                for (int k = tid; k < hdr.n_elem * NB2; k += blockDim.x)
+                    Ls[k] = __ldg(Lg + k);
+            }
+            __syncthreads();
+
+            // ---- B. element contractions, EPW elements per warp pass ----
+            const int el_local = lane / NQ;
+            const int r = lane - el_local * NQ; // row / column owned by this lane
+            double * sc = scratch + (warp * EPW + el_local) * SCR;
+            const int n_pass = (hdr.n_elem + EPW - 1) / EPW;
+
+            for (int pass = warp; pass < n_pass; pass += nwarps) {
+                const int e = pass * EPW + el_local;
+                const bool live = (lane < LW) && (e < hdr.n_elem);
+
+                // prefetch this lane's metric values (row r of the element, all columns)
+                double g[NK];
+                {
+                    const double * gp = G + ((size_t)blockIdx.x * n_pass_patch + pass) * (size_t)(NK * LW) + lane;
+                    if (lane < LW) {
+#pragma unroll
+                        for (int k = 0; k < NK; ++k)
+                            g[k] = ld_stream(gp + k * LW);
+                    }
+                }
+
+                // stage 1: lane j = r < NB holds column j of U; contracts the first index with P (and D)
+                if (live && r < NB) {
+                    double u[NB];
+                    const uint16_t * Le = Ls + e * NB2 + NB * r;
+#pragma unroll
+                    for (int k = 0; k < NB; ++k)
+                        u[k] = xloc[Le[k]];
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        double pu = 0.0, du = 0.0;
+#pragma unroll
+                        for (int k = 0; k < NB; ++k) {
+                            pu = fma(tab.P[q + NQ * k], u[k], pu);
+                            if (STIFF)
+                                du = fma(tab.D[q + NQ * k], u[k], du);
+                        }
+                        sc[q * NB + r] = pu;
+                        if (STIFF)
+                            sc[NQ * NB + q * NB + r] = du;
+                    }
+                }
+                __syncwarp();
+
+                // stage 2: lane q = r holds row q; second-index contraction, metric, and the transposed
+                // second-index contraction back to the basis
+                double a0[NB], a1[STIFF ? NB : 1];
+                if (live) {
+                    double pu[NB], du[STIFF ? NB : 1];
+#pragma unroll
+                    for (int l = 0; l < NB; ++l) {
+                        pu[l] = sc[r * NB + l];
+                        if (STIFF)
+                            du[l] = sc[NQ * NB + r * NB + l];
+                    }
+#pragma unroll
+                    for (int t = 0; t < NB; ++t) {
+                        a0[t] = 0.0;
+                        if (STIFF)
+                            a1[t] = 0.0;
+                    }
+#pragma unroll
+                    for (int ty = 0; ty < NQ; ++ty) {
+                        if (STIFF) {
+                            double Dx = 0.0, Dy = 0.0;
+#pragma unroll
+                            for (int l = 0; l < NB; ++l) {
+                                Dx = fma(tab.P[ty + NQ * l], du[l], Dx);
+                                Dy = fma(tab.D[ty + NQ * l], pu[l], Dy);
+                            }
+                            const double A = g[3 * ty], B = g[3 * ty + 1], C = g[3 * ty + 2];
+                            const double F0 = A * Dx + B * Dy;
+                            const double F1 = B * Dx + C * Dy;
+#pragma unroll
+                            for (int t = 0; t < NB; ++t) {
+                                a0[t] = fma(tab.P[ty + NQ * t], F0, a0[t]);
+                                a1[t] = fma(tab.D[ty + NQ * t], F1, a1[t]);
+                            }
+                        }
+                        else {
+                            double ppu = 0.0;
+#pragma unroll
+                            for (int l = 0; l < NB; ++l)
+                                ppu = fma(tab.P[ty + NQ * l], pu[l], ppu);
+                            const double val = g[ty] * ppu;
+#pragma unroll
+                            for (int t = 0; t < NB; ++t)
+                                a0[t] = fma(tab.P[ty + NQ * t], val, a0[t]);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (live) {
+#pragma unroll
+                    for (int t = 0; t < NB; ++t) {
+                        sc[r * NB + t] = a0[t];
+                        if (STIFF)
+                            sc[NQ * NB + r * NB + t] = a1[t];
+                    }
+                }
+                __syncwarp();
+
+                // stage 3: lane b = r < NB contracts the first index back to the basis
+                if (live && r < NB) {
+                    double A0[NQ], A1[STIFF ? NQ : 1];
+#pragma unroll
+                    for (int i = 0; i < NQ; ++i) {
+                        A0[i] = sc[i * NB + r];
+                        if (STIFF)
+                            A1[i] = sc[NQ * NB + i * NB + r];
+                    }
+                    double * so = su + e * NB2 + NB * r;
+#pragma unroll
+                    for (int t = 0; t < NB; ++t) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int i = 0; i < NQ; ++i) {
+                            if (STIFF) {
+                                s = fma(tab.D[i + NQ * t], A0[i], s);
+                                s = fma(tab.P[i + NQ * t], A1[i], s);
+                            }
+                            else
+                                s = fma(tab.P[i + NQ * t], A0[i], s);
+                        }
+                        so[t] = s;
+                    }
+                }
+                __syncwarp();
+            }
+            __syncthreads();
+
+            // ---- C. deterministic in-patch assembly: colours in order, no two elements of a colour share a DOF ----
+            {
+                const int * cp = plan.color_ptr + hdr.color_begin;
+                for (int col = 0; col < hdr.n_colors; ++col) {
+                    const int k0 = cp[col] * NB2, k1 = cp[col + 1] * NB2;
+                    for (int k = k0 + tid; k < k1; k += blockDim.x)
+                        yloc[Ls[k]] += su[k];
+                    __syncthreads();
+                }
+            }
+
+            // ---- D. write-back: patch-private DOFs straight to y, shared ones to their partial slot ----
+            for (int d = tid; d < hdr.n_int; d += blockDim.x) {
+                const int gi = __ldg(plan.gid + hdr.pdof_begin + d);
+                const double v = c * yloc[d];
+                y[gi] = accumulate ? (y[gi] + v) : v;
+            }
+            for (int d = hdr.n_int + tid; d < hdr.n_pdof; d += blockDim.x)
+                partial[__ldg(plan.slot + hdr.slot_begin + d - hdr.n_int)] = yloc[d];
+        }
+
+        // generic fallback for (nb, nq) pairs without a template instance: same algorithm and data layout
+        // with EPW = 1 (one element per warp pass), runtime loops, tables in global memory.
+        __global__ void __launch_bounds__(256)
+        volume_action_generic(const int NB, const int NQ, const int STIFF, const double * __restrict__ Pt,
+                              const double * __restrict__ Dt, const PlanDev plan, const double * __restrict__ G,
+                              const double * __restrict__ x, double * __restrict__ y, double * __restrict__ partial,
+                              const double c, const int accumulate, const int max_pdof)
+        {
+            extern __shared__ __align__(16) unsigned char smem_raw[];
+            const int NB2 = NB * NB;
+            const int NK = STIFF ? 3 * NQ : NQ;
+            const int SCR = (STIFF ? 2 : 1) * NQ * NB;
+            const int PE = plan.PE;
+            const int nwarps = blockDim.x >> 5;
+            double * xloc = reinterpret_cast<double *>(smem_raw);
+            double * yloc = xloc + max_pdof;
+            double * su = yloc + max_pdof;
+            double * scratch = su + PE * NB2;
+            uint16_t * Ls = reinterpret_cast<uint16_t *>(scratch + nwarps * SCR);
+            const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+            const PatchHdr hdr = plan.hdr[blockIdx.x];
+
+            for (int d = tid; d < hdr.n_pdof; d += blockDim.x) {
+                xloc[d] = __ldg(x + __ldg(plan.gid + hdr.pdof_begin + d));
+                yloc[d] = 0.0;
+            }
+            const uint16_t * Lg = plan.L + (size_t)hdr.elem_begin * NB2;
+            for (int k = tid; k < hdr.n_elem * NB2; k += blockDim.x)
+                Ls[k] = __ldg(Lg + k);
+            __syncthreads();
+
+            double * sc = scratch + warp * SCR;
+            const int r = lane;
+            for (int e = warp; e < hdr.n_elem; e += nwarps) {
+                const double * gp = G + ((size_t)blockIdx.x * PE + e) * (size_t)(NK * NQ) + lane;
+                if (r < NB) {
+                    const uint16_t * Le = Ls + e * NB2 + NB * r;
+                    for (int q = 0; q < NQ; ++q) {
+                        double pu = 0.0, du = 0.0;
+                        for (int k = 0; k < NB; ++k) {
+                            const double uk = xloc[Le[k]];
+                            pu = fma(Pt[q + NQ * k], uk, pu);
+                            if (STIFF)
+                                du = fma(Dt[q + NQ * k], uk, du);
+                        }
+                        sc[q * NB + r] = pu;
+                        if (STIFF)
+                            sc[NQ * NB + q * NB + r] = du;
+                    }
+                }
+                __syncwarp();
+                double a0[MAXQ], a1[MAXQ];
+                if (r < NQ) {
+                    for (int t = 0; t < NB; ++t)
+                        a0[t] = a1[t] = 0.0;
+                    for (int ty = 0; ty < NQ; ++ty) {
+                        if (STIFF) {
+                            double Dx = 0.0, Dy = 0.0;
+                            for (int l = 0; l < NB; ++l) {
+                                Dx = fma(Pt[ty + NQ * l], sc[NQ * NB + r * NB + l], Dx);
+                                Dy = fma(Dt[ty + NQ * l], sc[r * NB + l], Dy);
+                            }
+                            const double A = gp[(3 * ty) * NQ], B = gp[(3 * ty + 1) * NQ], C = gp[(3 * ty + 2) * NQ];
+                            const double F0 = A * Dx + B * Dy, F1 = B * Dx + C * Dy;
+                            for (int t = 0; t < NB; ++t) {
+                                a0[t] = fma(Pt[ty + NQ * t], F0, a0[t]);
+                                a1[t] = fma(Dt[ty + NQ * t], F1, a1[t]);
+                            }
+                        }
+                        else {
+                            double ppu = 0.0;
+                            for (int l = 0; l < NB; ++l)
+                                ppu = fma(Pt[ty + NQ * l], sc[r * NB + l], ppu);
+                            const double val = gp[ty * NQ] * ppu;
+                            for (int t = 0; t < NB; ++t)
+                                a0[t] = fma(Pt[ty + NQ * t], val, a0[t]);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (r < NQ)
+                    for (int t = 0; t < NB; ++t) {
+                        sc[r * NB + t] = a0[t];
+                        if (STIFF)
+                            sc[NQ * NB + r * NB + t] = a1[t];
+                    }
+                __syncwarp();
+                if (r < NB) {
+                    double * so = su + e * NB2 + NB * r;
+                    for (int t = 0; t < NB; ++t) {
+                        double s = 0.0;
+                        for (int i = 0; i < NQ; ++i) {
+                            if (STIFF) {
+                                s = fma(Dt[i + NQ * t], sc[i * NB + r], s);
+                                s = fma(Pt[i + NQ * t], sc[NQ * NB + i * NB + r], s);
+                            }
+                            else
+                                s = fma(Pt[i + NQ * t], sc[i * NB + r], s);
+                        }
+                        so[t] = s;
+                    }
+                }
+                __syncwarp();
+            }
+            __syncthreads();
+            const int * cp = plan.color_ptr + hdr.color_begin;
+            for (int col = 0; col < hdr.n_colors; ++col) {
+                const int k0 = cp[col] * NB2, k1 = cp[col + 1] * NB2;
+                for (int k = k0 + tid; k < k1; k += blockDim.x)
+                    yloc[Ls[k]] += su[k];
+                __syncthreads();
+            }
+            for (int d = tid; d < hdr.n_int; d += blockDim.x) {
+                const int gi = __ldg(plan.gid + hdr.pdof_begin + d);
+                const double v = c * yloc[d];
+                y[gi] = accumulate ? (y[gi] + v) : v;
+            }
+            for (int d = hdr.n_int + tid; d < hdr.n_pdof; d += blockDim.x)
+                partial[__ldg(plan.slot + hdr.slot_begin + d - hdr.n_int)] = yloc[d];
+        }
+
+        // second pass: DOFs shared between patches, partial slots summed in patch order
+        __global__ void assemble_shared_kernel(const int64_t n_shared, const int * __restrict__ sh_gid,
+                                               const int * __restrict__ sh_ptr, const double * __restrict__ partial,
+                                               double * __restrict__ y, const double c, const int accumulate)
+        {
+            const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+            if (s >= n_shared)
+                return;
+            const int b = sh_ptr[s], e = sh_ptr[s + 1];
+            double sum = 0.0;
+            for (int k = b; k < e; ++k)
+                sum += partial[k];
+            const int gi = sh_gid[s];
+            const double v = c * sum;
+            y[gi] = accumulate ? (y[gi] + v) : v;
+        }
+
+        // ------------------------------------------------------------------------------------------
+        // setup kernels: metric data in plan ("lane-major") order.
+        //   index(slot e of patch p, q = first quad index, k) =
+        //       ((p * n_pass + e / EPW) * NK + k) * LW + (e % EPW) * NQ + q
+        // Jacobian of the bilinear map: source/Element.cpp:21-27; G: source/StiffnessMatrix.cpp:5-38;
+        // mass weights: source/MassMatrix.cpp:5-67.
+        // ------------------------------------------------------------------------------------------
+        __device__ __forceinline__ void bilinear_jacobian(const double * c, double xi0, double xi1, double * J)
+        {
+            J[0] = 0.25 * ((1.0 - xi1) * (c[2] - c[0]) + (1.0 + xi1) * (c[4] - c[6]));
+            J[1] = 0.25 * ((1.0 - xi1) * (c[3] - c[1]) + (1.0 + xi1) * (c[5] - c[7]));
+            J[2] = 0.25 * ((1.0 - xi0) * (c[6] - c[0]) + (1.0 + xi0) * (c[4] - c[2]));
+            J[3] = 0.25 * ((1.0 - xi0) * (c[7] - c[1]) + (1.0 + xi0) * (c[5] - c[3]));
+        }
+
+        __global__ void setup_stiffness_kernel(const int64_t n_slots, const int PE, const int NQ, const int EPW,
+                                               const int n_pass, const int * __restrict__ slot_elem,
+                                               const double * __restrict__ corners, const double * __restrict__ xq,
+                                               const double * __restrict__ wq, double * __restrict__ G)
+        {
+            const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+            const int nq2 = NQ * NQ;
+            if (t >= n_slots * nq2)
+                return;
+            const int64_t slot = t / nq2;
+            const int rem = (int)(t - slot * nq2);
+            const int i = rem % NQ, j = rem / NQ;
+            const int64_t p = slot / PE;
+            const int e = (int)(slot - p * PE);
+            const int el = slot_elem[slot];
+            const int LW = EPW * NQ, NK = 3 * NQ;
+            const size_t base = ((size_t)(p * n_pass + e / EPW) * NK) * LW + (size_t)(e % EPW) * NQ + i;
+            double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+            if (el >= 0) {
+                double J[4];
+                bilinear_jacobian(corners + 8 * (size_t)el, xq[i], xq[j], J);
+                const double W = wq[i] * wq[j];
+                const double X_xi = J[0], Y_xi = J[1], X_eta = J[2], Y_eta = J[3];
+                const double det = X_xi * Y_eta - X_eta * Y_xi;
+                g0 = W * (Y_eta * Y_eta + X_eta * X_eta) / det;
+                g1 = -W * (Y_xi * Y_eta + X_xi * X_eta) / det;
+                g2 = W * (Y_xi * Y_xi + X_xi * X_xi) / det;
+            }
+            G[base + (size_t)(3 * j + 0) * LW] = g0;
+            G[base + (size_t)(3 * j + 1) * LW] = g1;
+            G[base + (size_t)(3 * j + 2) * LW] = g2;
+        }
+
+        __global__ void setup_mass_kernel(const int64_t n_slots, const int PE, const int NB, const int NQ, const int EPW,
+                                          const int n_pass, const int * __restrict__ slot_elem,
+                                          const double * __restrict__ corners, const int * __restrict__ I,
+                                          const double * __restrict__ coef, const double * __restrict__ P,
+                                          const double * __restrict__ xq, const double * __restrict__ wq,
+                                          double * __restrict__ A)
+        {
+            const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+            const int nq2 = NQ * NQ;
+            if (t >= n_slots * nq2)
+                return;
+            const int64_t slot = t / nq2;
+            const int rem = (int)(t - slot * nq2);
+            const int tx = rem % NQ, ty = rem / NQ;
+            const int64_t p = slot / PE;
+            const int e = (int)(slot - p * PE);
+            const int el = slot_elem[slot];
+            const int LW = EPW * NQ, NK = NQ;
+            const size_t idx = ((size_t)(p * n_pass + e / EPW) * NK + ty) * LW + (size_t)(e % EPW) * NQ + tx;
+            double val = 0.0;
+            if (el >= 0) {
+                double ppx = 0.0;
+                const int * Ie = I + (size_t)NB * NB * el;
+                for (int l = 0; l < NB; ++l) {
+                    double z = 0.0; // z[tx][l] = sum_k P(tx,k) Q[k][l]
+                    for (int k = 0; k < NB; ++k)
+                        z += P[tx + NQ * k] * (coef ? coef[Ie[k + NB * l]] : 1.0);
+                    ppx += P[ty + NQ * l] * z;
+                }
+                double J[4];
+                bilinear_jacobian(corners + 8 * (size_t)el, xq[tx], xq[ty], J);
+                const double det = J[0] * J[3] - J[1] * J[2];
+                ppx *= wq[tx] * wq[ty] * det;
+                val = ppx;
+            }
+            A[idx] = val;
+        }
+
+        // lumped (GLL-collocated) mass diagonal, DOF-centric and deterministic: one thread per element node
+        // writes its contribution into an element-local array, a second kernel sums per DOF through the plan?
+        // Setup-only and tiny: use a simple two-step (element-local products, then ordered gather by a
+        // transposed map built on the host).
+        __global__ void diag_mass_contrib_kernel(const int64_t nel, const int NB, const int * __restrict__ I,
+                                                 const double * __restrict__ corners, const double * __restrict__ coef,
+                                                 const double * __restrict__ xg, const double * __restrict__ wg,
+                                                 double * __restrict__ contrib)
+        {
+            const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+            const int nb2 = NB * NB;
+            if (t >= nel * nb2)
+                return;
+            const int64_t el = t / nb2;
+            const int rem = (int)(t - el * nb2);
+            const int i = rem % NB, j = rem / NB;
+            double J[4];
+            bilinear_jacobian(corners + 8 * (size_t)el, xg[i], xg[j], J);
+            double m = wg[i] * wg[j] * (J[0] * J[3] - J[1] * J[2]);
+            if (coef)
+                m *= coef[I[t]];
+            contrib[t] = m;
+        }
+
+        __global__ void gather_sum_recip_kernel(const int64_t n, const int * __restrict__ ptr, const int * __restrict__ src,
+                                                const double * __restrict__ contrib, double * __restrict__ out)
+        {
+            const int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+            if (d >= n)
+                return;
+            double s = 0.0;
+            for (int k = ptr[d]; k < ptr[d + 1]; ++k)
+                s += contrib[src[k]];
+            out[d] = 1.0 / s;
+        }
+
+        __global__ void diag_apply_kernel(const int64_t n, const double * __restrict__ p, const double c, const int accumulate,
+                                          const double * __restrict__ x, double * __restrict__ y)
+        {
+            const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+            if (i >= n)
+                return;
+            // reference source/MassMatrix.cpp:316-334: y += c*p*x  /  y = p*x
+            y[i] = accumulate ? (y[i] + c * p[i] * x[i]) : (c * p[i] * x[i]);
+        }
+
+        // ------------------------------------------------------------------------------------------
+        // face mass: reference source/FaceMassMatrix.cpp:141-193. One thread per face-space DOF walks its
+        // incident (face, k) pairs in fixed order (deterministic; replaces atomicAdd). `gather`/`scatter`
+        // fuse FaceSpace::restrict / prolong (source/H1Space.cpp:189-211) when operating on H1 vectors.
+        // ------------------------------------------------------------------------------------------
+        __global__ void facemass_action_kernel(const int64_t fdof, const int NB, const int NQ, const double * __restrict__ P,
+                                               const double * __restrict__ a, const int * __restrict__ If,
+                                               const int * __restrict__ inc_ptr, const int * __restrict__ inc,
+                                               const int * __restrict__ proj /* null: face-space vectors */,
+                                               const double c, const int accumulate, const double * __restrict__ x,
+                                               double * __restrict__ y)
+        {
+            const int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+            if (d >= fdof)
+                return;
+            double sum = 0.0;
+            for (int t = inc_ptr[d]; t < inc_ptr[d + 1]; ++t) {
+                const int fk = inc[t];
+                const int f = fk / NB, k = fk - f * NB;
+                const int * Ifa = If + (size_t)NB * f;
+                double Mu = 0.0;
+                for (int i = 0; i < NQ; ++i) {
+                    double pu = 0.0;
+                    for (int l = 0; l < NB; ++l) {
+                        const int xi = proj ? proj[Ifa[l]] : Ifa[l];
+                        pu += P[i + NQ * l] * x[xi];
+                    }
+                    pu *= a[i + (size_t)NQ * f];
+                    Mu += P[i + NQ * k] * pu;
+                }
+                sum += c * Mu;
+            }
+            const int64_t yi = proj ? proj[d] : d;
+            y[yi] = accumulate ? (y[yi] + sum) : sum;
+        }
+
+        __global__ void setup_facemass_kernel(const int64_t nf, const int NB, const int NQ, const double * __restrict__ wq,
+                                              const double * __restrict__ P, const double * __restrict__ meas,
+                                              const double * __restrict__ coef, const int * __restrict__ If,
+                                              double * __restrict__ op)
+        {
+            const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+            if (t >= nf * NQ)
+                return;
+            const int64_t f = t / NQ;
+            const int k = (int)(t - f * NQ);
+            double pa = 0.0;
+            for (int l = 0; l < NB; ++l)
+                pa += P[k + NQ * l] * (coef ? coef[If[l + (size_t)NB * f]] : 1.0);
+            pa *= wq[k] * meas[f];
+            op[t] = pa;
+        }
+
+        __global__ void diag_facemass_kernel(const int64_t fdof, const int NB, const double * __restrict__ wg,
+                                             const double * __restrict__ meas, const double * __restrict__ coef,
+                                             const int * __restrict__ inc_ptr, const int * __restrict__ inc,
+                                             double * __restrict__ out)
+        {
+            const int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+            if (d >= fdof)
+                return;
+            double s = 0.0;
+            for (int t = inc_ptr[d]; t < inc_ptr[d + 1]; ++t) {
+                const int fk = inc[t];
+                const int f = fk / NB, i = fk - f * NB;
+                double m = wg[i] * meas[f];
+                if (coef)
+                    m *= coef[d];
+                s += m;
+            }
+            out[d] = 1.0 / s;
+        }
+
+        __global__ void restrict_kernel(const int64_t n, const int * __restrict__ proj, const double * __restrict__ x, double * __restrict__ y)
+        {
+            const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+            if (i < n)
+                y[i] = x[proj[i]];
+        }
+        __global__ void prolong_kernel(const int64_t n, const int * __restrict__ proj, const double * __restrict__ x, double * __restrict__ y)
+        {
+            const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+            if (i < n)
+                y[proj[i]] += x[i]; // proj is injective: no atomics needed
+        }
+        __global__ void orth_kernel(const int64_t n, const int * __restrict__ proj, double * __restrict__ x)
+        {
+            const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+            if (i < n)
+                x[proj[i]] = 0.0;
+        }
+        __global__ void negate_kernel(const int64_t n, double * __restrict__ x)
+        {
+            const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+            if (i < n)
+                x[i] = -x[i];
+        }
+
+        inline unsigned blocks_for(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+        // ------------------------------------------------------------------------------------------
+        // launch plumbing
+        // ------------------------------------------------------------------------------------------
+        int pick_warps(int n_pass)
+        {
+            int best = std::min(8, n_pass);
+            for (int w = 8; w >= 4; --w)
+                if (n_pass % w == 0) {
+                    best = w;
+                    break;
+                }
+            return std::max(best, 1);
+        }
+
+        template <int NB, int NQ, bool STIFF>
+        void launch_volume(VolumeOp & op, const PlanDev & pd, const Plan & plan, double c, int accumulate, const double * x,
+                           double * y, cudaStream_t s)
+        {
+            constexpr int EPW = 32 / NQ;
+            constexpr int SCR = (STIFF ? 2 : 1) * NQ * NB;
+            const int n_pass = (plan.PE + EPW - 1) / EPW;
+            const int nwarps = pick_warps(n_pass);
+            size_t smem = sizeof(double) * ((size_t)2 * plan.max_pdof + (size_t)plan.PE * NB * NB + (size_t)nwarps * EPW * SCR) +
+                          sizeof(uint16_t) * (size_t)plan.PE * NB * NB;
+            smem = (smem + 15) & ~size_t(15);
+            Tables<NB, NQ, STIFF> tab;
+            for (int k = 0; k < NQ * NB; ++k) {
+                tab.P[k] = op.P[k];
+                if (STIFF)
+                    tab.D[k] = op.D[k];
+            }
+            auto kern = volume_action_kernel<NB, NQ, STIFF>;
+            static bool attr_set = false;
+            static size_t attr_smem = 0;
+            if (!attr_set || smem > attr_smem) {
+                CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)49152)));
+                attr_set = true;
+                attr_smem = std::max(smem, (size_t)49152);
+            }
+            kern<<<(unsigned)plan.n_patches, nwarps * 32, smem, s>>>(tab, pd, op.d_G.p, x, y, op.d_partial.p, c, accumulate,
+                                                                       plan.max_pdof);
+            CB_LAUNCHED();
+        }
+
+        using LaunchFn = void (*)(VolumeOp &, const PlanDev &, const Plan &, double, int, const double *, double *, cudaStream_t);
+
+        template <bool STIFF>
+        LaunchFn find_instance(int nb, int nq)
+        {
+#define CB_CASE(NB_, NQ_)                                                                                              \
+    if (nb == NB_ && nq == NQ_)                                                                                        \
+        return &launch_volume<NB_, NQ_, STIFF>;
+            // default rules: nq = nb + 1 (reference StiffnessMatrix.cpp:45, MassMatrix.cpp:74)
+            CB_CASE(2, 3) CB_CASE(3, 4) CB_CASE(4, 5) CB_CASE(5, 6) CB_CASE(6, 7) CB_CASE(7, 8) CB_CASE(8, 9) CB_CASE(9, 10)
+            // the reference tests' nb + 2 rules (tests/stiffness.cpp:84, tests/mass.cpp:94)
+            CB_CASE(3, 5) CB_CASE(4, 6) CB_CASE(5, 7) CB_CASE(6, 8) CB_CASE(7, 9) CB_CASE(8, 10)
+            if (!STIFF) { // weighted mass: nq = 1 + 3nb/2 + 1 (MassMatrix.cpp:108)
+                CB_CASE(2, 5) CB_CASE(3, 6) CB_CASE(4, 8) CB_CASE(5, 9) CB_CASE(6, 11) CB_CASE(7, 12) CB_CASE(8, 14) CB_CASE(9, 15)
+            }
+#undef CB_CASE
+            return nullptr;
+        }
+    } // namespace
+
+    void VolumeOp::apply(double c, int accumulate, const double * x, double * y, cudaStream_t s)
+    {
+        Plan & plan = fem->get_plan();
+        PlanDev pd{plan.d_hdr.p, plan.d_gid.p, plan.d_slot.p, plan.d_L.p, plan.d_color_ptr.p, plan.PE};
+        LaunchFn fn = generic ? nullptr : (stiff ? find_instance<true>(nb, nq) : find_instance<false>(nb, nq));
+        if (fn)
+            fn(*this, pd, plan, c, accumulate, x, y, s);
+        else {
+            const int nwarps = std::min(8, plan.PE);
+            const int SCR = (stiff ? 2 : 1) * nq * nb;
+            size_t smem = sizeof(double) * ((size_t)2 * plan.max_pdof + (size_t)plan.PE * nb * nb + (size_t)nwarps * SCR) +
+                          sizeof(uint16_t) * (size_t)plan.PE * nb * nb;
+            smem = (smem + 15) & ~size_t(15);
+            CB_REQUIRE(smem <= 227 * 1024, "operator action: patch does not fit in shared memory for this (n_basis, n_quad)");
+            CB_CUDA(cudaFuncSetAttribute(volume_action_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)49152)));
+            volume_action_generic<<<(unsigned)plan.n_patches, nwarps * 32, smem, s>>>(nb, nq, stiff ? 1 : 0, d_P.p, d_D.p, pd, d_G.p, x, y,
+                                                                                      d_partial.p, c, accumulate, plan.max_pdof);
+            CB_LAUNCHED();
+        }
+        if (plan.n_shared > 0) {
+            assemble_shared_kernel<<<blocks_for(plan.n_shared, 256), 256, 0, s>>>(plan.n_shared, plan.d_sh_gid.p, plan.d_sh_ptr.p,
+                                                                                  d_partial.p, y, c, accumulate);
+            CB_LAUNCHED();
+        }
+    }
+
+    size_t VolumeOp::algorithmic_bytes() const
+    {
+        // stiffness 24nq^2 + 4nb^2 + 16(nb-1)^2 ; mass 8nq^2 + 4nb^2 + 16(nb-1)^2 bytes per element
+        const size_t per = (size_t)(stiff ? 24 : 8) * nq * nq + 4 * (size_t)nb * nb + 16 * (size_t)(nb - 1) * (nb - 1);
+        return per * (size_t)fem->n_elem;
+    }
+
+    namespace
+    {
+        void init_volume_common(VolumeOp & op, H1Space * fem, int nq, bool stiff, bool force_generic)
+        {
+            op.fem = fem;
+            op.nb = fem->nb;
+            op.nq = nq;
+            op.stiff = stiff;
+            CB_REQUIRE(nq >= 1 && nq <= MAXQ, stiff ? "StiffnessMatrix::action does not support quadrature rules with more than 24 points."
+                                                    : "MassMatrix error: quadrature rules with more than 32 points not yet supported.");
+            LaunchFn fn = stiff ? find_instance<true>(op.nb, nq) : find_instance<false>(op.nb, nq);
+            op.generic = force_generic || (fn == nullptr);
+            op.epw = op.generic ? 1 : 32 / nq;
+            op.lw = op.epw * nq;
+            op.nk = (stiff ? 3 : 1) * nq;
+            Plan & plan = fem->get_plan();
+            op.n_pass = (plan.PE + op.epw - 1) / op.epw;
+            op.d_partial.alloc((size_t)std::max<int64_t>(plan.n_slots_total, 1));
+            op.d_G.alloc((size_t)plan.n_patches * op.n_pass * op.nk * op.lw);
+            CB_CUDA(cudaMemset(op.d_G.p, 0, op.d_G.n * sizeof(double)));
+        }
+    } // namespace
+
+    std::unique_ptr<VolumeOp> make_stiffness(H1Space * fem, int nq, int quad_type)
+    {
+        std::unique_ptr<VolumeOp> op(new VolumeOp);
+        if (nq <= 0)
+            nq = fem->nb + 1; // mesh.max_element_order() (=1) + n_basis, StiffnessMatrix.cpp:45
+        CB_REQUIRE(nq <= 24, "StiffnessMatrix::action does not support quadrature rules with more than 24 points.");
+        init_volume_common(*op, fem, nq, true, getenv("CUDDH_B200_FORCE_GENERIC") != nullptr);
+        std::vector<double> xq(nq), wq(nq);
+        quadrature_rule(nq, quad_type, xq.data(), wq.data());
+        op->P.resize((size_t)nq * fem->nb);
+        op->D.resize((size_t)nq * fem->nb);
+        fem->basis->eval(nq, xq.data(), op->P.data());
+        fem->basis->deriv(nq, xq.data(), op->D.data());
+        op->d_P.upload(op->P);
+        op->d_D.upload(op->D);
+        DevBuf<double> d_x, d_w;
+        d_x.upload(xq);
+        d_w.upload(wq);
+        Plan & plan = fem->get_plan();
+        const int64_t n_slots = plan.n_patches * plan.PE;
+        setup_stiffness_kernel<<<blocks_for(n_slots * nq * nq, 256), 256>>>(n_slots, plan.PE, nq, op->epw, op->n_pass, plan.d_slot_elem.p,
+                                                                            fem->device_corners(), d_x.p, d_w.p, op->d_G.p);
+        CB_LAUNCHED();
+        CB_CUDA(cudaDeviceSynchronize());
+        return op;
+    }
+
+    std::unique_ptr<VolumeOp> make_mass(H1Space * fem, const double * d_coef, int nq)
+    {
+        std::unique_ptr<VolumeOp> op(new VolumeOp);
+        if (nq <= 0) // MassMatrix.cpp:74 (unweighted) / :108 (weighted)
+            nq = d_coef ? (1 + 3 * fem->nb / 2 + 1) : (fem->nb + 1);
+        init_volume_common(*op, fem, nq, false, getenv("CUDDH_B200_FORCE_GENERIC") != nullptr);
+        std::vector<double> xq(nq), wq(nq);
+        quadrature_rule(nq, GAUSS_LEGENDRE, xq.data(), wq.data());
+        op->P.resize((size_t)nq * fem->nb);
+        fem->basis->eval(nq, xq.data(), op->P.data());
+        op->d_P.upload(op->P);
+        DevBuf<double> d_x, d_w;
+        d_x.upload(xq);
+        d_w.upload(wq);
+        Plan & plan = fem->get_plan();
+        const int64_t n_slots = plan.n_patches * plan.PE;
+        setup_mass_kernel<<<blocks_for(n_slots * nq * nq, 256), 256>>>(n_slots, plan.PE, fem->nb, nq, op->epw, op->n_pass, plan.d_slot_elem.p,
+                                                                       fem->device_corners(), fem->device_I(), d_coef, op->d_P.p, d_x.p,
+                                                                       d_w.p, op->d_G.p);
+        CB_LAUNCHED();
+        CB_CUDA(cudaDeviceSynchronize());
+        return op;
+    }
+
+    void DiagOp::apply(double c, int accumulate, const double * x, double * y, cudaStream_t s)
+    {
+        if (n == 0)
+            return;
+        diag_apply_kernel<<<blocks_for(n, 256), 256, 0, s>>>(n, d_p.p, c, accumulate, x, y);
+        CB_LAUNCHED();
+    }
+
+    std::unique_ptr<DiagOp> make_diag_inv_mass(H1Space * fem, const double * d_coef)
+    {
+        // reference source/MassMatrix.cpp:241-314: p = 1 / sum_e w_i w_j detJ(x_i,x_j) [a], GLL collocation
+        std::unique_ptr<DiagOp> op(new DiagOp);
+        op->n = fem->ndof;
+        op->d_p.alloc((size_t)fem->ndof);
+        const int nb = fem->nb;
+        const int64_t N = (int64_t)nb * nb * fem->n_elem;
+        // transposed map (DOF -> element-local entries, ascending) for an ordered, atomic-free sum
+        std::vector<int> ptr((size_t)fem->ndof + 1, 0), src((size_t)N);
+        for (int64_t t = 0; t < N; ++t)
+            ptr[fem->I[t] + 1]++;
+        for (int64_t d = 0; d < fem->ndof; ++d)
+            ptr[d + 1] += ptr[d];
+        {
+            std::vector<int> cur(ptr.begin(), ptr.end() - 1);
+            for (int64_t t = 0; t < N; ++t)
+                src[cur[fem->I[t]]++] = (int)t;
+        }
+        DevBuf<int> d_ptr, d_src;
+        d_ptr.upload(ptr);
+        d_src.upload(src);
+        DevBuf<double> contrib((size_t)N), d_x, d_w;
+        d_x.upload(fem->basis->x);
+        d_w.upload(fem->basis->w);
+        diag_mass_contrib_kernel<<<blocks_for(N, 256), 256>>>(fem->n_elem, nb, fem->device_I(), fem->device_corners(), d_coef, d_x.p, d_w.p,
+                                                              contrib.p);
+        CB_LAUNCHED();
+        gather_sum_recip_kernel<<<blocks_for(fem->ndof, 256), 256>>>(fem->ndof, d_ptr.p, d_src.p, contrib.p, op->d_p.p);
+        CB_LAUNCHED();
+        CB_CUDA(cudaDeviceSynchronize());
+        return op;
+    }
+
+    std::unique_ptr<FaceMassOp> make_facemass(FaceSpace * fs, const double * d_coef, int nq)
+    {
+        std::unique_ptr<FaceMassOp> op(new FaceMassOp);
+        fs->ensure_device();
+        op->fs = fs;
+        op->nb = fs->nb;
+        if (nq <= 0) // FaceMassMatrix.cpp:56 / :103
+            nq = d_coef ? (1 + 3 * fs->nb / 2 + 1) : (fs->nb + 1);
+        CB_REQUIRE(nq <= 64, "FaceMassMatrix does not support quadrature rules with more than 64 points.");
+        op->nq = nq;
+        std::vector<double> xq(nq), wq(nq), P((size_t)nq * fs->nb);
+        quadrature_rule(nq, GAUSS_LEGENDRE, xq.data(), wq.data());
+        fs->fem->basis->eval(nq, xq.data(), P.data());
+        op->d_P.upload(P);
+        DevBuf<double> d_w;
+        d_w.upload(wq);
+        op->d_a.alloc((size_t)nq * fs->n_faces);
+        if (fs->n_faces > 0) {
+            setup_facemass_kernel<<<blocks_for(fs->n_faces * nq, 128), 128>>>(fs->n_faces, fs->nb, nq, d_w.p, op->d_P.p, fs->d_meas.p, d_coef,
+                                                                              fs->d_I.p, op->d_a.p);
+            CB_LAUNCHED();
+            CB_CUDA(cudaDeviceSynchronize());
+        }
+        return op;
+    }
+
+    void FaceMassOp::apply(double c, int accumulate, const double * x, double * y, cudaStream_t s)
+    {
+        if (fs->fdof == 0)
+            return;
+        facemass_action_kernel<<<blocks_for(fs->fdof, 128), 128, 0, s>>>(fs->fdof, nb, nq, d_P.p, d_a.p, fs->d_I.p, fs->d_inc_ptr.p,
+                                                                         fs->d_inc.p, nullptr, c, accumulate, x, y);
+        CB_LAUNCHED();
+    }
+
+    void FaceMassOp::apply_h1(double c, const double * x, double * y, cudaStream_t s)
+    {
+        if (fs->fdof == 0)
+            return;
+        facemass_action_kernel<<<blocks_for(fs->fdof, 128), 128, 0, s>>>(fs->fdof, nb, nq, d_P.p, d_a.p, fs->d_I.p, fs->d_inc_ptr.p,
+                                                                         fs->d_inc.p, fs->d_proj.p, c, 1, x, y);
+        CB_LAUNCHED();
+    }
+
+    std::unique_ptr<DiagOp> make_diag_inv_facemass(FaceSpace * fs, const double * d_coef)
+    {
+        // reference source/FaceMassMatrix.cpp:226-270
+        std::unique_ptr<DiagOp> op(new DiagOp);
+        fs->ensure_device();
+        op->n = fs->fdof;
+        op->d_p.alloc((size_t)std::max<int64_t>(fs->fdof, 1));
+        DevBuf<double> d_w;
+        d_w.upload(fs->fem->basis->w);
+        if (fs->fdof > 0) {
+            diag_facemass_kernel<<<blocks_for(fs->fdof, 128), 128>>>(fs->fdof, fs->nb, d_w.p, fs->d_meas.p, d_coef, fs->d_inc_ptr.p,
+                                                                     fs->d_inc.p, op->d_p.p);
+            CB_LAUNCHED();
+            CB_CUDA(cudaDeviceSynchronize());
+        }
+        return op;
+    }
+
+    void face_restrict(FaceSpace * fs, const double * x, double * y, cudaStream_t s)
+    {
+        if (fs->fdof == 0)
+            return;
+        fs->ensure_device();
+        restrict_kernel<<<blocks_for(fs->fdof, 256), 256, 0, s>>>(fs->fdof, fs->d_proj.p, x, y);
+        CB_LAUNCHED();
+    }
+    void face_prolong(FaceSpace * fs, const double * x, double * y, cudaStream_t s)
+    {
+        if (fs->fdof == 0)
+            return;
+        fs->ensure_device();
+        prolong_kernel<<<blocks_for(fs->fdof, 256), 256, 0, s>>>(fs->fdof, fs->d_proj.p, x, y);
+        CB_LAUNCHED();
+    }
+    void face_orth(FaceSpace * fs, double * x, cudaStream_t s)
+    {
+        if (fs->fdof == 0)
+            return;
+        fs->ensure_device();
+        orth_kernel<<<blocks_for(fs->fdof, 256), 256, 0, s>>>(fs->fdof, fs->d_proj.p, x);
+        CB_LAUNCHED();
+    }
+
+    std::unique_ptr<HelmholtzOp> make_helmholtz(double omega, const double * d_a2, const double * d_a, H1Space * fem, FaceSpace * fs)
+    {
+        std::unique_ptr<HelmholtzOp> op(new HelmholtzOp);
+        op->omega = omega;
+        op->fem = fem;
+        op->fs = fs;
+        op->S = make_stiffness(fem, 0, GAUSS_LEGENDRE);
+        op->M = make_mass(fem, d_a2, 0);
+        op->H = make_facemass(fs, d_a, 0);
+        return op;
+    }
+
+    void HelmholtzOp::apply(const double * x, double * y, cudaStream_t s)
+    {
+        // examples/Helmholtz.hpp:28-56:  Au = S u - w^2 M u - w H v ;  Av = -(S v - w^2 M v + w H u)
+        // 6 launches + 4 tiny assembly passes instead of the reference's 11 kernels + 4 memsets.
+        const int64_t n = fem->ndof;
+        const double * u = x;
+        const double * v = x + n;
+        double * Au = y;
+        double * Av = y + n;
+        S->apply(1.0, 0, u, Au, s);
+        S->apply(1.0, 0, v, Av, s);
+        M->apply(-omega * omega, 1, u, Au, s);
+        M->apply(-omega * omega, 1, v, Av, s);
+        H->apply_h1(-omega, v, Au, s);
+        H->apply_h1(omega, u, Av, s);
+        negate_kernel<<<blocks_for(n, 256), 256, 0, s>>>(n, Av);
+        CB_LAUNCHED();
+    }
+} // namespace cb200

@@ -1,0 +1,64 @@
+// Operator objects behind the C ABI (FP64 path A of SURVEY §8a): stiffness, mass, face mass, their
+// diagonal inverses, face restrict/prolong/orth and the fused Helmholtz composite.
+#pragma once
+#include "common.hpp"
+
+namespace cb200
+{
+    // y = (accumulate ? y : 0) + c * A x  for a patch-planned volume operator
+    struct VolumeOp
+    {
+        H1Space * fem = nullptr;
+        int nb = 0, nq = 0;
+        bool stiff = false;
+        std::vector<double> P, D;     // (nq, nb) column-major tables
+        DevBuf<double> d_P, d_D;      // device copies (generic kernel)
+        DevBuf<double> d_G;           // plan-ordered metric data: stiffness 3 comps, mass 1 comp
+        DevBuf<double> d_partial;     // partial sums of patch-boundary DOFs
+        int epw = 0, lw = 0, n_pass = 0, nk = 0;  // layout constants (see operators.cu)
+        bool generic = false;
+
+        void apply(double c, int accumulate, const double * x, double * y, cudaStream_t s);
+        size_t algorithmic_bytes() const; // SURVEY §8(d) per-element bytes * n_elem
+    };
+
+    std::unique_ptr<VolumeOp> make_stiffness(H1Space * fem, int nq, int quad_type);
+    std::unique_ptr<VolumeOp> make_mass(H1Space * fem, const double * d_coef /* device nodal coefficient or null */, int nq /* <=0: reference default */);
+
+    struct DiagOp // y (+)= c * p .* x
+    {
+        int64_t n = 0;
+        DevBuf<double> d_p;
+        void apply(double c, int accumulate, const double * x, double * y, cudaStream_t s);
+    };
+    std::unique_ptr<DiagOp> make_diag_inv_mass(H1Space * fem, const double * d_coef);
+
+    struct FaceMassOp
+    {
+        FaceSpace * fs = nullptr;
+        int nb = 0, nq = 0;
+        DevBuf<double> d_P, d_a; // P (nq,nb); a (nq, n_faces) = coef * w * measure
+        // face-space vectors
+        void apply(double c, int accumulate, const double * x, double * y, cudaStream_t s);
+        // fused restrict + action + prolong on H1 vectors: y[proj] += c * H * x[proj]
+        void apply_h1(double c, const double * x, double * y, cudaStream_t s);
+    };
+    std::unique_ptr<FaceMassOp> make_facemass(FaceSpace * fs, const double * d_coef /* device face-space coefficient or null */, int nq);
+    std::unique_ptr<DiagOp> make_diag_inv_facemass(FaceSpace * fs, const double * d_coef);
+
+    void face_restrict(FaceSpace * fs, const double * x, double * y, cudaStream_t s);
+    void face_prolong(FaceSpace * fs, const double * x, double * y, cudaStream_t s);
+    void face_orth(FaceSpace * fs, double * x, cudaStream_t s);
+
+    // examples/Helmholtz.hpp:28-56 composite on [u;v]
+    struct HelmholtzOp
+    {
+        double omega = 0;
+        H1Space * fem = nullptr;
+        FaceSpace * fs = nullptr;
+        std::unique_ptr<VolumeOp> S, M;
+        std::unique_ptr<FaceMassOp> H;
+        void apply(const double * x, double * y, cudaStream_t s);
+    };
+    std::unique_ptr<HelmholtzOp> make_helmholtz(double omega, const double * d_a2, const double * d_a, H1Space * fem, FaceSpace * fs);
+} // namespace cb200

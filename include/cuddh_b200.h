@@ -1,0 +1,163 @@
+/* cuddh_b200.h — C ABI of libcuddh_b200.so: the B200 (sm_100a) implementation of CuDDHelmholtz's solve path.
+ *
+ * This is the drop-in boundary. Every entry point states the reference interface it replaces
+ * (file:line relative to the reference tree). Conventions, all taken from the reference:
+ *   - every `const double*` / `double*` / `float*` vector argument named x, y, b, u, f, lambda is a DEVICE
+ *     pointer (include/gmres.hpp:25-33, include/H1Space.hpp:112-126); arrays named h_* or documented "host"
+ *     are HOST pointers;
+ *   - arrays are column-major, first index fastest (include/Tensor.hpp:31-47);
+ *   - x and y of an action must not alias.
+ * Differences by design: explicit stream argument (a cudaStream_t passed as void*; NULL = legacy default
+ * stream, which is what the reference always uses), 64-bit sizes, and status codes instead of abort():
+ * every function returns 0 on success or a non-zero code, with the text available from
+ * cuddh_b200_last_error(). The C++ classes in cuddhelmholtz_b200/cxx map non-zero to cuddh_error().
+ *
+ * No torch / C++ types cross this boundary.
+ */
+#ifndef CUDDH_B200_H
+#define CUDDH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cuddh_mesh_s * cuddh_mesh_t;
+typedef struct cuddh_basis_s * cuddh_basis_t;
+typedef struct cuddh_h1space_s * cuddh_h1space_t;
+typedef struct cuddh_facespace_s * cuddh_facespace_t;
+typedef struct cuddh_operator_s * cuddh_operator_t;   /* any FP64 operator: y (+)= c*A*x */
+typedef struct cuddh_ddh_s * cuddh_ddh_t;
+
+#define CUDDH_GAUSS_LEGENDRE 0
+#define CUDDH_GAUSS_LOBATTO 1
+
+/* ---- library ------------------------------------------------------------------------------------ */
+int cuddh_b200_version(void);
+const char * cuddh_b200_last_error(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t cuddh_b200_launch_count(void);
+
+/* ---- 1-D tables: QuadratureRule(n, type) include/QuadratureRule.hpp:31 ; Basis(n) include/Basis.hpp:16 --- */
+int cuddh_b200_quadrature(int n, int type, double * h_x, double * h_w);
+int cuddh_b200_basis_create(int n, cuddh_basis_t * out);
+int cuddh_b200_basis_destroy(cuddh_basis_t b);
+/* Basis::eval / Basis::deriv (include/Basis.hpp:30,37): P, D have shape (m, n) column-major, host */
+int cuddh_b200_basis_eval(cuddh_basis_t b, int m, const double * h_x, double * h_P);
+int cuddh_b200_basis_deriv(cuddh_basis_t b, int m, const double * h_x, double * h_D);
+int cuddh_b200_basis_nodes(cuddh_basis_t b, double * h_x, double * h_w);   /* Basis::quadrature() */
+
+/* ---- Mesh2D: include/Mesh2D.hpp:266-277 --------------------------------------------------------- */
+int cuddh_b200_mesh_uniform_rect(int nx, double ax, double bx, int ny, double ay, double by, cuddh_mesh_t * out);
+int cuddh_b200_mesh_from_vertices(int64_t nv, const double * h_xy /* (2,nv) */, int64_t nel, const int * h_elems /* (4,nel) */,
+                                  cuddh_mesh_t * out);
+int cuddh_b200_mesh_destroy(cuddh_mesh_t m);
+/* sizes[0..4] = n_elem, n_nodes, n_edges, n_boundary_edges, n_interior_edges (Mesh2D::n_elem/n_nodes/n_edges) */
+int cuddh_b200_mesh_sizes(cuddh_mesh_t m, int64_t * sizes);
+/* (8, n_edges) records: nodes[0], nodes[1], elements[0], elements[1], sides[0], sides[1], delta, is_boundary
+ * (include/Edge.hpp:25-52; elements[1]/sides[1] = -1 on the boundary) */
+int cuddh_b200_mesh_edges(cuddh_mesh_t m, int * h_edges);
+int cuddh_b200_mesh_boundary_edges(cuddh_mesh_t m, int * h_list);     /* Mesh2D::boundary_edges() */
+int cuddh_b200_mesh_h(cuddh_mesh_t m, double * min_h, double * max_h); /* Mesh2D::min_h / max_h */
+
+/* ---- H1Space: include/H1Space.hpp:21-65 --------------------------------------------------------- */
+int cuddh_b200_h1space_create(cuddh_mesh_t mesh, int n_basis, cuddh_h1space_t * out);
+int cuddh_b200_h1space_destroy(cuddh_h1space_t s);
+int64_t cuddh_b200_h1space_size(cuddh_h1space_t s);                       /* H1Space::size() */
+int cuddh_b200_h1space_global_indices(cuddh_h1space_t s, int * h_I);      /* (nb,nb,n_elem) host copy */
+int cuddh_b200_h1space_physical_coordinates(cuddh_h1space_t s, double * h_xy); /* (2,ndof) host copy */
+const int * cuddh_b200_h1space_device_indices(cuddh_h1space_t s);         /* global_indices(DEVICE) */
+const double * cuddh_b200_h1space_device_coordinates(cuddh_h1space_t s);  /* physical_coordinates(DEVICE) */
+
+/* ---- FaceSpace: include/H1Space.hpp:69-147 ------------------------------------------------------ */
+int cuddh_b200_facespace_create(cuddh_h1space_t s, int64_t n_faces, const int * h_faces, cuddh_facespace_t * out);
+int cuddh_b200_facespace_destroy(cuddh_facespace_t f);
+int64_t cuddh_b200_facespace_size(cuddh_facespace_t f);
+int cuddh_b200_facespace_subspace_indices(cuddh_facespace_t f, int * h_I);   /* (nb, n_faces) */
+int cuddh_b200_facespace_global_indices(cuddh_facespace_t f, int * h_proj);  /* (fdof) */
+int cuddh_b200_facespace_restrict(cuddh_facespace_t f, const double * x, double * y, void * stream); /* y[i] = x[proj[i]] */
+int cuddh_b200_facespace_prolong(cuddh_facespace_t f, const double * x, double * y, void * stream);  /* y[proj[i]] += x[i] */
+int cuddh_b200_facespace_orth(cuddh_facespace_t f, double * x, void * stream);                        /* x[proj[i]] = 0 */
+
+/* ---- operators: Operator::action include/Operator.hpp:12-16 ------------------------------------- */
+/* StiffnessMatrix(fem) / StiffnessMatrix(fem, quad): include/StiffnessMatrix.hpp:14-15. n_quad <= 0 -> n_basis + 1 Gauss-Legendre */
+int cuddh_b200_stiffness_create(cuddh_h1space_t s, int n_quad, int quad_type, cuddh_operator_t * out);
+/* MassMatrix(fem) / MassMatrix(a, fem): include/MassMatrix.hpp:19-24. d_a: DEVICE nodal coefficient or NULL; n_quad <= 0 -> reference default */
+int cuddh_b200_mass_create(cuddh_h1space_t s, const double * d_a, int n_quad, cuddh_operator_t * out);
+/* DiagInvMassMatrix(fem) / (a, fem): include/MassMatrix.hpp:47-54 */
+int cuddh_b200_diag_inv_mass_create(cuddh_h1space_t s, const double * d_a, cuddh_operator_t * out);
+/* FaceMassMatrix(fs) / (a, fs): include/FaceMassMatrix.hpp ; vectors are FaceSpace vectors */
+int cuddh_b200_facemass_create(cuddh_facespace_t f, const double * d_a, int n_quad, cuddh_operator_t * out);
+int cuddh_b200_diag_inv_facemass_create(cuddh_facespace_t f, const double * d_a, cuddh_operator_t * out);
+/* the Helmholtz composite of examples/Helmholtz.hpp:10-80 on x = [u; v] (length 2*ndof) */
+int cuddh_b200_helmholtz_create(double omega, const double * d_a2, const double * d_a, cuddh_h1space_t s, cuddh_facespace_t f,
+                                cuddh_operator_t * out);
+/* y <- (accumulate ? y : 0) + c * A * x.  action(c,x,y) == apply(op,c,1,..); action(x,y) == apply(op,1.0,0,..) */
+int cuddh_b200_operator_apply(cuddh_operator_t op, double c, int accumulate, const double * x, double * y, void * stream);
+/* fused FaceSpace::restrict + FaceMassMatrix::action + FaceSpace::prolong on H1 vectors: y[proj] += c*H*x[proj] */
+int cuddh_b200_facemass_apply_h1(cuddh_operator_t op, double c, const double * x, double * y, void * stream);
+int cuddh_b200_operator_destroy(cuddh_operator_t op);
+/* algorithmic bytes of one apply, 0 if not defined for this operator */
+int64_t cuddh_b200_operator_bytes(cuddh_operator_t op);
+
+/* ---- linalg: include/linalg.hpp:16-54 (double and float) ---------------------------------------- */
+int cuddh_b200_axpby_d(int64_t n, double a, const double * x, double b, double * y, void * stream);
+int cuddh_b200_axpby_f(int64_t n, float a, const float * x, float b, float * y, void * stream);
+int cuddh_b200_dot_d(int64_t n, const double * x, const double * y, double * h_result, void * stream);
+int cuddh_b200_dot_f(int64_t n, const float * x, const float * y, float * h_result, void * stream);
+int cuddh_b200_dist_d(int64_t n, const double * x, const double * y, double * h_result, void * stream);
+int cuddh_b200_dist_f(int64_t n, const float * x, const float * y, float * h_result, void * stream);
+int cuddh_b200_copy_d(int64_t n, const double * x, double * y, void * stream);
+int cuddh_b200_copy_f(int64_t n, const float * x, float * y, void * stream);
+int cuddh_b200_copy_i(int64_t n, const int * x, int * y, void * stream);
+int cuddh_b200_scal_d(int64_t n, double a, double * x, void * stream);
+int cuddh_b200_scal_f(int64_t n, float a, float * x, void * stream);
+int cuddh_b200_fill_d(int64_t n, double a, double * x, void * stream);
+int cuddh_b200_fill_f(int64_t n, float a, float * x, void * stream);
+int cuddh_b200_fill_i(int64_t n, int a, int * x, void * stream);
+
+/* ---- gmres: include/gmres.hpp:14-36 ------------------------------------------------------------- */
+typedef void (*cuddh_apply_d_fn)(void * ctx, const double * x, double * y); /* must enqueue y = A x (device pointers) */
+typedef void (*cuddh_apply_f_fn)(void * ctx, const float * x, float * y);
+typedef struct
+{
+    int success;      /* solver_out.success */
+    int num_iter;     /* solver_out.num_iter */
+    int num_matvec;   /* solver_out.num_matvec */
+    int n_res;        /* entries written to res_norm / time (<= cap) */
+} cuddh_solver_out;
+/* P == NULL: gmres(n,x,A,b,m,maxit,tol,verbose,max_seconds); otherwise the left-preconditioned overload.
+ * res_norm / time: HOST arrays of capacity `cap` (>= maxit+1 to get everything) or NULL. */
+int cuddh_b200_gmres_d(int64_t n, double * x, cuddh_apply_d_fn A, void * A_ctx, const double * b, cuddh_apply_d_fn P, void * P_ctx,
+                       int m, int maxit, double tol, int verbose, double max_seconds, cuddh_solver_out * out, double * h_res_norm,
+                       double * h_time, int cap, void * stream);
+int cuddh_b200_gmres_f(int64_t n, float * x, cuddh_apply_f_fn A, void * A_ctx, const float * b, int m, int maxit, float tol,
+                       int verbose, double max_seconds, cuddh_solver_out * out, double * h_res_norm, double * h_time, int cap,
+                       void * stream);
+/* convenience trampolines so that a cuddh_operator_t / cuddh_ddh_t can be handed to gmres without a host callback */
+void cuddh_b200_operator_as_apply(void * op_handle, const double * x, double * y);
+void cuddh_b200_ddh_as_apply(void * ddh_handle, const float * x, float * y);
+
+/* ---- DDH: include/DDH.hpp:21-84 ----------------------------------------------------------------- */
+/* DDH(omega, h_a, fem, nx, ny): h_a HOST nodal coefficient (length ndof). block = 1-D node size of a subdomain
+ * (the reference's compile-time DDH_BLOCK_SIZE, source/DDH.cpp:5): 16 or 32. */
+int cuddh_b200_ddh_create(double omega, const double * h_a, cuddh_h1space_t s, int nx, int ny, int block, cuddh_ddh_t * out);
+int cuddh_b200_ddh_destroy(cuddh_ddh_t d);
+int64_t cuddh_b200_ddh_size(cuddh_ddh_t d);                                    /* DDH::size() = 2*n_lambda */
+int cuddh_b200_ddh_rhs(cuddh_ddh_t d, const double * f, float * b, void * stream);                 /* DDH::rhs */
+int cuddh_b200_ddh_action(cuddh_ddh_t d, const float * x, float * y, void * stream);               /* DDH::action */
+int cuddh_b200_ddh_postprocess(cuddh_ddh_t d, const float * lambda, const double * f, double * u, void * stream); /* DDH::postprocess */
+/* introspection for parity tests: info[0..7] = n_domains, n_shared, nt, mx_dof, mx_fdof, mx_elem_per_dom, n_basis, block ; dt */
+int cuddh_b200_ddh_info(cuddh_ddh_t d, int64_t * info, double * dt);
+/* host copies of the index / coefficient arrays in the reference's layouts (names as in source/DDH.cpp):
+ * "B" (mx_fdof,2,dom) int, "gI" (mx_dof,dom) int, "sI" (nb,nb,mx_elem,dom) int, "cmap" (4,n_shared) int,
+ * "m","gmi","a" (mx_dof,dom) float, "H" (mx_fdof,dom) float, "wh_filter" (nt+1) float. Returns element count in *count. */
+int cuddh_b200_ddh_get_array(cuddh_ddh_t d, const char * name, void * h_out, int64_t cap_bytes, int64_t * count);
+/* algorithmic FP32 flops of one action */
+double cuddh_b200_ddh_flops(cuddh_ddh_t d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,403 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+
+Tolerances: FP64 operator actions 1e-12 relative in l2 (north_star); FP32 DDH action 2e-4 relative for one action
+(5*nt*2 chained FP32 stiffness applies), GMRES iteration counts within +-1."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cuddhelmholtz_b200 as cb
+from conftest import load_mesh_file
+from gpu_util import as_tensor, dev, host, rel
+from oracle import ops as O
+from oracle import setup_np as S
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def make(kind, nb, nx=10):
+    if kind == "rect":
+        om = S.uniform_rect(nx, -1.0, 1.0, nx, -1.0, 1.0)
+        pm = cb.Mesh2D.uniform_rect(nx, -1.0, 1.0, nx, -1.0, 1.0)
+    elif kind == "rect_aniso":  # non-square elements, ragged patch tiling (nx, ny not multiples of the patch shape)
+        om = S.uniform_rect(13, -1.0, 2.0, 7, 0.0, 1.0)
+        pm = cb.Mesh2D.uniform_rect(13, -1.0, 2.0, 7, 0.0, 1.0)
+    else:
+        xy, el = load_mesh_file()
+        om = S.mesh_from_vertices(xy, el)
+        pm = cb.Mesh2D.from_vertices(xy, el)
+    ofem = O.H1(om, nb)
+    pfem = cb.H1Space(pm, cb.Basis(nb))
+    assert np.array_equal(pfem.global_indices().ravel(), ofem.I)
+    return om, pm, ofem, pfem
+
+
+def vec(n, seed):
+    return np.random.default_rng(seed).uniform(-1.0, 1.0, n)
+
+
+@pytest.mark.parametrize("kind", ["rect", "unstr", "rect_aniso"])
+@pytest.mark.parametrize("nb", [2, 3, 4, 5, 6, 7, 8, 9])
+def test_stiffness_and_mass_actions(kind, nb):
+    om, pm, ofem, pfem = make(kind, nb)
+    n = ofem.ndof
+    x = vec(n, 1)
+    a2 = 1.0 + 0.5 * np.sin(np.pi * ofem.xy[:, 0]) * np.cos(np.pi * ofem.xy[:, 1])
+    dx, da = dev(x), dev(a2)
+    y = torch.full((n,), 7.0, dtype=torch.float64, device="cuda")  # garbage: action(x,y) must overwrite
+
+    cases = [("S", cb.StiffnessMatrix(pfem), O.StiffnessMatrix(ofem))]
+    if 3 <= nb <= 8:
+        cases.append(("S_q2", cb.StiffnessMatrix(pfem, cb.QuadratureRule(nb + 2, cb.GaussLegendre)), O.StiffnessMatrix(ofem, nb + 2)))
+    cases.append(("M", cb.MassMatrix(pfem), O.MassMatrix(ofem)))
+    cases.append(("Mw", cb.MassMatrix(da, pfem), O.MassMatrix(ofem, a2)))
+    for name, P, R in cases:
+        P.action(dx, y)
+        ref = R.action(x)
+        assert rel(host(y), ref) < TOL, (name, rel(host(y), ref))
+        # y <- y + c A x on a non-trivial y
+        y0 = vec(n, 2)
+        dy = dev(y0)
+        P.action(-0.75, dx, dy)
+        ref2 = R.action(x, y0.copy(), -0.75)
+        assert rel(host(dy), ref2) < TOL, (name, "acc")
+        # bitwise reproducible (deterministic assembly; the reference's atomicAdd scatter is not)
+        y2 = torch.empty_like(y)
+        P.action(dx, y2)
+        assert torch.equal(y, y2), name
+
+
+def test_generic_kernel_path():
+    # a (nb, nq) pair without a template instance and the forced-generic switch must give the same answers
+    om, pm, ofem, pfem = make("unstr", 5)
+    x = vec(ofem.ndof, 3)
+    dx = dev(x)
+    y = torch.empty_like(dx)
+    P = cb.StiffnessMatrix(pfem, cb.QuadratureRule(12, cb.GaussLegendre))
+    P.action(dx, y)
+    assert rel(host(y), O.StiffnessMatrix(ofem, 12).action(x)) < TOL
+    os.environ["CUDDH_B200_FORCE_GENERIC"] = "1"
+    try:
+        Pg = cb.MassMatrix(pfem)
+        Sg = cb.StiffnessMatrix(pfem)
+    finally:
+        del os.environ["CUDDH_B200_FORCE_GENERIC"]
+    Pg.action(dx, y)
+    assert rel(host(y), O.MassMatrix(ofem).action(x)) < TOL
+    Sg.action(dx, y)
+    assert rel(host(y), O.StiffnessMatrix(ofem).action(x)) < TOL
+
+
+def test_reference_analytic_kats_on_gpu():
+    # tests/mass.cpp forward error (1e-8) and tests/stiffness.cpp (1e-6) with the operators computed on the GPU
+    from test_oracle_golden import _lf
+    for kind in ("rect", "unstr"):
+        for nb in (3, 4, 5, 6, 7, 8):
+            om, pm, ofem, pfem = make(kind, nb)
+            X, Y = ofem.xy[:, 0], ofem.xy[:, 1]
+            fm = 3 * X * X - 2 * X * Y + Y + 1
+            y = torch.empty(ofem.ndof, dtype=torch.float64, device="cuda")
+            cb.MassMatrix(pfem).action(dev(fm), y)
+            b = _lf(ofem, nb + 2, lambda x, y_: 3 * x * x - 2 * x * y_ + y_ + 1)
+            assert rel(host(y), b) < 1e-8
+            if nb >= 6:
+                f = (X ** 5 - 5 * X) * (Y ** 3 - 3 * Y)
+                cb.StiffnessMatrix(pfem, cb.QuadratureRule(nb + 2, cb.GaussLegendre)).action(dev(f), y)
+                L = _lf(ofem, nb + 2, lambda x, y_: -6.0 * y_ * (x ** 5 - 5 * x) - 20.0 * x ** 3 * (y_ ** 3 - 3.0 * y_))
+                assert rel(host(y), L) < 1e-6
+
+
+@pytest.mark.parametrize("kind", ["rect", "unstr"])
+@pytest.mark.parametrize("nb", [2, 4, 5, 8, 9])
+def test_face_operators(kind, nb):
+    om, pm, ofem, pfem = make(kind, nb)
+    ofs = O.FaceSpace(ofem, om.boundary_edges)
+    pfs = cb.FaceSpace(pfem, pm.boundary_edges())
+    n, nf = ofem.ndof, ofs.fdof
+    assert pfs.size() == nf
+    x = vec(n, 4)
+    dx = dev(x)
+    xf = torch.empty(nf, dtype=torch.float64, device="cuda")
+    pfs.restrict(dx, xf)
+    assert np.array_equal(host(xf), ofs.restrict(x))
+    af = 1.0 + 0.5 * np.sin(np.pi * ofem.xy[ofs.proj, 0]) * np.cos(np.pi * ofem.xy[ofs.proj, 1])
+    daf = dev(af)
+    yf = torch.empty_like(xf)
+    for P, R in [(cb.FaceMassMatrix(pfs), O.FaceMassMatrix(ofs)), (cb.FaceMassMatrix(daf, pfs), O.FaceMassMatrix(ofs, af))]:
+        P.action(xf, yf)
+        ref = R.action(ofs.restrict(x))
+        assert rel(host(yf), ref) < TOL
+        yacc = dev(vec(nf, 5))
+        P.action(2.5, xf, yacc)
+        assert rel(host(yacc), R.action(ofs.restrict(x), vec(nf, 5), 2.5)) < TOL
+        # fused restrict + action + prolong
+        y0 = vec(n, 6)
+        dy = dev(y0)
+        P.action_h1(-1.5, dx, dy)
+        want = ofs.prolong(R.action(ofs.restrict(x), None, -1.5), y0.copy())
+        assert rel(host(dy), want) < TOL
+    for P, R in [(cb.DiagInvFaceMassMatrix(pfs), O.DiagInvFaceMassMatrix(ofs)), (cb.DiagInvFaceMassMatrix(daf, pfs), O.DiagInvFaceMassMatrix(ofs, af))]:
+        P.action(xf, yf)
+        assert rel(host(yf), R.action(ofs.restrict(x))) < TOL
+    # prolong / orth
+    y0 = vec(n, 7)
+    dy = dev(y0)
+    pfs.prolong(xf, dy)
+    assert np.array_equal(host(dy), ofs.prolong(ofs.restrict(x), y0.copy()))
+    pfs.orth(dy)
+    assert np.array_equal(host(dy), ofs.orth(ofs.prolong(ofs.restrict(x), y0.copy())))
+    # lumped inverse mass
+    a2 = 1.0 + 0.5 * np.sin(np.pi * ofem.xy[:, 0]) * np.cos(np.pi * ofem.xy[:, 1])
+    y = torch.empty_like(dx)
+    cb.DiagInvMassMatrix(pfem).action(dx, y)
+    assert rel(host(y), O.DiagInvMassMatrix(ofem).action(x)) < TOL
+    cb.DiagInvMassMatrix(dev(a2), pfem).action(dx, y)
+    assert rel(host(y), O.DiagInvMassMatrix(ofem, a2).action(x)) < TOL
+
+
+@pytest.mark.parametrize("kind,nb", [("rect", 4), ("rect", 5), ("unstr", 5), ("unstr", 8)])
+def test_helmholtz_composite(kind, nb):
+    om, pm, ofem, pfem = make(kind, nb)
+    ofs = O.FaceSpace(ofem, om.boundary_edges)
+    pfs = cb.FaceSpace(pfem, pm.boundary_edges())
+    n = ofem.ndof
+    c = 1.0 + 0.5 * np.sin(np.pi * ofem.xy[:, 0]) * np.cos(np.pi * ofem.xy[:, 1])
+    a2, af = c * c, c[ofs.proj]
+    omega = 10.0
+    A = cb.Helmholtz(omega, dev(a2), dev(af), pfem, pfs)
+    R = O.Helmholtz(omega, a2, af, ofem, ofs)
+    x = vec(2 * n, 8)
+    y = torch.empty(2 * n, dtype=torch.float64, device="cuda")
+    A.action(dev(x), y)
+    assert rel(host(y), R.action(x)) < TOL
+    with pytest.raises(cb.CuddhError):  # examples/Helmholtz.hpp:62-65
+        A.action(1.0, dev(x), y)
+
+
+def test_linalg():
+    # tests/linalg.cpp:7-259
+    n = 1024 * 37 + 5
+    for dt_, tol in [(torch.float64, 1e-12), (torch.float32, 1e-4)]:
+        g = torch.Generator(device="cpu").manual_seed(0)
+        hx = torch.rand(n, generator=g, dtype=dt_)
+        hy = torch.rand(n, generator=g, dtype=dt_)
+        x, y = hx.cuda(), hy.cuda()
+        d = cb.dot(n, x, y)
+        ref = float(np.dot(hx.double().numpy(), hy.double().numpy()))
+        assert abs(d - ref) < tol * abs(ref)
+        assert abs(cb.dist(n, x, y) - float(np.linalg.norm(hx.double().numpy() - hy.double().numpy()))) < tol * 100
+        assert cb.dot(n, x, y) == d  # deterministic reduction
+        y2 = y.clone()
+        cb.axpby(n, 2.0, x, -0.5, y2)
+        assert torch.allclose(y2.cpu(), 2.0 * hx - 0.5 * hy, rtol=1e-12 if dt_ == torch.float64 else 1e-6)
+        cb.copy(n, x, y2)
+        assert torch.equal(y2, x)
+        cb.scal(n, 3.0, y2)
+        assert torch.equal(y2.cpu(), 3.0 * hx)
+        cb.fill(n, 1.5, y2)
+        assert torch.equal(y2.cpu(), torch.full((n,), 1.5, dtype=dt_))
+    xi = torch.zeros(100, dtype=torch.int32, device="cuda")
+    cb.fill(100, 7, xi)
+    yi = torch.zeros_like(xi)
+    cb.copy(100, xi, yi)
+    assert int(yi.sum()) == 700
+
+
+class Toeplitz:
+    """tests/gmres.cpp:8-39: user-defined operator receiving raw device pointers through the callback ABI."""
+
+    def __init__(self, n, dtype=torch.float64):
+        self.n, self.dtype = n, dtype
+
+    def action(self, xp, yp):
+        x = as_tensor(xp, self.n, self.dtype)
+        y = as_tensor(yp, self.n, self.dtype)
+        y.copy_(-3.0 * x)
+        y[1:] += 1.0 * x[:-1]
+        y[:-1] += 1.5 * x[1:]
+
+
+def test_gmres_toeplitz_kat():
+    n = 1 << 10
+    A = Toeplitz(n)
+    xt = torch.rand(n, dtype=torch.float64, device="cuda")
+    b = torch.empty_like(xt)
+    A.action(xt.data_ptr(), b.data_ptr())
+    x = torch.zeros_like(xt)
+    out = cb.gmres(n, x, A, b, 5, 100, 1e-10)
+    assert out.success
+    assert rel(host(x), host(xt)) < 1e-8
+    # same control flow as the reference restatement: identical iteration / matvec counts
+    xo = np.zeros(n)
+
+    def Anp(v):
+        y = -3.0 * v
+        y[1:] += 1.0 * v[:-1]
+        y[:-1] += 1.5 * v[1:]
+        return y
+
+    oo = O.gmres(n, xo, Anp, host(b), 5, 100, 1e-10)
+    assert out.num_iter == oo["num_iter"] and out.num_matvec == oo["num_matvec"]
+    assert np.allclose(out.res_norm, oo["res_norm"], rtol=1e-6, atol=1e-14)
+    # FP32 instantiation
+    A32 = Toeplitz(n, torch.float32)
+    b32 = b.float()
+    x32 = torch.zeros(n, dtype=torch.float32, device="cuda")
+    out32 = cb.gmres(n, x32, A32, b32, 5, 100, 1e-4)
+    assert out32.success and rel(host(x32), host(xt)) < 1e-3
+
+
+@pytest.mark.parametrize("kind", ["rect", "unstr"])
+def test_mass_solve_with_lumped_preconditioner(kind):
+    # tests/mass.cpp backward error: gmres(M, b, DiagInvMass, m=5, maxit=10, tol=1e-12) recovers nodal f to 1e-8
+    from test_oracle_golden import _lf
+    for nb in (3, 5, 8):
+        om, pm, ofem, pfem = make(kind, nb)
+        X, Y = ofem.xy[:, 0], ofem.xy[:, 1]
+        f = 3 * X * X - 2 * X * Y + Y + 1
+        b = _lf(ofem, nb + 2, lambda x, y_: 3 * x * x - 2 * x * y_ + y_ + 1)
+        M, Pm = cb.MassMatrix(pfem), cb.DiagInvMassMatrix(pfem)
+        u = torch.zeros(ofem.ndof, dtype=torch.float64, device="cuda")
+        out = cb.gmres(ofem.ndof, u, M, dev(b), 5, 10, 1e-12, P=Pm)
+        assert rel(host(u), f) < 1e-8
+        # iteration count parity with the restatement of the reference solver
+        oM, oP = O.MassMatrix(ofem), O.DiagInvMassMatrix(ofem)
+        uo = np.zeros(ofem.ndof)
+        oo = O.gmres(ofem.ndof, uo, lambda v: oM.action(v), b, 5, 10, 1e-12, P=lambda v: oP.action(v))
+        assert abs(out.num_iter - oo["num_iter"]) <= 1
+
+
+def test_helmholtz_gmres_iteration_parity():
+    # config 1a: unstructured mesh, n_basis 5, omega 10, FP64 GMRES(20), tol 1e-6
+    om, pm, ofem, pfem = make("unstr", 5)
+    ofs = O.FaceSpace(ofem, om.boundary_edges)
+    pfs = cb.FaceSpace(pfem, pm.boundary_edges())
+    n = ofem.ndof
+    omega = 10.0
+    c = 1.0 + 0.5 * np.sin(np.pi * ofem.xy[:, 0]) * np.cos(np.pi * ofem.xy[:, 1])
+    a2, af = c * c, c[ofs.proj]
+    A = cb.Helmholtz(omega, dev(a2), dev(af), pfem, pfs)
+    R = O.Helmholtz(omega, a2, af, ofem, ofs)
+    s = omega * omega
+    X, Y = ofem.xy[:, 0], ofem.xy[:, 1]
+    src = s / np.pi * np.exp(-s * ((X + 0.5) ** 2 + Y ** 2)) + s / np.pi * np.exp(-s * ((X - 0.5) ** 2 + (Y + 0.5) ** 2))
+    b = np.concatenate([O.MassMatrix(ofem).action(src), np.zeros(n)])
+    U = torch.zeros(2 * n, dtype=torch.float64, device="cuda")
+    out = cb.gmres(2 * n, U, A, dev(b), 20, 400, 1e-6)
+    Uo = np.zeros(2 * n)
+    oo = O.gmres(2 * n, Uo, R.action, b, 20, 400, 1e-6)
+    assert out.success and oo["success"]
+    assert abs(out.num_iter - oo["num_iter"]) <= 1, (out.num_iter, oo["num_iter"])
+    assert rel(host(U), Uo) < 1e-4
+    r = R.action(host(U)) - b
+    assert np.linalg.norm(r) < 1.01e-6 * np.linalg.norm(b)
+
+
+def _ddh_pair(nx, nb, omega, block=16, seed=0):
+    om = S.uniform_rect(nx, -1.0, 1.0, nx, -1.0, 1.0)
+    pm = cb.Mesh2D.uniform_rect(nx, -1.0, 1.0, nx, -1.0, 1.0)
+    ofem = O.H1(om, nb)
+    pfem = cb.H1Space(pm, cb.Basis(nb))
+    X, Y = ofem.xy[:, 0], ofem.xy[:, 1]
+    ha = np.where(X * X + Y * Y < 0.0625, 0.2, 1.0) + 0.05 * np.sin(3 * X)  # variable coefficient
+    oD = O.DDH(omega, ha, ofem, nx, nx, block)
+    pD = cb.DDH(omega, ha, pfem, nx, nx, block)
+    s = omega * omega
+    src = s / np.pi * np.exp(-s * ((X + 0.5) ** 2 + Y ** 2)) + s / np.pi * np.exp(-s * ((X - 0.5) ** 2 + (Y + 0.5) ** 2))
+    f = np.concatenate([O.MassMatrix(ofem).action(src), np.zeros(ofem.ndof)])
+    return ofem, pfem, oD, pD, f
+
+
+@pytest.mark.parametrize("nx,nb,block", [(8, 4, 16), (4, 8, 16), (16, 4, 32), (8, 8, 32)])
+def test_ddh_rhs_action_postprocess(nx, nb, block):
+    omega = 10.0
+    ofem, pfem, oD, pD, f = _ddh_pair(nx, nb, omega, block)
+    n = pD.size()
+    assert n == oD.size
+    df = dev(f)
+    b = torch.full((n,), 3.0, dtype=torch.float32, device="cuda")
+    pD.rhs(df, b)
+    bo = oD.rhs(f)
+    assert rel(host(b), bo) < 2e-4, rel(host(b), bo)
+    # orphan slots (never written by any subdomain) are zeroed explicitly
+    written = np.zeros(n, bool)
+    Bo = oD.d.B[:, 1, :]
+    idx = Bo[Bo >= 0]
+    written[idx] = True
+    written[oD.n_lambda + idx] = True
+    assert np.all(host(b)[~written] == 0.0)
+    lam = np.random.default_rng(2024).uniform(-1, 1, n).astype(np.float32)
+    lam[~written] = 0.0  # orphan components zeroed
+    y = torch.empty(n, dtype=torch.float32, device="cuda")
+    pD.action(dev(lam, torch.float32), y)
+    yo = oD.action(lam)
+    assert rel(host(y), yo) < 2e-4, rel(host(y), yo)
+    y2 = torch.empty_like(y)
+    pD.action(dev(lam, torch.float32), y2)
+    assert torch.equal(y, y2)  # deterministic (the reference's smem float atomics are not)
+    u = torch.empty(2 * ofem.ndof, dtype=torch.float64, device="cuda")
+    pD.postprocess(dev(lam, torch.float32), df, u)
+    uo = oD.postprocess(lam, f)
+    assert rel(host(u), uo) < 2e-4, rel(host(u), uo)
+
+
+def test_ddh_gmres_solve_parity():
+    # config 1b: uniform_rect(8), n_basis 4, omega 10, 4 subdomains, FP32 GMRES(20), maxit 100, tol 1e-4
+    omega = 10.0
+    ofem, pfem, oD, pD, f = _ddh_pair(8, 4, omega)
+    n = pD.size()
+    df = dev(f)
+    b = torch.empty(n, dtype=torch.float32, device="cuda")
+    pD.rhs(df, b)
+    L = torch.zeros(n, dtype=torch.float32, device="cuda")
+    out = cb.gmres(n, L, pD, b, 20, 100, 1e-4)
+    U = torch.empty(2 * ofem.ndof, dtype=torch.float64, device="cuda")
+    pD.postprocess(L, df, U)
+    bo = oD.rhs(f)
+    Lo = np.zeros(n, np.float32)
+    oo = O.gmres(n, Lo, oD.action, bo, 20, 100, 1e-4, dtype=np.float32)
+    Uo = oD.postprocess(Lo, f)
+    assert out.success and oo["success"]
+    assert abs(out.num_iter - oo["num_iter"]) <= 1, (out.num_iter, oo["num_iter"])
+    assert abs(out.num_matvec - oo["num_matvec"]) <= 2
+    assert rel(host(U), Uo) < 1e-3, rel(host(U), Uo)
+
+
+def test_full_size_properties():
+    # BASELINE config 2 size (uniform_rect(1024), n_basis 5): size-independent properties of the operators
+    nx, nb = 1024, 5
+    mesh = cb.Mesh2D.uniform_rect(nx, -1.0, 1.0, nx, -1.0, 1.0)
+    fem = cb.H1Space(mesh, cb.Basis(nb))
+    n = fem.size()
+    assert n == (nx * (nb - 1) + 1) ** 2
+    Sm, M = cb.StiffnessMatrix(fem), cb.MassMatrix(fem)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.rand(n, generator=g, dtype=torch.float64, device="cuda") - 0.5
+    z = torch.rand(n, generator=g, dtype=torch.float64, device="cuda") - 0.5
+    one = torch.ones(n, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(x)
+    y2 = torch.empty_like(x)
+    # constants are in the null space of the stiffness matrix; total mass = area of [-1,1]^2
+    Sm.action(one, y)
+    assert float(y.abs().max()) < 1e-11
+    M.action(one, y)
+    assert abs(float(y.sum()) - 4.0) < 1e-11
+    # symmetry: z.Sx == x.Sz ; linearity: S(2x - 3z) == 2Sx - 3Sz
+    Sm.action(x, y)
+    Sm.action(z, y2)
+    a, b = float(torch.dot(z, y)), float(torch.dot(x, y2))
+    assert abs(a - b) < 1e-11 * max(abs(a), 1.0)
+    comb = torch.empty_like(x)
+    Sm.action(2 * x - 3 * z, comb)
+    assert float((comb - (2 * y - 3 * y2)).norm() / comb.norm()) < 1e-13
+    # accumulate form against the plain form
+    acc = y.clone()
+    M.action(0.5, x, acc)
+    M.action(x, y2)
+    assert float((acc - (y + 0.5 * y2)).norm() / acc.norm()) < 1e-14
+    # bitwise reproducibility at full size
+    Sm.action(x, y2)
+    assert torch.equal(y, y2)

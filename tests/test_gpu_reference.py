@@ -1,0 +1,156 @@
+"""GPU: the CUDA path against the UNMODIFIED reference's own CUDA kernels, run on this box through
+oracle/_ref/ref_driver (built in the build container from the sources under /root/reference; see oracle/Makefile).
+This is "the reference itself run here": the strongest parity pin. Skipped when the prebuilt driver is absent."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+import cuddhelmholtz_b200 as cb
+from conftest import MESH_FILE, REF_DRIVER, load_mesh_file
+from gpu_util import dev, host, rel
+from oracle.rdmp import read_rdmp
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(REF_DRIVER), reason="oracle/_ref/ref_driver not built")]
+
+
+def ref(*args, timeout=600):
+    with tempfile.NamedTemporaryFile(suffix=".bin") as f:
+        subprocess.check_call([REF_DRIVER, *[str(a) for a in args], f.name], timeout=timeout)
+        return read_rdmp(f.name)
+
+
+def product_mesh(spec):
+    if spec.startswith("rect:"):
+        nx = int(spec[5:])
+        return cb.Mesh2D.uniform_rect(nx, -1.0, 1.0, nx, -1.0, 1.0)
+    xy, el = load_mesh_file()
+    return cb.Mesh2D.from_vertices(xy, el)
+
+
+@pytest.mark.parametrize("spec", ["rect:10", "file:" + MESH_FILE, "rect:64"])
+@pytest.mark.parametrize("nb", [4, 5, 8, 9])
+def test_operator_actions_match_reference_kernels(spec, nb):
+    if spec == "rect:64" and nb not in (4, 5):
+        pytest.skip("large case only for the headline orders")
+    omega = 10.0
+    r = ref("ops", spec, nb, omega, 12345)
+    mesh = product_mesh(spec)
+    fem = cb.H1Space(mesh, cb.Basis(nb))
+    fs = cb.FaceSpace(fem, mesh.boundary_edges())
+    n, nf = fem.size(), fs.size()
+    assert n == r["ndof"][0] and nf == r["fdof"][0]
+    f_s, f_m, a2, af = dev(r["f_stiff"]), dev(r["f_mass"]), dev(r["a2"]), dev(r["af"])
+    y = torch.empty(n, dtype=torch.float64, device="cuda")
+    tol = 1e-12
+
+    S = cb.StiffnessMatrix(fem)
+    S.action(f_s, y)
+    assert rel(host(y), r["S_default_f"]) < tol
+    S.action(-0.75, f_m, y)
+    assert rel(host(y), r["S_default_acc"]) < tol
+    cb.StiffnessMatrix(fem, cb.QuadratureRule(nb + 2, cb.GaussLegendre)).action(f_s, y)
+    assert rel(host(y), r["S_q2_f"]) < tol
+
+    cb.MassMatrix(fem).action(f_m, y)
+    assert rel(host(y), r["M_f"]) < tol
+    Mw = cb.MassMatrix(a2, fem)
+    Mw.action(f_m, y)
+    assert rel(host(y), r["Mw_f"]) < tol
+    Mw.action(2.5, f_s, y)
+    assert rel(host(y), r["Mw_acc"]) < tol
+    cb.DiagInvMassMatrix(fem).action(f_m, y)
+    assert rel(host(y), r["Mi_f"]) < tol
+    cb.DiagInvMassMatrix(a2, fem).action(f_m, y)
+    assert rel(host(y), r["Miw_f"]) < tol
+
+    xf = torch.empty(nf, dtype=torch.float64, device="cuda")
+    yf = torch.empty_like(xf)
+    fs.restrict(f_m, xf)
+    assert np.array_equal(host(xf), r["restrict_f"])
+    cb.FaceMassMatrix(fs).action(xf, yf)
+    assert rel(host(yf), r["H_f"]) < tol
+    cb.FaceMassMatrix(af, fs).action(xf, yf)
+    assert rel(host(yf), r["Hw_f"]) < tol
+    cb.DiagInvFaceMassMatrix(fs).action(xf, yf)
+    assert rel(host(yf), r["Hi_f"]) < tol
+    y.copy_(f_s)
+    fs.prolong(yf, y)
+    assert rel(host(y), r["prolong"]) < 1e-15
+    fs.orth(y)
+    assert np.array_equal(host(y), r["orth"])
+
+    A = cb.Helmholtz(omega, a2, af, fem, fs)
+    Ax = torch.empty(2 * n, dtype=torch.float64, device="cuda")
+    A.action(dev(r["helm_x"]), Ax)
+    assert rel(host(Ax), r["helm_Ax"]) < tol
+
+
+@pytest.mark.parametrize("spec,nb,m", [("file:" + MESH_FILE, 5, 20), ("file:" + MESH_FILE, 4, 20), ("rect:16", 4, 30)])
+def test_helmholtz_gmres_matches_reference(spec, nb, m):
+    # config 1a: FP64 GMRES(m) on the Helmholtz composite; iteration count +-1, same solution
+    omega, maxit, tol = 10.0, 2000, 1e-6
+    r = ref("helm_gmres", spec, nb, omega, m, maxit, tol)
+    mesh = product_mesh(spec)
+    fem = cb.H1Space(mesh, cb.Basis(nb))
+    fs = cb.FaceSpace(fem, mesh.boundary_edges())
+    n = fem.size()
+    xy = fem.physical_coordinates()
+    c = 1.0 + 0.5 * np.sin(np.pi * xy[:, 0]) * np.cos(np.pi * xy[:, 1])
+    A = cb.Helmholtz(omega, dev(c * c), dev(c[fs.global_indices()]), fem, fs)
+    U = torch.zeros(2 * n, dtype=torch.float64, device="cuda")
+    out = cb.gmres(2 * n, U, A, dev(r["b"]), m, maxit, tol)
+    assert out.success == bool(r["success"][0])
+    assert abs(out.num_iter - int(r["num_iter"][0])) <= 1, (out.num_iter, int(r["num_iter"][0]))
+    assert rel(host(U), r["U"]) < 1e-4
+    k = min(len(out.res_norm), len(r["res_norm"]))
+    assert np.allclose(out.res_norm[:k - 1], r["res_norm"][:k - 1], rtol=1e-3)
+
+
+@pytest.mark.parametrize("nx,nb", [(8, 4), (16, 4), (32, 4), (8, 8), (16, 8)])
+def test_ddh_matches_reference(nx, nb):
+    # examples/DDH.cpp flow (config 1b and the ladder of SURVEY §8d): index data bit-exact, rhs / one action /
+    # postprocess within the FP32 tolerance (bounded by the reference's own run-to-run spread x10, floor 2e-4),
+    # GMRES iteration count +-1, solution 1e-3.
+    omega = 2 * np.pi * nx / 10
+    r = ref("ddh", nx, nb, omega, 20, 100, 1e-4, 2024, timeout=1500)
+    mesh = cb.Mesh2D.uniform_rect(nx, -1.0, 1.0, nx, -1.0, 1.0)
+    fem = cb.H1Space(mesh, cb.Basis(nb))
+    D = cb.DDH(omega, r["a"], fem, nx, nx, 16)
+    info = D.info()
+    n = D.size()
+    assert n == r["n_lambda"][0] and info["n_domains"] == r["n_domains"][0] and info["nt"] == r["nt"][0] and info["dt"] == r["dt"][0]
+    # DDH constructor tables, bit for bit (ints) / exactly (floats rounded from the same doubles)
+    assert np.array_equal(D.array("B"), r["Bf"])
+    assert np.array_equal(D.array("gI"), r["gI"]) and np.array_equal(D.array("sI"), r["sI"])
+    assert np.array_equal(D.array("m"), r["m"]) and np.array_equal(D.array("H"), r["H"])
+    assert np.array_equal(D.array("a"), r["acoef"]) and np.array_equal(D.array("gmi"), r["gmi"])
+    assert np.array_equal(D.array("wh_filter"), r["wh_filter"])
+    assert np.allclose(D.array("g"), r["g_tensor"], rtol=2e-7, atol=0)
+
+    spread = rel(r["act_y2"], r["act_y"])  # the reference against itself (shared-memory float atomics)
+    tol = max(10 * spread, 2e-4)
+    f = dev(r["b"])
+    b = torch.empty(n, dtype=torch.float32, device="cuda")
+    D.rhs(f, b)
+    assert rel(host(b), r["rhs"]) < tol
+    y = torch.empty(n, dtype=torch.float32, device="cuda")
+    D.action(dev(r["act_x"], torch.float32), y)
+    # slots that no subdomain writes hold lambda - (stale memory) in the reference; compare the written ones
+    Bout = D.array("B").reshape(info["n_domains"], 2, info["mx_fdof"])[:, 1, :]
+    idx = Bout[Bout >= 0]
+    mask = np.zeros(n, bool)
+    mask[idx] = True
+    mask[n // 2 + idx] = True
+    assert rel(host(y)[mask], r["act_y"][mask]) < tol, (rel(host(y)[mask], r["act_y"][mask]), spread)
+
+    L = torch.zeros(n, dtype=torch.float32, device="cuda")
+    out = cb.gmres(n, L, D, b, 20, 100, 1e-4)
+    U = torch.empty(2 * fem.size(), dtype=torch.float64, device="cuda")
+    D.postprocess(L, f, U)
+    assert out.success == bool(r["success"][0])
+    assert abs(out.num_iter - int(r["num_iter"][0])) <= 1, (out.num_iter, int(r["num_iter"][0]))
+    assert rel(host(U), r["U"]) < 1e-3, rel(host(U), r["U"])
