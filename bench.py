@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (BASELINE.json configs[1]):
+
+    operator apply on a synthetic structured 1024x1024 quad mesh, n_basis 5 (degree 4): one "step" is one
+    Helmholtz composite action (stiffness + weighted mass on u and v, boundary face mass) on [u; v], measured in
+    GDOF/s = 2*ndof / time, next to the fraction of the measured HBM roofline of the dominant kernel.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 (launched by torch.distributed.run): weak scaling, one 1024x1024 slab per rank, interface rows exchanged
+with NCCL send/recv (cuddhelmholtz_b200/parallel.py). `--impl reference` times the CPU port of the reference's
+kernels (oracle/, OpenMP over all host cores; the reference has no host-only build) on a bounded sample.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "helmholtz_operator_apply_gdofs"
+UNIT = "GDOF/s"
+
+
+def coef(x, y):
+    return 1.0 + 0.5 * np.sin(np.pi * x) * np.cos(np.pi * y)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_port_setup(nx, nb, omega):
+    """oracle Helmholtz operator on a uniform_rect(nx) sample; index data from the library's host setup (bit-identical to
+    the oracle's own, tests/test_host_setup.py) because the oracle's pure-Python setup is too slow at this size."""
+    import cuddhelmholtz_b200 as cb
+    from oracle import ops as O
+    mesh = cb.Mesh2D.uniform_rect(nx, -1.0, 1.0, nx, -1.0, 1.0)
+    fem = cb.H1Space(mesh, cb.Basis(nb))
+    fs = cb.FaceSpace(fem, mesh.boundary_edges())
+    xy = fem.physical_coordinates()
+    I = fem.global_indices()
+    # element corners of uniform_rect: vertex (i, j) at (-1 + 2 i / nx, -1 + 2 j / nx)
+    h = 2.0 / nx
+    ii, jj = np.meshgrid(np.arange(nx), np.arange(nx), indexing="xy")
+    ii, jj = ii.ravel(), jj.ravel()
+    X = lambda i: -1.0 + h * i
+    corners = np.stack([np.stack([X(ii), X(jj)], -1), np.stack([X(ii + 1), X(jj)], -1), np.stack([X(ii + 1), X(jj + 1)], -1),
+                        np.stack([X(ii), X(jj + 1)], -1)], 1)
+    ofem = O.H1.from_arrays(nb, I, xy, corners)
+    be = mesh.boundary_edges()
+    ofs = O.FaceSpace.from_arrays(ofem, fs.subspace_indices(), fs.global_indices(), np.full(len(be), h / 2.0))
+    c = coef(xy[:, 0], xy[:, 1])
+    A = O.Helmholtz(omega, c * c, c[ofs.proj], ofem, ofs)
+    return A, ofem.ndof
+
+
+def time_cpu_port(nx, nb, omega, steps, warmup):
+    from oracle import ops as O
+    A, ndof = cpu_port_setup(nx, nb, omega)
+    x = np.random.default_rng(12345).uniform(-1, 1, 2 * ndof)
+    for _ in range(warmup):
+        A.action(x)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        A.action(x)
+    dt = (time.perf_counter() - t0) / steps
+    return 2 * ndof / dt / 1e9, dt, O.max_threads(), ndof
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nx_s = args.cpu_nx
+    val, dt, cores, ndof = time_cpu_port(nx_s, args.nb, args.omega, args.steps, args.warmup)
+    sample = "uniform_rect(%d) n_basis %d (%.3g of the workload's elements), %d applies, OpenMP %d threads" % (
+        nx_s, args.nb, (nx_s / args.nx) ** 2, args.steps, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "Helmholtz composite apply (stiffness+weighted mass+boundary face mass on [u;v]), "
+                                   "uniform_rect(%d)^2 n_basis %d omega %g; CPU port timed on a uniform_rect(%d) sample" % (
+                                       args.nx, args.nb, args.omega, nx_s)},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "the reference has no host-only build (all operator bodies are __device__ lambdas); this arm is the CPU "
+                    "restatement in oracle/oracle.c"}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--nx", type=int, default=1024)
+    ap.add_argument("--nb", type=int, default=5)
+    ap.add_argument("--omega", type=float, default=100.0)
+    ap.add_argument("--cpu-nx", type=int, default=512, help="edge of the bounded CPU-baseline sample mesh")
+    ap.add_argument("--no-extras", action="store_true", help="skip the DDH / reference-GPU / n_basis 4 context numbers")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import cuddhelmholtz_b200 as cb
+    from cuddhelmholtz_b200.parallel import GpuSlabHelmholtz
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cb.load()
+
+    nx, nb, omega, K, W = args.nx, args.nb, args.omega, args.steps, args.warmup
+    slab = GpuSlabHelmholtz(nx, nx, nb, omega, coef, rank, world)
+    ndof = slab.ndof
+    hx = torch.from_numpy(np.random.default_rng(12345 + rank).uniform(-1, 1, 2 * ndof)).pin_memory()
+    hy = torch.empty(2 * ndof, dtype=torch.float64).pin_memory()
+    x = hx.cuda()
+    y = torch.empty_like(x)
+    if world > 1:  # make x consistent on the interface rows (both neighbours must hold the same values)
+        slab.exchange(x)
+        x.mul_(1.0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ----
+    for _ in range(W):
+        slab.apply(x, y)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = cb.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        slab.apply(x, y)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = cb.launch_count() - l0
+    if sampler:
+        sampler.stop_flag = True
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / K
+    value = 2.0 * ndof * world / (ms_step * 1e-3) / 1e9
+
+    # ---- end to end through the public API with host buffers (pinned H2D of [u;v], apply, D2H of the result) ----
+    Ke = max(3, min(K, 5))
+    for _ in range(2):
+        x.copy_(hx, non_blocking=True)
+        slab.apply(x, y)
+        hy.copy_(y, non_blocking=True)
+    barrier()
+    e0.record()
+    for _ in range(Ke):
+        x.copy_(hx, non_blocking=True)
+        slab.apply(x, y)
+        hy.copy_(y, non_blocking=True)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / Ke
+    e2e_value = 2.0 * ndof * world / (e2e_ms * 1e-3) / 1e9
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (stiffness patch kernel), timed alone with CUDA events on its stream ----
+    peak, peak_src = measured_peaks()
+    Sop = cb.StiffnessMatrix(slab.fem)
+    u = x[:ndof]
+    yy = y[:ndof]
+    ms_patch, ms_shared = Sop.time_phases(u, yy, max(K, 10))
+    bytes_S = Sop.algorithmic_bytes()
+    roof = {"bound": "hbm", "kernel": "volume_action_kernel<%d,%d,stiffness>" % (nb, nb + 1), "achieved": bytes_S / (ms_patch * 1e-3) / 1e9,
+            "peak": peak, "unit": "GB/s", "peak_source": peak_src, "ms_per_launch": ms_patch, "algorithmic_bytes": bytes_S,
+            "shared_assembly_ms": ms_shared, "traffic": None}
+    roof["frac"] = roof["achieved"] / peak
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roof["traffic"] = json.load(open(tr)).get("stiffness_%d_%d_nx%d" % (nb, nb + 1, nx))
+        except Exception:
+            pass
+    Mop = cb.MassMatrix(slab._a2, slab.fem)
+    mp_, ms_ = Mop.time_phases(u, yy, max(K, 10))
+    per_op = {"stiffness": {"ms": ms_patch + ms_shared, "gdofs": ndof / ((ms_patch + ms_shared) * 1e-3) / 1e9,
+                            "hbm_frac": bytes_S / ((ms_patch + ms_shared) * 1e-3) / 1e9 / peak},
+              "mass_weighted": {"ms": mp_ + ms_, "gdofs": ndof / ((mp_ + ms_) * 1e-3) / 1e9,
+                                "hbm_frac": Mop.algorithmic_bytes() / ((mp_ + ms_) * 1e-3) / 1e9 / peak},
+              "helmholtz_composite": {"ms": ms_step, "hbm_frac_fused_formulation": slab.op.algorithmic_bytes() / (ms_step * 1e-3) / 1e9 / peak}}
+    del Mop
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "Helmholtz composite apply (stiffness + weighted mass on u and v + boundary face mass), "
+                                   "uniform_rect(%d x %d) per GPU, n_basis %d (degree %d), omega %g" % (nx, nx, nb, nb - 1, omega),
+                       "ndof_per_gpu": ndof, "parallelism": "slab%d" % world,
+                       "l2": "inputs larger than L2 (x,y 2x%.0f MB, metric data %.0f MB)" % (16 * ndof / 1e6, (bytes_S + Mop_bytes(nb, nx)) / 1e6)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": 16 * ndof, "d2h_bytes_per_step": 16 * ndof},
+            "gpu_launches": int(launches), "roofline": roof, "operators": per_op,
+            "clocks": sampler.summary() if sampler else None}
+    if world > 1:
+        line["exchange_bytes_per_step"] = slab.exchange.bytes_per_apply
+
+    # ---- CPU baseline: the oracle port on the box's host cores, bounded sample ----
+    if world == 1:
+        try:
+            val, dt, cores, nd = time_cpu_port(args.cpu_nx, nb, omega, 3, 1)
+            line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "uniform_rect(%d) n_basis %d (%.3g of the workload's elements), 3 applies, %.2f s each" % (
+                                        args.cpu_nx, nb, (args.cpu_nx / nx) ** 2, dt)}
+        except Exception as e:  # the checker is optional for the number, never for the product
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+        if not args.no_extras:
+            line["context"] = extras(args, cb, torch)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def Mop_bytes(nb, nx):
+    nq = 1 + 3 * nb // 2 + 1
+    return 8 * nq * nq * nx * nx
+
+
+def extras(args, cb, torch):
+    """context numbers next to the headline: the reference's own CUDA kernels (sm_100 build of the unmodified sources)
+    on this GPU, and the DDH-GMRES solve (path B) at the reference example's size."""
+    out = {}
+    drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if os.path.exists(drv):
+        try:
+            r = subprocess.run([drv, "time_ops", str(args.nx), str(args.nb), str(args.omega), "10"], capture_output=True, text=True, timeout=600)
+            out["reference_gpu_kernels"] = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as e:
+            out["reference_gpu_kernels"] = "failed: %r" % (e,)
+    try:
+        out["ddh"] = ddh_bench(cb, torch, drv if os.path.exists(drv) else None)
+    except Exception as e:
+        out["ddh"] = "failed: %r" % (e,)
+    return out
+
+
+def ddh_bench(cb, torch, drv, nx=128, nb=4):
+    """examples/DDH.cpp: uniform_rect(128), n_basis 4, omega = 2 pi 12.8, FP32 GMRES(20), maxit 100, tol 1e-4."""
+    omega = 2 * np.pi * nx / 10
+    mesh = cb.Mesh2D.uniform_rect(nx, -1.0, 1.0, nx, -1.0, 1.0)
+    fem = cb.H1Space(mesh, cb.Basis(nb))
+    xy = fem.physical_coordinates()
+    X, Y = xy[:, 0], xy[:, 1]
+    ha = np.where(X * X + Y * Y < 0.0625, 0.2, 1.0)
+    s = omega * omega
+    src = s / np.pi * np.exp(-s * ((X + 0.5) ** 2 + Y ** 2)) + s / np.pi * np.exp(-s * ((X - 0.5) ** 2 + (Y + 0.5) ** 2))
+    dev = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device="cuda")
+    n = fem.size()
+    f = torch.zeros(2 * n, dtype=torch.float64, device="cuda")
+    cb.MassMatrix(fem).action(dev(src), f[:n])
+    D = cb.DDH(omega, ha, fem, nx, nx, 16)
+    m = D.size()
+    b = torch.empty(m, dtype=torch.float32, device="cuda")
+    L = torch.zeros(m, dtype=torch.float32, device="cuda")
+    D.rhs(f, b)
+    tmp = torch.empty_like(b)
+    D.action(b, tmp)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        D.action(b, tmp)
+    e1.record()
+    torch.cuda.synchronize()
+    act_ms = e0.elapsed_time(e1) / 3
+    t0 = time.perf_counter()
+    out = cb.gmres(m, L, D, b, 20, 100, 1e-4)
+    torch.cuda.synchronize()
+    solve_s = time.perf_counter() - t0
+    info = D.info()
+    res = {"nx": nx, "n_basis": nb, "omega": omega, "n_domains": info["n_domains"], "nt": info["nt"], "n_lambda": m,
+           "action_ms": act_ms, "action_fp32_tflops": D.flops() / (act_ms * 1e-3) / 1e12, "gmres_seconds": solve_s,
+           "gmres_restarts": out.num_iter, "gmres_matvec": out.num_matvec, "success": out.success}
+    if drv:
+        try:
+            r = subprocess.run([drv, "time_ddh", str(nx), str(nb), repr(float(omega)), "3"], capture_output=True, text=True, timeout=900)
+            res["reference_gpu_kernel"] = json.loads(r.stdout.strip().splitlines()[-1])
+            res["action_speedup_vs_reference_kernel"] = res["reference_gpu_kernel"]["action_ms"] / act_ms
+        except Exception as e:
+            res["reference_gpu_kernel"] = "failed: %r" % (e,)
+    return res
+
+
+if __name__ == "__main__":
+    main()

@@ -270,6 +270,12 @@ class Operator:
     def algorithmic_bytes(self):
         return int(load().cuddh_b200_operator_bytes(self._h))
 
+    def time_phases(self, x, y, reps):
+        """(ms of the patch kernel alone, ms of the shared-DOF assembly pass alone), CUDA events on the current stream."""
+        a, b = C.c_float(), C.c_float()
+        check(load().cuddh_b200_operator_time_phases(self._h, _ptr(x), _ptr(y), reps, C.byref(a), C.byref(b), _stream()))
+        return a.value, b.value
+
     # C callback usable by gmres without a Python trampoline
     def _as_apply(self):
         return C.cast(load().cuddh_b200_operator_as_apply, C.c_void_p), self._h

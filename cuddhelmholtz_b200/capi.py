@@ -68,6 +68,7 @@ def _proto(lib):
         "cuddh_b200_helmholtz_create": (C.c_int, [C.c_double, c_dp, c_dp, c_vp, c_vp, P(c_vp)]),
         "cuddh_b200_operator_apply": (C.c_int, [c_vp, C.c_double, C.c_int, c_dp, c_dp, c_vp]),
         "cuddh_b200_facemass_apply_h1": (C.c_int, [c_vp, C.c_double, c_dp, c_dp, c_vp]),
+        "cuddh_b200_operator_time_phases": (C.c_int, [c_vp, c_dp, c_dp, C.c_int, P(C.c_float), P(C.c_float), c_vp]),
         "cuddh_b200_operator_destroy": (C.c_int, [c_vp]),
         "cuddh_b200_operator_bytes": (c_i64, [c_vp]),
         "cuddh_b200_axpby_d": (C.c_int, [c_i64, C.c_double, c_dp, C.c_double, c_dp, c_vp]),

@@ -307,6 +307,34 @@ int cuddh_b200_facemass_apply_h1(cuddh_operator_t op, double c, const double * x
     op->face->apply_h1(c, x, y, S(stream));
     CB_CATCH
 }
+int cuddh_b200_operator_time_phases(cuddh_operator_t op, const double * x, double * y, int reps, float * ms_patch, float * ms_shared,
+                                    void * stream)
+{
+    CB_TRY
+    CB_REQUIRE(op->vol != nullptr && reps > 0, "operator_time_phases: needs a stiffness / mass handle and reps > 0");
+    cudaEvent_t e0, e1, e2;
+    CB_CUDA(cudaEventCreate(&e0));
+    CB_CUDA(cudaEventCreate(&e1));
+    CB_CUDA(cudaEventCreate(&e2));
+    op->vol->apply(1.0, 0, x, y, S(stream), 3); // warm
+    CB_CUDA(cudaEventRecord(e0, S(stream)));
+    for (int i = 0; i < reps; ++i)
+        op->vol->apply(1.0, 0, x, y, S(stream), 1);
+    CB_CUDA(cudaEventRecord(e1, S(stream)));
+    for (int i = 0; i < reps; ++i)
+        op->vol->apply(1.0, 0, x, y, S(stream), 2);
+    CB_CUDA(cudaEventRecord(e2, S(stream)));
+    CB_CUDA(cudaEventSynchronize(e2));
+    float a = 0, b = 0;
+    CB_CUDA(cudaEventElapsedTime(&a, e0, e1));
+    CB_CUDA(cudaEventElapsedTime(&b, e1, e2));
+    *ms_patch = a / reps;
+    *ms_shared = b / reps;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    CB_CATCH
+}
 int cuddh_b200_operator_destroy(cuddh_operator_t op)
 {
     delete op;

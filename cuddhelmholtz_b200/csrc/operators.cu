@@ -682,12 +682,14 @@ namespace cb200
         }
     } // namespace
 
-    void VolumeOp::apply(double c, int accumulate, const double * x, double * y, cudaStream_t s)
+    void VolumeOp::apply(double c, int accumulate, const double * x, double * y, cudaStream_t s, int phases)
     {
         Plan & plan = fem->get_plan();
         PlanDev pd{plan.d_hdr.p, plan.d_gid.p, plan.d_slot.p, plan.d_L.p, plan.d_color_ptr.p, plan.PE};
         LaunchFn fn = generic ? nullptr : (stiff ? find_instance<true>(nb, nq) : find_instance<false>(nb, nq));
-        if (fn)
+        if (!(phases & 1)) {
+        }
+        else if (fn)
             fn(*this, pd, plan, c, accumulate, x, y, s);
         else {
             const int nwarps = std::min(8, plan.PE);
@@ -701,7 +703,7 @@ namespace cb200
                                                                                       d_partial.p, c, accumulate, plan.max_pdof);
             CB_LAUNCHED();
         }
-        if (plan.n_shared > 0) {
+        if (plan.n_shared > 0 && (phases & 2)) {
             assemble_shared_kernel<<<blocks_for(plan.n_shared, 256), 256, 0, s>>>(plan.n_shared, plan.d_sh_gid.p, plan.d_sh_ptr.p,
                                                                                   d_partial.p, y, c, accumulate);
             CB_LAUNCHED();

@@ -18,7 +18,8 @@ namespace cb200
         int epw = 0, lw = 0, n_pass = 0, nk = 0;  // layout constants (see operators.cu)
         bool generic = false;
 
-        void apply(double c, int accumulate, const double * x, double * y, cudaStream_t s);
+        // phases: bit 0 = patch kernel, bit 1 = shared-DOF assembly pass (3 = the full action)
+        void apply(double c, int accumulate, const double * x, double * y, cudaStream_t s, int phases = 3);
         size_t algorithmic_bytes() const; // SURVEY §8(d) per-element bytes * n_elem
     };
 

@@ -1,0 +1,113 @@
+"""Multi-GPU layer for path A (operator apply): one process per GPU, `torch.distributed` for the plumbing.
+
+The reference is single-GPU (no NCCL/MPI anywhere); this is the partitioning SURVEY §8(e) prescribes:
+a uniform_rect(nx, ny_total) mesh is cut into `world` slabs of element rows, one per rank. A rank holds every DOF its
+elements touch, so the node row on a slab interface is held (with identical values) by both neighbours. One operator
+apply is: local matrix-free apply (partial sums on the interface rows) -> exchange of the interface rows with the
+two neighbours (NCCL send/recv over NVLink, 8*(nx*(nb-1)+1) bytes per vector per neighbour) -> add. The sum
+`own + received` is the same two-term FP addition on both sides (commutative), so both copies stay bitwise
+identical and the result does not depend on the rank count.
+
+The exchange is the only collective on this path. The logic here is backend-agnostic (the local operator is any
+object with apply / restrict / prolong), which is how tests/test_parallel_cpu.py runs it on 2 gloo ranks with the
+oracle as local operator.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def slab_geometry(rank, world, ny_local, ay=-1.0, height=2.0):
+    """y-range of rank's slab: slabs are stacked upwards, each `height` tall (weak scaling: fixed work per rank)."""
+    return ay + height * rank, ay + height * (rank + 1)
+
+
+def classify_boundary_edges(edges, boundary_edges, nx, ny):
+    """Split the boundary edges of a uniform_rect(nx, ny) mesh (vertex id = i + (nx+1) j) into bottom / top / sides,
+    each in edge-id order (= increasing x for bottom / top)."""
+    n0 = edges[boundary_edges, 0].astype(np.int64)
+    n1 = edges[boundary_edges, 1].astype(np.int64)
+    row = nx + 1
+    bottom = boundary_edges[(n0 < row) & (n1 < row)]
+    top = boundary_edges[(n0 >= row * ny) & (n1 >= row * ny)]
+    sides = boundary_edges[((n0 % row == 0) & (n1 % row == 0)) | ((n0 % row == nx) & (n1 % row == nx))]
+    assert len(bottom) == nx and len(top) == nx and len(sides) == 2 * ny
+    return bottom, top, sides
+
+
+class SlabExchange:
+    """Adds the neighbours' partial sums on the slab-interface rows of one or more stacked vectors.
+
+    local: object with
+        n_vec_rows()                      -> number of DOFs in one interface row
+        restrict(which, y, buf)           -> buf <- y[interface row]     which in {"bottom", "top"}
+        prolong(which, buf, y)            -> y[interface row] += buf
+    Vectors may be stacks ([u; v]): `offsets` lists the start of each stacked block.
+    """
+
+    def __init__(self, local, rank, world, offsets=(0,), dtype=torch.float64, device="cpu", group=None):
+        self.local, self.rank, self.world, self.offsets, self.group = local, rank, world, tuple(offsets), group
+        m = local.n_vec_rows() * len(self.offsets)
+        mk = lambda: torch.empty(m, dtype=dtype, device=device)
+        self.has_bottom, self.has_top = rank > 0, rank < world - 1
+        self.send_b, self.recv_b = (mk(), mk()) if self.has_bottom else (None, None)
+        self.send_t, self.recv_t = (mk(), mk()) if self.has_top else (None, None)
+        self.bytes_per_apply = 8 * m * (int(self.has_bottom) + int(self.has_top))
+
+    def __call__(self, y):
+        if self.world == 1:
+            return
+        r = self.local.n_vec_rows()
+        ops = []
+        for which, sb, rb, peer in (("bottom", self.send_b, self.recv_b, self.rank - 1), ("top", self.send_t, self.recv_t, self.rank + 1)):
+            if sb is None:
+                continue
+            for k, off in enumerate(self.offsets):
+                self.local.restrict(which, y, off, sb[k * r:(k + 1) * r])
+            ops.append(dist.P2POp(dist.isend, sb, peer, group=self.group))
+            ops.append(dist.P2POp(dist.irecv, rb, peer, group=self.group))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        for which, rb in (("bottom", self.recv_b), ("top", self.recv_t)):
+            if rb is None:
+                continue
+            for k, off in enumerate(self.offsets):
+                self.local.prolong(which, rb[k * r:(k + 1) * r], y, off)
+
+
+class GpuSlabHelmholtz:
+    """Helmholtz composite (examples/Helmholtz.hpp) on this rank's slab, on the GPU, plus the interface exchange."""
+
+    def __init__(self, nx, ny_local, nb, omega, coef, rank, world, group=None):
+        import cuddhelmholtz_b200 as cb
+        self.cb = cb
+        self.rank, self.world = rank, world
+        ay, by = slab_geometry(rank, world, ny_local)
+        self.mesh = cb.Mesh2D.uniform_rect(nx, -1.0, 1.0, ny_local, ay, by)
+        self.fem = cb.H1Space(self.mesh, cb.Basis(nb))
+        self.ndof = self.fem.size()
+        edges, bnd = self.mesh.edges(), self.mesh.boundary_edges()
+        bottom, top, sides = classify_boundary_edges(edges, bnd, nx, ny_local)
+        phys = [sides] + ([bottom] if rank == 0 else []) + ([top] if rank == world - 1 else [])
+        self.fs_phys = cb.FaceSpace(self.fem, np.sort(np.concatenate(phys)))   # the physical boundary only
+        self.fs = {"bottom": cb.FaceSpace(self.fem, bottom), "top": cb.FaceSpace(self.fem, top)}
+        xy = self.fem.physical_coordinates()
+        c = coef(xy[:, 0], xy[:, 1])
+        dev = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda")
+        self._a2, self._af = dev(c * c), dev(c[self.fs_phys.global_indices()])
+        self.op = cb.Helmholtz(omega, self._a2, self._af, self.fem, self.fs_phys)
+        self.exchange = SlabExchange(self, rank, world, offsets=(0, self.ndof), device="cuda", group=group)
+
+    def n_vec_rows(self):
+        return self.fs["bottom"].size()
+
+    def restrict(self, which, y, off, buf):
+        self.fs[which].restrict(y[off:off + self.ndof], buf)
+
+    def prolong(self, which, buf, y, off):
+        self.fs[which].prolong(buf, y[off:off + self.ndof])
+
+    def apply(self, x, y):
+        """y = A x on [u; v] with x consistent on the interface rows; y comes out consistent as well."""
+        self.op.action(x, y)
+        self.exchange(y)

@@ -97,6 +97,10 @@ int cuddh_b200_helmholtz_create(double omega, const double * d_a2, const double 
 int cuddh_b200_operator_apply(cuddh_operator_t op, double c, int accumulate, const double * x, double * y, void * stream);
 /* fused FaceSpace::restrict + FaceMassMatrix::action + FaceSpace::prolong on H1 vectors: y[proj] += c*H*x[proj] */
 int cuddh_b200_facemass_apply_h1(cuddh_operator_t op, double c, const double * x, double * y, void * stream);
+/* measurement aid (bench.py roofline): average CUDA-event time, over `reps` back-to-back launches on `stream`, of the
+ * patch kernel alone and of the shared-DOF assembly pass alone (stiffness / mass handles; computes y = A x) */
+int cuddh_b200_operator_time_phases(cuddh_operator_t op, const double * x, double * y, int reps, float * ms_patch, float * ms_shared,
+                                    void * stream);
 int cuddh_b200_operator_destroy(cuddh_operator_t op);
 /* algorithmic bytes of one apply, 0 if not defined for this operator */
 int64_t cuddh_b200_operator_bytes(cuddh_operator_t op);

@@ -57,6 +57,21 @@ class H1:
         self.nel = mesh.n_elem
         self.corners = _f64(mesh.corners.reshape(-1))  # (2,4,nel) column-major
 
+    @classmethod
+    def from_arrays(cls, nb, I, xy, corners, boundary_faces_I=None):
+        """oracle space over externally supplied index data (bench.py's CPU baseline at sizes where the pure-Python
+        setup above would take minutes): I (nel*nb*nb) int32, xy (ndof,2), corners (nel,4,2)."""
+        self = cls.__new__(cls)
+        self.mesh = None
+        self.basis = S.Basis(nb)
+        self.nb = nb
+        self.I = _i32(np.asarray(I).reshape(-1))
+        self.xy = np.asarray(xy, float)
+        self.ndof = len(self.xy)
+        self.corners = _f64(np.asarray(corners).reshape(-1))
+        self.nel = len(self.corners) // 8
+        return self
+
     def measures(self, xq):
         nq = len(xq)
         out = np.zeros(nq * nq * self.nel)
@@ -152,8 +167,23 @@ class FaceSpace:
         self.fdof = len(proj)
         self.nf = len(self.faces)
 
+    @classmethod
+    def from_arrays(cls, fem, fI, proj, face_meas):
+        """oracle face space over externally supplied index data (see H1.from_arrays)."""
+        self = cls.__new__(cls)
+        self.fem = fem
+        self.faces = None
+        self.I = _i32(np.asarray(fI).reshape(-1))
+        self.proj = _i32(proj)
+        self.fdof = len(self.proj)
+        self.nf = len(self.I) // fem.nb
+        self._meas = np.asarray(face_meas, float)
+        return self
+
     def measures(self, nq):
         # StraightEdge::measure is constant along the edge (include/Edge.hpp:134-137); (nq, nf) column-major
+        if self.faces is None:
+            return _f64(np.repeat(self._meas, nq))
         return _f64(np.repeat(self.fem.mesh.edge_meas[self.faces], nq))
 
     def restrict(self, x):

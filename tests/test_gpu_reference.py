@@ -89,10 +89,13 @@ def test_operator_actions_match_reference_kernels(spec, nb):
     assert rel(host(Ax), r["helm_Ax"]) < tol
 
 
-@pytest.mark.parametrize("spec,nb,m", [("file:" + MESH_FILE, 5, 20), ("file:" + MESH_FILE, 4, 20), ("rect:16", 4, 30)])
-def test_helmholtz_gmres_matches_reference(spec, nb, m):
-    # config 1a: FP64 GMRES(m) on the Helmholtz composite; iteration count +-1, same solution
-    omega, maxit, tol = 10.0, 2000, 1e-6
+@pytest.mark.parametrize("spec,nb,m,maxit,tol", [("file:" + MESH_FILE, 5, 20, 30, 1e-6), ("file:" + MESH_FILE, 4, 200, 60, 1e-4),
+                                                 ("rect:16", 4, 30, 30, 1e-6)])
+def test_helmholtz_gmres_matches_reference(spec, nb, m, maxit, tol):
+    # config 1a: FP64 GMRES(m) on the Helmholtz composite. GMRES(20/30) stagnates on this indefinite problem, so those
+    # cases compare the residual history of a fixed number of restart cycles; GMRES(200) (the reference example's m)
+    # converges and is compared on iteration count (+-1) and solution.
+    omega = 10.0
     r = ref("helm_gmres", spec, nb, omega, m, maxit, tol)
     mesh = product_mesh(spec)
     fem = cb.H1Space(mesh, cb.Basis(nb))
@@ -105,9 +108,12 @@ def test_helmholtz_gmres_matches_reference(spec, nb, m):
     out = cb.gmres(2 * n, U, A, dev(r["b"]), m, maxit, tol)
     assert out.success == bool(r["success"][0])
     assert abs(out.num_iter - int(r["num_iter"][0])) <= 1, (out.num_iter, int(r["num_iter"][0]))
-    assert rel(host(U), r["U"]) < 1e-4
     k = min(len(out.res_norm), len(r["res_norm"]))
-    assert np.allclose(out.res_norm[:k - 1], r["res_norm"][:k - 1], rtol=1e-3)
+    if out.success:
+        assert rel(host(U), r["U"]) < 1e-3
+    else:
+        assert np.allclose(out.res_norm[:k], r["res_norm"][:k], rtol=1e-6)
+        assert rel(host(U), r["U"]) < 1e-6
 
 
 @pytest.mark.parametrize("nx,nb", [(8, 4), (16, 4), (32, 4), (8, 8), (16, 8)])

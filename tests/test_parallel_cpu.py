@@ -1,0 +1,101 @@
+"""CPU, world_size 2, gloo: the slab partition + interface exchange of cuddhelmholtz_b200/parallel.py with the oracle
+as the local operator, against the oracle on the undivided mesh. Covers the host-side logic of the N>1 path."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleSlab:
+    def __init__(self, nx, ny_local, nb, omega, coef, rank, world):
+        from cuddhelmholtz_b200.parallel import SlabExchange, classify_boundary_edges, slab_geometry
+        from oracle import ops as O
+        from oracle import setup_np as S
+        ay, by = slab_geometry(rank, world, ny_local)
+        om = S.uniform_rect(nx, -1.0, 1.0, ny_local, ay, by)
+        self.fem = O.H1(om, nb)
+        self.ndof = self.fem.ndof
+        bottom, top, sides = classify_boundary_edges(om.edges, om.boundary_edges, nx, ny_local)
+        phys = [sides] + ([bottom] if rank == 0 else []) + ([top] if rank == world - 1 else [])
+        fs_phys = O.FaceSpace(self.fem, np.sort(np.concatenate(phys)))
+        self.fs = {"bottom": O.FaceSpace(self.fem, bottom), "top": O.FaceSpace(self.fem, top)}
+        c = coef(self.fem.xy[:, 0], self.fem.xy[:, 1])
+        self.op = O.Helmholtz(omega, c * c, c[fs_phys.proj], self.fem, fs_phys)
+        self.exchange = SlabExchange(self, rank, world, offsets=(0, self.ndof), device="cpu")
+
+    def n_vec_rows(self):
+        return self.fs["bottom"].fdof
+
+    def restrict(self, which, y, off, buf):
+        buf.copy_(y[off:off + self.ndof][torch.as_tensor(self.fs[which].proj, dtype=torch.long)])
+
+    def prolong(self, which, buf, y, off):
+        y[off:off + self.ndof][torch.as_tensor(self.fs[which].proj, dtype=torch.long)] += buf
+
+    def apply(self, x):
+        y = torch.from_numpy(self.op.action(x.numpy()))
+        self.exchange(y)
+        return y
+
+
+def coef(x, y):
+    return 1.0 + 0.5 * np.sin(np.pi * x) * np.cos(0.5 * np.pi * y)
+
+
+def _worker(rank, world, port, nx, ny_local, nb, omega, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import ops as O
+        from oracle import setup_np as S
+        slab = OracleSlab(nx, ny_local, nb, omega, coef, rank, world)
+        # the undivided problem (every rank builds it: small)
+        om = S.uniform_rect(nx, -1.0, 1.0, ny_local * world, -1.0, -1.0 + 2.0 * world)
+        gfem = O.H1(om, nb)
+        gfs = O.FaceSpace(gfem, om.boundary_edges)
+        c = coef(gfem.xy[:, 0], gfem.xy[:, 1])
+        G = O.Helmholtz(omega, c * c, c[gfs.proj], gfem, gfs)
+        key = lambda xy: [(int(round(a * 1e8)), int(round(b * 1e8))) for a, b in xy]
+        gmap = {k: i for i, k in enumerate(key(gfem.xy))}
+        loc2glob = np.array([gmap[k] for k in key(slab.fem.xy)])
+        xg = np.random.default_rng(7).uniform(-1, 1, 2 * gfem.ndof)
+        yg = G.action(xg)
+        xl = np.concatenate([xg[loc2glob], xg[gfem.ndof + loc2glob]])
+        yl = slab.apply(torch.from_numpy(xl)).numpy()
+        want = np.concatenate([yg[loc2glob], yg[gfem.ndof + loc2glob]])
+        err = float(np.linalg.norm(yl - want) / np.linalg.norm(want))
+        # interface rows are bitwise identical on both sides
+        row = yl[:slab.ndof][slab.fs["top" if rank == 0 else "bottom"].proj].copy()
+        rows = [None] * world
+        dist.all_gather_object(rows, row)
+        same = bool(np.array_equal(rows[0], rows[1]))
+        q.put((rank, err, same, slab.exchange.bytes_per_apply))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nb", [4, 5])
+def test_slab_exchange_two_ranks_gloo(nb):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + nb + (os.getpid() % 200)
+    nx, ny_local, world = 6, 4, 2
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nx, ny_local, nb, 7.0, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, same, nbytes in res:
+        assert err < 1e-12, (rank, err)
+        assert same
+        assert nbytes == 8 * 2 * (nx * (nb - 1) + 1)
