@@ -42,11 +42,18 @@ namespace cb200
             int PE;
         };
 
+        // 1-D tables as a kernel parameter (constant bank). Both orientations are stored so that every inner loop
+        // reads one contiguous, even-padded row: Prow[q][k] = P(q,k) (contractions over the basis index),
+        // Pcol[t][i] = P(i,t) (contractions over the quadrature index).
         template <int NB, int NQ, bool STIFF>
         struct Tables
         {
-            double P[NQ * NB];
-            double D[STIFF ? NQ * NB : 1];
+            static constexpr int NBP = (NB + 1) & ~1;
+            static constexpr int NQP = (NQ + 1) & ~1;
+            double Prow[NQ][NBP];
+            double Pcol[NB][NQP];
+            double Drow[STIFF ? NQ : 1][NBP];
+            double Dcol[STIFF ? NB : 1][NQP];
         };
 
         __device__ __forceinline__ double ld_stream(const double * p)
@@ -54,11 +61,23 @@ namespace cb200
             return __ldcs(p);
         }
 
+        // cp.async.bulk.prefetch.L2 (TMA bulk prefetch): size a multiple of 16 bytes, 16-byte aligned address
+        __device__ __forceinline__ void bulk_prefetch_l2(const void * p, size_t bytes)
+        {
+            const unsigned n = (unsigned)(bytes & ~size_t(15));
+            if (n)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(n) : "memory");
+        }
+
         // ------------------------------------------------------------------------------------------
         // main action kernel
         // ------------------------------------------------------------------------------------------
+        // Outer loops of the three contraction stages are deliberately NOT unrolled (#pragma unroll 1): with rolled
+        // loops ptxas streams each table row through uniform registers (one LDCU per DFMA pair) and the kernel needs
+        // ~70 registers; fully unrolled it runs out of the 63 uniform registers, parks the tables in ~120 regular
+        // registers and shuffles them back with R2UR (190 registers, 1 CTA / SM, issue-bound: profiles/r01_*).
         template <int NB, int NQ, bool STIFF>
-        __global__ void __launch_bounds__(256)
+        __global__ void __launch_bounds__(256, (NB <= 6 ? 3 : 2))
         volume_action_kernel(const __grid_constant__ Tables<NB, NQ, STIFF> tab, const PlanDev plan,
                              const double * __restrict__ G, const double * __restrict__ x, double * __restrict__ y,
                              double * __restrict__ partial, const double c, const int accumulate, const int max_pdof)
@@ -67,6 +86,8 @@ namespace cb200
             constexpr int LW = EPW * NQ;          // active lanes
             constexpr int NB2 = NB * NB;
             constexpr int NK = STIFF ? 3 * NQ : NQ; // metric values per lane
+            constexpr int NKI = STIFF ? 3 : 1;      // metric values per lane per quadrature column
+            constexpr int PD = STIFF ? 2 : 4;       // metric prefetch depth (quadrature columns) in stage 2
             constexpr int SCR = (STIFF ? 2 : 1) * NQ * NB; // scratch doubles per element
 
             extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -84,15 +105,44 @@ namespace cb200
             const int warp = tid >> 5;
             const PatchHdr hdr = plan.hdr[blockIdx.x];
 
-            // ---- A. stage the patch: gather x, zero the accumulator, copy the local map ----
-            for (int d = tid; d < hdr.n_pdof; d += blockDim.x) {
-                xloc[d] = __ldg(x + __ldg(plan.gid + hdr.pdof_begin + d));
-                yloc[d] = 0.0;
+            // The patch's metric data is one contiguous block (plan order): pull it into L2 with a single bulk
+            // prefetch while the gather below is in flight, so that the per-column loads of stage 2 are L2 hits.
+            if (tid == 0) {
+                const size_t bytes = (size_t)n_pass_patch * NK * LW * sizeof(double);
+                bulk_prefetch_l2(G + (size_t)blockIdx.x * n_pass_patch * (size_t)(NK * LW), bytes);
             }
+
+            // ---- A. stage the patch: gather x, zero the accumulator, copy the local map ----
+            // (index loads, then value loads, then stores: AU independent gathers in flight per thread)
             {
-                const uint16_t * Lg = plan.L + (size_t)hdr.elem_begin * NB2;
-                for (int k = tid; k < hdr.n_elem * NB2; k += blockDim.x)
-                    Ls[k] = __ldg(Lg + k);
+                constexpr int AU = 6;
+                const int * gidp = plan.gid + hdr.pdof_begin;
+                for (int base = tid; base < hdr.n_pdof; base += AU * blockDim.x) {
+                    int gi[AU];
+                    double xv[AU];
+#pragma unroll
+                    for (int a = 0; a < AU; ++a) {
+                        const int d = base + a * blockDim.x;
+                        gi[a] = (d < hdr.n_pdof) ? __ldg(gidp + d) : -1;
+                    }
+#pragma unroll
+                    for (int a = 0; a < AU; ++a)
+                        xv[a] = (gi[a] >= 0) ? __ldg(x + gi[a]) : 0.0;
+#pragma unroll
+                    for (int a = 0; a < AU; ++a) {
+                        const int d = base + a * blockDim.x;
+                        if (d < hdr.n_pdof) {
+                            xloc[d] = xv[a];
+                            yloc[d] = 0.0;
+                        }
+                    }
+                }
+                // local map: PE*NB2 is even for every patch shape, so copy two 16-bit entries at a time
+                const uint32_t * Lg = reinterpret_cast<const uint32_t *>(plan.L + (size_t)hdr.elem_begin * NB2);
+                uint32_t * Ls32 = reinterpret_cast<uint32_t *>(Ls);
+                const int n32 = (hdr.n_elem * NB2 + 1) >> 1;
+                for (int k = tid; k < n32; k += blockDim.x)
+                    Ls32[k] = __ldg(Lg + k);
             }
             __syncthreads();
 
@@ -105,16 +155,16 @@ namespace cb200
             for (int pass = warp; pass < n_pass; pass += nwarps) {
                 const int e = pass * EPW + el_local;
                 const bool live = (lane < LW) && (e < hdr.n_elem);
-
-                // prefetch this lane's metric values (row r of the element, all columns)
-                double g[NK];
-                {
-                    const double * gp = G + ((size_t)blockIdx.x * n_pass_patch + pass) * (size_t)(NK * LW) + lane;
-                    if (lane < LW) {
+                // this lane's metric values: row r of the element, NKI values per quadrature column, kept PD columns
+                // ahead of the contraction in a register ring (the loads hit L2: the whole patch was bulk-prefetched)
+                const double * gp = G + ((size_t)blockIdx.x * n_pass_patch + pass) * (size_t)(NK * LW) + lane;
+                double gring[PD][NKI];
+                if (lane < LW) {
 #pragma unroll
-                        for (int k = 0; k < NK; ++k)
-                            g[k] = ld_stream(gp + k * LW);
-                    }
+                    for (int i = 0; i < PD; ++i)
+#pragma unroll
+                        for (int a = 0; a < NKI; ++a)
+                            gring[i][a] = (i < NQ) ? ld_stream(gp + (NKI * i + a) * LW) : 0.0;
                 }
 
                 // stage 1: lane j = r < NB holds column j of U; contracts the first index with P (and D)
@@ -124,14 +174,14 @@ namespace cb200
 #pragma unroll
                     for (int k = 0; k < NB; ++k)
                         u[k] = xloc[Le[k]];
-#pragma unroll
+#pragma unroll 1
                     for (int q = 0; q < NQ; ++q) {
                         double pu = 0.0, du = 0.0;
 #pragma unroll
                         for (int k = 0; k < NB; ++k) {
-                            pu = fma(tab.P[q + NQ * k], u[k], pu);
+                            pu = fma(tab.Prow[q][k], u[k], pu);
                             if (STIFF)
-                                du = fma(tab.D[q + NQ * k], u[k], du);
+                                du = fma(tab.Drow[q][k], u[k], du);
                         }
                         sc[q * NB + r] = pu;
                         if (STIFF)
@@ -143,13 +193,13 @@ namespace cb200
                 // stage 2: lane q = r holds row q; second-index contraction, metric, and the transposed
                 // second-index contraction back to the basis
                 double a0[NB], a1[STIFF ? NB : 1];
-                if (live) {
+                if (lane < LW) {
                     double pu[NB], du[STIFF ? NB : 1];
 #pragma unroll
                     for (int l = 0; l < NB; ++l) {
-                        pu[l] = sc[r * NB + l];
+                        pu[l] = live ? sc[r * NB + l] : 0.0;
                         if (STIFF)
-                            du[l] = sc[NQ * NB + r * NB + l];
+                            du[l] = live ? sc[NQ * NB + r * NB + l] : 0.0;
                     }
 #pragma unroll
                     for (int t = 0; t < NB; ++t) {
@@ -157,33 +207,48 @@ namespace cb200
                         if (STIFF)
                             a1[t] = 0.0;
                     }
+#pragma unroll 1
+                    for (int ty0 = 0; ty0 < NQ; ty0 += PD) {
 #pragma unroll
-                    for (int ty = 0; ty < NQ; ++ty) {
-                        if (STIFF) {
-                            double Dx = 0.0, Dy = 0.0;
+                        for (int i = 0; i < PD; ++i) {
+                            const int ty = ty0 + i;
+                            if (ty < NQ) {
+                                double gcur[NKI];
 #pragma unroll
-                            for (int l = 0; l < NB; ++l) {
-                                Dx = fma(tab.P[ty + NQ * l], du[l], Dx);
-                                Dy = fma(tab.D[ty + NQ * l], pu[l], Dy);
+                                for (int a = 0; a < NKI; ++a)
+                                    gcur[a] = gring[i][a];
+                                if (ty + PD < NQ) {
+#pragma unroll
+                                    for (int a = 0; a < NKI; ++a)
+                                        gring[i][a] = ld_stream(gp + (NKI * (ty + PD) + a) * LW);
+                                }
+                                if (STIFF) {
+                                    double Dx = 0.0, Dy = 0.0;
+#pragma unroll
+                                    for (int l = 0; l < NB; ++l) {
+                                        Dx = fma(tab.Prow[ty][l], du[l], Dx);
+                                        Dy = fma(tab.Drow[ty][l], pu[l], Dy);
+                                    }
+                                    const double A = gcur[0], B = gcur[NKI > 1 ? 1 : 0], C = gcur[NKI > 2 ? 2 : 0];
+                                    const double F0 = A * Dx + B * Dy;
+                                    const double F1 = B * Dx + C * Dy;
+#pragma unroll
+                                    for (int t = 0; t < NB; ++t) {
+                                        a0[t] = fma(tab.Prow[ty][t], F0, a0[t]);
+                                        a1[t] = fma(tab.Drow[ty][t], F1, a1[t]);
+                                    }
+                                }
+                                else {
+                                    double ppu = 0.0;
+#pragma unroll
+                                    for (int l = 0; l < NB; ++l)
+                                        ppu = fma(tab.Prow[ty][l], pu[l], ppu);
+                                    const double val = gcur[0] * ppu;
+#pragma unroll
+                                    for (int t = 0; t < NB; ++t)
+                                        a0[t] = fma(tab.Prow[ty][t], val, a0[t]);
+                                }
                             }
-                            const double A = g[3 * ty], B = g[3 * ty + 1], C = g[3 * ty + 2];
-                            const double F0 = A * Dx + B * Dy;
-                            const double F1 = B * Dx + C * Dy;
-#pragma unroll
-                            for (int t = 0; t < NB; ++t) {
-                                a0[t] = fma(tab.P[ty + NQ * t], F0, a0[t]);
-                                a1[t] = fma(tab.D[ty + NQ * t], F1, a1[t]);
-                            }
-                        }
-                        else {
-                            double ppu = 0.0;
-#pragma unroll
-                            for (int l = 0; l < NB; ++l)
-                                ppu = fma(tab.P[ty + NQ * l], pu[l], ppu);
-                            const double val = g[ty] * ppu;
-#pragma unroll
-                            for (int t = 0; t < NB; ++t)
-                                a0[t] = fma(tab.P[ty + NQ * t], val, a0[t]);
                         }
                     }
                 }
@@ -208,19 +273,19 @@ namespace cb200
                             A1[i] = sc[NQ * NB + i * NB + r];
                     }
                     double * so = su + e * NB2 + NB * r;
-#pragma unroll
+#pragma unroll 1
                     for (int t = 0; t < NB; ++t) {
-                        double s = 0.0;
+                        double s0 = 0.0, s1 = 0.0;
 #pragma unroll
                         for (int i = 0; i < NQ; ++i) {
                             if (STIFF) {
-                                s = fma(tab.D[i + NQ * t], A0[i], s);
-                                s = fma(tab.P[i + NQ * t], A1[i], s);
+                                s0 = fma(tab.Dcol[t][i], A0[i], s0);
+                                s1 = fma(tab.Pcol[t][i], A1[i], s1);
                             }
                             else
-                                s = fma(tab.P[i + NQ * t], A0[i], s);
+                                s0 = fma(tab.Pcol[t][i], A0[i], s0);
                         }
-                        so[t] = s;
+                        so[t] = STIFF ? (s0 + s1) : s0;
                     }
                 }
                 __syncwarp();
@@ -632,6 +697,12 @@ namespace cb200
             return std::max(best, 1);
         }
 
+        int env_int(const char * name, int dflt)
+        {
+            const char * v = getenv(name);
+            return v ? atoi(v) : dflt;
+        }
+
         template <int NB, int NQ, bool STIFF>
         void launch_volume(VolumeOp & op, const PlanDev & pd, const Plan & plan, double c, int accumulate, const double * x,
                            double * y, cudaStream_t s)
@@ -639,21 +710,30 @@ namespace cb200
             constexpr int EPW = 32 / NQ;
             constexpr int SCR = (STIFF ? 2 : 1) * NQ * NB;
             const int n_pass = (plan.PE + EPW - 1) / EPW;
-            const int nwarps = pick_warps(n_pass);
+            static const int warps_override = env_int("CUDDH_B200_WARPS", 0);
+            const int nwarps = warps_override > 0 ? std::min(warps_override, 16) : pick_warps(n_pass);
             size_t smem = sizeof(double) * ((size_t)2 * plan.max_pdof + (size_t)plan.PE * NB * NB + (size_t)nwarps * EPW * SCR) +
                           sizeof(uint16_t) * (size_t)plan.PE * NB * NB;
             smem = (smem + 15) & ~size_t(15);
             Tables<NB, NQ, STIFF> tab;
-            for (int k = 0; k < NQ * NB; ++k) {
-                tab.P[k] = op.P[k];
-                if (STIFF)
-                    tab.D[k] = op.D[k];
-            }
+            std::memset(&tab, 0, sizeof(tab));
+            for (int q = 0; q < NQ; ++q)
+                for (int k = 0; k < NB; ++k) {
+                    tab.Prow[q][k] = op.P[q + NQ * k];
+                    tab.Pcol[k][q] = op.P[q + NQ * k];
+                    if (STIFF) {
+                        tab.Drow[q][k] = op.D[q + NQ * k];
+                        tab.Dcol[k][q] = op.D[q + NQ * k];
+                    }
+                }
             auto kern = volume_action_kernel<NB, NQ, STIFF>;
             static bool attr_set = false;
             static size_t attr_smem = 0;
             if (!attr_set || smem > attr_smem) {
                 CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)49152)));
+                // several CTAs per SM are needed to overlap the staging / assembly phases of one patch with the
+                // contractions of another: ask for the largest shared-memory carve-out
+                CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
                 attr_set = true;
                 attr_smem = std::max(smem, (size_t)49152);
             }
@@ -674,7 +754,7 @@ namespace cb200
             CB_CASE(2, 3) CB_CASE(3, 4) CB_CASE(4, 5) CB_CASE(5, 6) CB_CASE(6, 7) CB_CASE(7, 8) CB_CASE(8, 9) CB_CASE(9, 10)
             // the reference tests' nb + 2 rules (tests/stiffness.cpp:84, tests/mass.cpp:94)
             CB_CASE(3, 5) CB_CASE(4, 6) CB_CASE(5, 7) CB_CASE(6, 8) CB_CASE(7, 9) CB_CASE(8, 10)
-            if (!STIFF) { // weighted mass: nq = 1 + 3nb/2 + 1 (MassMatrix.cpp:108)
+            if constexpr (!STIFF) { // weighted mass: nq = 1 + 3nb/2 + 1 (MassMatrix.cpp:108)
                 CB_CASE(2, 5) CB_CASE(3, 6) CB_CASE(4, 8) CB_CASE(5, 9) CB_CASE(6, 11) CB_CASE(7, 12) CB_CASE(8, 14) CB_CASE(9, 15)
             }
 #undef CB_CASE
