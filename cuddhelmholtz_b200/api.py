@@ -40,6 +40,18 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream if torch.cuda.is_available() else None
 
 
+def _destroy(fn, obj):
+    """release a C handle; safe during interpreter shutdown (module globals may already be gone)"""
+    h = getattr(obj, "_h", None)
+    lib = getattr(capi, "_lib", None) if capi is not None else None
+    if h and lib is not None:
+        try:
+            getattr(lib, fn)(h)
+        except Exception:
+            pass
+    obj._h = None
+
+
 def _np(a, dtype):
     return np.ascontiguousarray(a, dtype=dtype)
 
@@ -80,9 +92,7 @@ class Basis:
         check(load().cuddh_b200_basis_create(n, C.byref(self._h)))
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            load().cuddh_b200_basis_destroy(self._h)
-            self._h = None
+        _destroy("cuddh_b200_basis_destroy", self)
 
     def size(self):
         return self.n
@@ -117,9 +127,7 @@ class Mesh2D:
         self._sizes = s
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            load().cuddh_b200_mesh_destroy(self._h)
-            self._h = None
+        _destroy("cuddh_b200_mesh_destroy", self)
 
     @staticmethod
     def uniform_rect(nx, ax, bx, ny, ay, by):
@@ -177,9 +185,7 @@ class H1Space:
         check(load().cuddh_b200_h1space_create(mesh._h, self.n_basis, C.byref(self._h)))
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            load().cuddh_b200_h1space_destroy(self._h)
-            self._h = None
+        _destroy("cuddh_b200_h1space_destroy", self)
 
     def size(self):
         return int(load().cuddh_b200_h1space_size(self._h))
@@ -214,9 +220,7 @@ class FaceSpace:
         check(load().cuddh_b200_facespace_create(fem._h, len(faces), _vp(faces), C.byref(self._h)))
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            load().cuddh_b200_facespace_destroy(self._h)
-            self._h = None
+        _destroy("cuddh_b200_facespace_destroy", self)
 
     def size(self):
         return int(load().cuddh_b200_facespace_size(self._h))
@@ -253,9 +257,7 @@ class Operator:
     _h = None
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            load().cuddh_b200_operator_destroy(self._h)
-            self._h = None
+        _destroy("cuddh_b200_operator_destroy", self)
 
     def action(self, *args):
         if len(args) == 2:
@@ -410,9 +412,7 @@ class DDH:
         check(load().cuddh_b200_ddh_create(float(omega), _vp(h_a), fem._h, nx, ny, block, C.byref(self._h)))
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            load().cuddh_b200_ddh_destroy(self._h)
-            self._h = None
+        _destroy("cuddh_b200_ddh_destroy", self)
 
     def size(self):
         return int(load().cuddh_b200_ddh_size(self._h))

@@ -129,26 +129,27 @@ namespace cb200
         int n_pdof;       // patch-local DOFs
         int n_int;        // first n_int are touched by this patch only (written straight to y)
         int slot_begin;   // offset into slot[] for the n_pdof - n_int shared ones
-        int color_begin;  // offset into color_ptr[]; colour c = element slots [cp[c], cp[c+1]) within patch
-        int n_colors;
+        int cptr_begin;   // offset into cptr[] (n_pdof + 1 entries): CSR patch-local DOF -> element-local entries
+        int reserved;
     };
 
     struct Plan
     {
         int nb = 0, PE = 0;
         int64_t n_patches = 0, n_slots_total = 0, n_shared = 0;
-        int max_pdof = 0, max_colors = 0;
+        int max_pdof = 0;
         std::vector<PatchHdr> hdr;
         std::vector<int> gid;              // patch-local -> global DOF, per patch ascending inside each class
         std::vector<int> slot;             // shared patch-local DOF -> index into the partial buffer
         std::vector<uint16_t> L;           // (nb*nb, PE, n_patches) element-local node -> patch-local DOF
-        std::vector<int> color_ptr;
+        std::vector<uint16_t> cptr;        // per patch n_pdof+1 offsets into its slice of cent
+        std::vector<uint16_t> cent;        // (nb*nb*PE, n_patches): element-local entries (slot*nb*nb + node) grouped by DOF
         std::vector<int> slot_elem;        // (PE, n_patches) global element id of each slot, -1 = padding
         std::vector<int> sh_gid, sh_ptr;   // shared DOFs: global id, CSR into the partial buffer (patch order)
         // device mirrors
         DevBuf<PatchHdr> d_hdr;
-        DevBuf<int> d_gid, d_slot, d_color_ptr, d_slot_elem, d_sh_gid, d_sh_ptr;
-        DevBuf<uint16_t> d_L;
+        DevBuf<int> d_gid, d_slot, d_slot_elem, d_sh_gid, d_sh_ptr;
+        DevBuf<uint16_t> d_L, d_cptr, d_cent;
         bool on_device = false;
         void ensure_device();
     };

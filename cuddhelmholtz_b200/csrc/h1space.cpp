@@ -263,53 +263,16 @@ namespace cb200
         const int64_t np = (int64_t)pel.size();
         plan.n_patches = np;
 
-        // 2. greedy colouring inside each patch (vertex-sharing elements get different colours), then
-        //    order the patch's elements by colour
+        // 2. element slots of each patch (patch order = element order of the lists above)
         plan.hdr.resize(np);
         plan.slot_elem.assign((size_t)np * PE, -1);
-        plan.color_ptr.clear();
-        {
-            std::vector<uint32_t> vmask((size_t)mesh.n_nodes, 0);
-            std::vector<int> col;
-            for (int64_t p = 0; p < np; ++p) {
-                auto & els = pel[p];
-                col.assign(els.size(), 0);
-                int ncol = 0;
-                for (size_t k = 0; k < els.size(); ++k) {
-                    uint32_t used = 0;
-                    for (int c = 0; c < 4; ++c)
-                        used |= vmask[mesh.elems[4 * (size_t)els[k] + c]];
-                    int cc = 0;
-                    while (used & (1u << cc))
-                        ++cc;
-                    CB_REQUIRE(cc < 32, "assembly plan: more than 32 colours needed in a patch");
-                    col[k] = cc;
-                    ncol = std::max(ncol, cc + 1);
-                    for (int c = 0; c < 4; ++c)
-                        vmask[mesh.elems[4 * (size_t)els[k] + c]] |= (1u << cc);
-                }
-                for (size_t k = 0; k < els.size(); ++k)
-                    for (int c = 0; c < 4; ++c)
-                        vmask[mesh.elems[4 * (size_t)els[k] + c]] = 0;
-                std::vector<int> order(els.size());
-                std::iota(order.begin(), order.end(), 0);
-                std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return col[a] < col[b]; });
-                PatchHdr & h = plan.hdr[p];
-                h.elem_begin = (int)(p * PE);
-                h.n_elem = (int)els.size();
-                h.color_begin = (int)plan.color_ptr.size();
-                h.n_colors = ncol;
-                plan.max_colors = std::max(plan.max_colors, ncol);
-                int pos = 0;
-                for (int c = 0; c < ncol; ++c) {
-                    plan.color_ptr.push_back(pos);
-                    while (pos < (int)order.size() && col[order[pos]] == c)
-                        ++pos;
-                }
-                plan.color_ptr.push_back(pos);
-                for (size_t k = 0; k < order.size(); ++k)
-                    plan.slot_elem[(size_t)p * PE + k] = els[order[k]];
-            }
+        for (int64_t p = 0; p < np; ++p) {
+            PatchHdr & h = plan.hdr[p];
+            h.elem_begin = (int)(p * PE);
+            h.n_elem = (int)pel[p].size();
+            h.reserved = 0;
+            for (size_t k = 0; k < pel[p].size(); ++k)
+                plan.slot_elem[(size_t)p * PE + k] = pel[p][k];
         }
 
         // 3. patch-local DOF lists; a DOF touched by more than one patch is "shared"
@@ -350,7 +313,11 @@ namespace cb200
         plan.gid.clear();
         plan.slot.clear();
         plan.L.assign((size_t)np * PE * nb2, 0);
+        plan.cent.assign((size_t)np * PE * nb2, 0);
+        plan.cptr.clear();
+        plan.cptr.reserve(plan.gid.capacity() + (size_t)np);
         std::vector<int> local((size_t)fem.ndof, -1);
+        std::vector<int> cnt;
         for (int64_t p = 0; p < np; ++p) {
             PatchHdr & h = plan.hdr[p];
             auto & g = pg[p];
@@ -378,6 +345,22 @@ namespace cb200
                 for (int a = 0; a < nb2; ++a)
                     Le[a] = (uint16_t)local[Ie[a]];
             }
+            // CSR: patch-local DOF -> its element-local entries in ascending (slot, node) order. This fixes the
+            // summation order of every DOF (deterministic assembly without atomics or colouring).
+            CB_REQUIRE((size_t)PE * nb2 < 65536, "assembly plan: patch too large for 16-bit entry ids");
+            cnt.assign((size_t)h.n_pdof + 1, 0);
+            const uint16_t * Lp = &plan.L[(size_t)p * PE * nb2];
+            const int n_ent = h.n_elem * nb2;
+            for (int k = 0; k < n_ent; ++k)
+                cnt[Lp[k] + 1]++;
+            for (int d = 0; d < h.n_pdof; ++d)
+                cnt[d + 1] += cnt[d];
+            h.cptr_begin = (int)plan.cptr.size();
+            for (int d = 0; d <= h.n_pdof; ++d)
+                plan.cptr.push_back((uint16_t)cnt[d]);
+            uint16_t * ce = &plan.cent[(size_t)p * PE * nb2];
+            for (int k = 0; k < n_ent; ++k)
+                ce[cnt[Lp[k]]++] = (uint16_t)k;
         }
 
     }
@@ -390,7 +373,8 @@ namespace cb200
         d_gid.upload(gid);
         d_slot.upload(slot);
         d_L.upload(L);
-        d_color_ptr.upload(color_ptr);
+        d_cptr.upload(cptr);
+        d_cent.upload(cent);
         d_slot_elem.upload(slot_elem);
         d_sh_gid.upload(sh_gid);
         d_sh_ptr.upload(sh_ptr);

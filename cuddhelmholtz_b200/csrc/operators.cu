@@ -38,7 +38,8 @@ namespace cb200
             const int * gid;
             const int * slot;
             const uint16_t * L;
-            const int * color_ptr;
+            const uint16_t * cptr;
+            const uint16_t * cent;
             int PE;
         };
 
@@ -64,9 +65,12 @@ namespace cb200
         // cp.async.bulk.prefetch.L2 (TMA bulk prefetch): size a multiple of 16 bytes, 16-byte aligned address
         __device__ __forceinline__ void bulk_prefetch_l2(const void * p, size_t bytes)
         {
-            const unsigned n = (unsigned)(bytes & ~size_t(15));
+            // align the window inwards/down to 16 bytes: a prefetch is a hint, losing a few bytes at the edges is fine
+            const size_t a = reinterpret_cast<size_t>(p);
+            const size_t a0 = a & ~size_t(15);
+            const unsigned n = (unsigned)((bytes + (a - a0)) & ~size_t(15));
             if (n)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(n) : "memory");
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(n) : "memory");
         }
 
         // ------------------------------------------------------------------------------------------
@@ -80,7 +84,8 @@ namespace cb200
         __global__ void __launch_bounds__(256, (NB <= 6 ? 3 : 2))
         volume_action_kernel(const __grid_constant__ Tables<NB, NQ, STIFF> tab, const PlanDev plan,
                              const double * __restrict__ G, const double * __restrict__ x, double * __restrict__ y,
-                             double * __restrict__ partial, const double c, const int accumulate, const int max_pdof)
+                             double * __restrict__ partial, const double c, const int accumulate, const int max_pdof,
+                             const int n_patches, const int pf_dist)
         {
             constexpr int EPW = 32 / NQ;          // elements per warp pass
             constexpr int LW = EPW * NQ;          // active lanes
@@ -95,10 +100,12 @@ namespace cb200
             const int n_pass_patch = (PE + EPW - 1) / EPW;
             const int nwarps = blockDim.x >> 5;
             double * xloc = reinterpret_cast<double *>(smem_raw);
-            double * yloc = xloc + max_pdof;
-            double * su = yloc + max_pdof;
+            double * su = xloc + max_pdof;
             double * scratch = su + PE * NB2;
-            uint16_t * Ls = reinterpret_cast<uint16_t *>(scratch + nwarps * EPW * SCR);
+            int * gids = reinterpret_cast<int *>(scratch + nwarps * EPW * SCR);
+            uint16_t * Ls = reinterpret_cast<uint16_t *>(gids + max_pdof);
+            uint16_t * cents = Ls + PE * NB2;          // PE*NB2 is even: stays 4-byte aligned
+            uint16_t * cptrs = cents + PE * NB2;       // max_pdof + 1 (+1 pad) entries
 
             const int tid = threadIdx.x;
             const int lane = tid & 31;
@@ -107,10 +114,21 @@ namespace cb200
 
             // The patch's metric data is one contiguous block (plan order): pull it into L2 with a single bulk
             // prefetch while the gather below is in flight, so that the per-column loads of stage 2 are L2 hits.
+            // The same is done one scheduling wave ahead (patch blockIdx.x + pf_dist) for that patch's metric block,
+            // local map and assembly lists, so that its staging phase runs at L2 instead of DRAM latency.
+            const int pnext = (pf_dist > 0 && (int)blockIdx.x + pf_dist < n_patches) ? (int)blockIdx.x + pf_dist : -1;
+            const size_t g_patch = (size_t)n_pass_patch * NK * LW;
             if (tid == 0) {
-                const size_t bytes = (size_t)n_pass_patch * NK * LW * sizeof(double);
-                bulk_prefetch_l2(G + (size_t)blockIdx.x * n_pass_patch * (size_t)(NK * LW), bytes);
+                bulk_prefetch_l2(G + (size_t)blockIdx.x * g_patch, g_patch * sizeof(double));
+                if (pnext >= 0) {
+                    bulk_prefetch_l2(G + (size_t)pnext * g_patch, g_patch * sizeof(double));
+                    bulk_prefetch_l2(plan.L + (size_t)pnext * PE * NB2, (size_t)PE * NB2 * sizeof(uint16_t));
+                    bulk_prefetch_l2(plan.cent + (size_t)pnext * PE * NB2, (size_t)PE * NB2 * sizeof(uint16_t));
+                }
             }
+            PatchHdr hnext;
+            if (tid == 32 && pnext >= 0)
+                hnext = plan.hdr[pnext];
 
             // ---- A. stage the patch: gather x, zero the accumulator, copy the local map ----
             // (index loads, then value loads, then stores: AU independent gathers in flight per thread)
@@ -133,7 +151,7 @@ namespace cb200
                         const int d = base + a * blockDim.x;
                         if (d < hdr.n_pdof) {
                             xloc[d] = xv[a];
-                            yloc[d] = 0.0;
+                            gids[d] = gi[a];
                         }
                     }
                 }
@@ -141,8 +159,21 @@ namespace cb200
                 const uint32_t * Lg = reinterpret_cast<const uint32_t *>(plan.L + (size_t)hdr.elem_begin * NB2);
                 uint32_t * Ls32 = reinterpret_cast<uint32_t *>(Ls);
                 const int n32 = (hdr.n_elem * NB2 + 1) >> 1;
-                for (int k = tid; k < n32; k += blockDim.x)
+                const uint32_t * Cg = reinterpret_cast<const uint32_t *>(plan.cent + (size_t)hdr.elem_begin * NB2);
+                uint32_t * Cs32 = reinterpret_cast<uint32_t *>(cents);
+                for (int k = tid; k < n32; k += blockDim.x) {
                     Ls32[k] = __ldg(Lg + k);
+                    Cs32[k] = __ldg(Cg + k);
+                }
+                const uint16_t * cpg = plan.cptr + hdr.cptr_begin;
+                for (int k = tid; k <= hdr.n_pdof; k += blockDim.x)
+                    cptrs[k] = __ldg(cpg + k);
+            }
+            if (tid == 32 && pnext >= 0) { // 16-byte aligned windows around the next patch's index lists
+                const int * g0 = plan.gid + (hnext.pdof_begin & ~3);
+                bulk_prefetch_l2(g0, ((size_t)hnext.n_pdof + 4) * sizeof(int));
+                const uint16_t * c0 = plan.cptr + (hnext.cptr_begin & ~7);
+                bulk_prefetch_l2(c0, ((size_t)hnext.n_pdof + 9) * sizeof(uint16_t));
             }
             __syncthreads();
 
@@ -292,25 +323,25 @@ namespace cb200
             }
             __syncthreads();
 
-            // ---- C. deterministic in-patch assembly: colours in order, no two elements of a colour share a DOF ----
+            // ---- C. deterministic assembly + write-back. One thread per patch-local DOF adds the DOF's element
+            //      contributions in the fixed order of the plan's CSR (no atomics, no colouring, no accumulator
+            //      array); patch-private DOFs go straight to y, shared ones to their slot of the partial buffer. ----
             {
-                const int * cp = plan.color_ptr + hdr.color_begin;
-                for (int col = 0; col < hdr.n_colors; ++col) {
-                    const int k0 = cp[col] * NB2, k1 = cp[col + 1] * NB2;
-                    for (int k = k0 + tid; k < k1; k += blockDim.x)
-                        yloc[Ls[k]] += su[k];
-                    __syncthreads();
+                const int * slotp = plan.slot + hdr.slot_begin - hdr.n_int;
+                for (int d = tid; d < hdr.n_pdof; d += blockDim.x) {
+                    const int b = cptrs[d], e = cptrs[d + 1];
+                    double sum = 0.0;
+                    for (int k = b; k < e; ++k)
+                        sum += su[cents[k]];
+                    if (d < hdr.n_int) {
+                        const int gi = gids[d];
+                        const double v = c * sum;
+                        y[gi] = accumulate ? (y[gi] + v) : v;
+                    }
+                    else
+                        partial[__ldg(slotp + d)] = sum;
                 }
             }
-
-            // ---- D. write-back: patch-private DOFs straight to y, shared ones to their partial slot ----
-            for (int d = tid; d < hdr.n_int; d += blockDim.x) {
-                const int gi = __ldg(plan.gid + hdr.pdof_begin + d);
-                const double v = c * yloc[d];
-                y[gi] = accumulate ? (y[gi] + v) : v;
-            }
-            for (int d = hdr.n_int + tid; d < hdr.n_pdof; d += blockDim.x)
-                partial[__ldg(plan.slot + hdr.slot_begin + d - hdr.n_int)] = yloc[d];
         }
 
         // generic fallback for (nb, nq) pairs without a template instance: same algorithm and data layout
@@ -328,17 +359,14 @@ namespace cb200
             const int PE = plan.PE;
             const int nwarps = blockDim.x >> 5;
             double * xloc = reinterpret_cast<double *>(smem_raw);
-            double * yloc = xloc + max_pdof;
-            double * su = yloc + max_pdof;
+            double * su = xloc + max_pdof;
             double * scratch = su + PE * NB2;
             uint16_t * Ls = reinterpret_cast<uint16_t *>(scratch + nwarps * SCR);
             const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
             const PatchHdr hdr = plan.hdr[blockIdx.x];
 
-            for (int d = tid; d < hdr.n_pdof; d += blockDim.x) {
+            for (int d = tid; d < hdr.n_pdof; d += blockDim.x)
                 xloc[d] = __ldg(x + __ldg(plan.gid + hdr.pdof_begin + d));
-                yloc[d] = 0.0;
-            }
             const uint16_t * Lg = plan.L + (size_t)hdr.elem_begin * NB2;
             for (int k = tid; k < hdr.n_elem * NB2; k += blockDim.x)
                 Ls[k] = __ldg(Lg + k);
@@ -418,20 +446,21 @@ namespace cb200
                 __syncwarp();
             }
             __syncthreads();
-            const int * cp = plan.color_ptr + hdr.color_begin;
-            for (int col = 0; col < hdr.n_colors; ++col) {
-                const int k0 = cp[col] * NB2, k1 = cp[col + 1] * NB2;
-                for (int k = k0 + tid; k < k1; k += blockDim.x)
-                    yloc[Ls[k]] += su[k];
-                __syncthreads();
+            const uint16_t * cp = plan.cptr + hdr.cptr_begin;
+            const uint16_t * ce = plan.cent + (size_t)hdr.elem_begin * NB2;
+            for (int d = tid; d < hdr.n_pdof; d += blockDim.x) {
+                const int b = cp[d], e = cp[d + 1];
+                double sum = 0.0;
+                for (int k = b; k < e; ++k)
+                    sum += su[ce[k]];
+                if (d < hdr.n_int) {
+                    const int gi = __ldg(plan.gid + hdr.pdof_begin + d);
+                    const double v = c * sum;
+                    y[gi] = accumulate ? (y[gi] + v) : v;
+                }
+                else
+                    partial[__ldg(plan.slot + hdr.slot_begin + d - hdr.n_int)] = sum;
             }
-            for (int d = tid; d < hdr.n_int; d += blockDim.x) {
-                const int gi = __ldg(plan.gid + hdr.pdof_begin + d);
-                const double v = c * yloc[d];
-                y[gi] = accumulate ? (y[gi] + v) : v;
-            }
-            for (int d = hdr.n_int + tid; d < hdr.n_pdof; d += blockDim.x)
-                partial[__ldg(plan.slot + hdr.slot_begin + d - hdr.n_int)] = yloc[d];
         }
 
         // second pass: DOFs shared between patches, partial slots summed in patch order
@@ -712,8 +741,8 @@ namespace cb200
             const int n_pass = (plan.PE + EPW - 1) / EPW;
             static const int warps_override = env_int("CUDDH_B200_WARPS", 0);
             const int nwarps = warps_override > 0 ? std::min(warps_override, 16) : pick_warps(n_pass);
-            size_t smem = sizeof(double) * ((size_t)2 * plan.max_pdof + (size_t)plan.PE * NB * NB + (size_t)nwarps * EPW * SCR) +
-                          sizeof(uint16_t) * (size_t)plan.PE * NB * NB;
+            size_t smem = sizeof(double) * ((size_t)plan.max_pdof + (size_t)plan.PE * NB * NB + (size_t)nwarps * EPW * SCR) +
+                          sizeof(int) * (size_t)plan.max_pdof + sizeof(uint16_t) * ((size_t)2 * plan.PE * NB * NB + plan.max_pdof + 2);
             smem = (smem + 15) & ~size_t(15);
             Tables<NB, NQ, STIFF> tab;
             std::memset(&tab, 0, sizeof(tab));
@@ -737,8 +766,16 @@ namespace cb200
                 attr_set = true;
                 attr_smem = std::max(smem, (size_t)49152);
             }
+            static int pf_dist = -1;
+            if (pf_dist < 0) { // one scheduling wave = resident CTAs per SM x SM count
+                int dev = 0, sms = 148, occ = 1;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nwarps * 32, smem);
+                pf_dist = env_int("CUDDH_B200_PFDIST", std::max(occ, 1) * sms);
+            }
             kern<<<(unsigned)plan.n_patches, nwarps * 32, smem, s>>>(tab, pd, op.d_G.p, x, y, op.d_partial.p, c, accumulate,
-                                                                       plan.max_pdof);
+                                                                       plan.max_pdof, (int)plan.n_patches, pf_dist);
             CB_LAUNCHED();
         }
 
@@ -765,7 +802,7 @@ namespace cb200
     void VolumeOp::apply(double c, int accumulate, const double * x, double * y, cudaStream_t s, int phases)
     {
         Plan & plan = fem->get_plan();
-        PlanDev pd{plan.d_hdr.p, plan.d_gid.p, plan.d_slot.p, plan.d_L.p, plan.d_color_ptr.p, plan.PE};
+        PlanDev pd{plan.d_hdr.p, plan.d_gid.p, plan.d_slot.p, plan.d_L.p, plan.d_cptr.p, plan.d_cent.p, plan.PE};
         LaunchFn fn = generic ? nullptr : (stiff ? find_instance<true>(nb, nq) : find_instance<false>(nb, nq));
         if (!(phases & 1)) {
         }
@@ -774,7 +811,7 @@ namespace cb200
         else {
             const int nwarps = std::min(8, plan.PE);
             const int SCR = (stiff ? 2 : 1) * nq * nb;
-            size_t smem = sizeof(double) * ((size_t)2 * plan.max_pdof + (size_t)plan.PE * nb * nb + (size_t)nwarps * SCR) +
+            size_t smem = sizeof(double) * ((size_t)plan.max_pdof + (size_t)plan.PE * nb * nb + (size_t)nwarps * SCR) +
                           sizeof(uint16_t) * (size_t)plan.PE * nb * nb;
             smem = (smem + 15) & ~size_t(15);
             CB_REQUIRE(smem <= 227 * 1024, "operator action: patch does not fit in shared memory for this (n_basis, n_quad)");
