@@ -52,6 +52,20 @@ def _proto(lib):
         "cuddh_b200_h1space_physical_coordinates": (C.c_int, [c_vp, c_vp]),
         "cuddh_b200_h1space_device_indices": (c_vp, [c_vp]),
         "cuddh_b200_h1space_device_coordinates": (c_vp, [c_vp]),
+        "cuddh_b200_h1space_host_indices": (c_vp, [c_vp]),
+        "cuddh_b200_h1space_host_coordinates": (c_vp, [c_vp]),
+        "cuddh_b200_h1space_device_corners": (c_vp, [c_vp]),
+        "cuddh_b200_element_metrics": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_dp, c_vp]),
+        "cuddh_b200_linear_functional_assemble": (C.c_int, [c_vp, C.c_int, c_vp, c_dp, C.c_double, c_dp, c_vp]),
+        "cuddh_b200_mesh_vertices": (C.c_int, [c_vp, c_vp]),
+        "cuddh_b200_mesh_elements": (C.c_int, [c_vp, c_vp]),
+        "cuddh_b200_facespace_indices_ptr": (c_vp, [c_vp, C.c_int, C.c_int]),
+        "cuddh_b200_facespace_n_faces": (c_i64, [c_vp]),
+        "cuddh_b200_face_linear_functional_assemble": (C.c_int, [c_vp, C.c_int, c_vp, c_dp, C.c_double, c_dp, c_vp]),
+        "cuddh_b200_ensemble_create": (C.c_int, [c_vp, C.c_int, c_vp, P(c_vp)]),
+        "cuddh_b200_ensemble_destroy": (C.c_int, [c_vp]),
+        "cuddh_b200_ensemble_info": (C.c_int, [c_vp, c_vp]),
+        "cuddh_b200_ensemble_array": (c_vp, [c_vp, C.c_char_p, P(c_i64)]),
         "cuddh_b200_facespace_create": (C.c_int, [c_vp, c_i64, c_vp, P(c_vp)]),
         "cuddh_b200_facespace_destroy": (C.c_int, [c_vp]),
         "cuddh_b200_facespace_size": (c_i64, [c_vp]),

@@ -1,6 +1,7 @@
 // extern "C" boundary of libcuddh_b200.so (see include/cuddh_b200.h). Every entry point converts C++
 // exceptions into a status code + last-error string; nothing throws across the ABI.
 #include "../../include/cuddh_b200.h"
+#include "aux.hpp"
 #include "common.hpp"
 #include "ddh.hpp"
 #include "linalg.hpp"
@@ -45,6 +46,7 @@ struct cuddh_operator_s
     std::unique_ptr<HelmholtzOp> helm;
 };
 struct cuddh_ddh_s { std::unique_ptr<DDH> d; };
+struct cuddh_ensemble_s { std::unique_ptr<Ensemble> e; };
 
 static inline cudaStream_t S(void * s) { return (cudaStream_t)s; }
 
@@ -187,7 +189,71 @@ const double * cuddh_b200_h1space_device_coordinates(cuddh_h1space_t s)
     }
 }
 
+const int * cuddh_b200_h1space_host_indices(cuddh_h1space_t s) { return s->s->I.data(); }
+const double * cuddh_b200_h1space_host_coordinates(cuddh_h1space_t s) { return s->s->xy.data(); }
+const double * cuddh_b200_h1space_device_corners(cuddh_h1space_t s)
+{
+    try {
+        return s->s->device_corners();
+    }
+    catch (const std::exception & e) {
+        set_last_error(e.what());
+        return nullptr;
+    }
+}
+int cuddh_b200_element_metrics(cuddh_h1space_t s, int nq, const double * h_xq, int which, double * d_out, void * stream)
+{
+    CB_TRY
+    CB_REQUIRE(which >= 0 && which <= 2, "element_metrics: which must be 0, 1 or 2");
+    element_metrics(s->s.get(), nq, h_xq, which, d_out, S(stream));
+    CB_CATCH
+}
+int cuddh_b200_linear_functional_assemble(cuddh_h1space_t s, int nq, const double * h_P, const double * d_g, double c, double * d_F,
+                                          void * stream)
+{
+    CB_TRY
+    linear_functional_assemble(s->s.get(), nq, h_P, d_g, c, d_F, S(stream));
+    CB_CATCH
+}
+int cuddh_b200_mesh_vertices(cuddh_mesh_t m, double * xy)
+{
+    CB_TRY
+    std::memcpy(xy, m->m->xy.data(), sizeof(double) * m->m->xy.size());
+    CB_CATCH
+}
+int cuddh_b200_mesh_elements(cuddh_mesh_t m, int * el)
+{
+    CB_TRY
+    std::memcpy(el, m->m->elems.data(), sizeof(int) * m->m->elems.size());
+    CB_CATCH
+}
+
 // ---- face space ----
+const int * cuddh_b200_facespace_indices_ptr(cuddh_facespace_t f, int which, int device)
+{
+    try {
+        FaceSpace & F = *f->f;
+        if (device) {
+            F.ensure_device();
+            if (which == 2 && !F.d_faces.p)
+                F.d_faces.upload(F.faces);
+            return which == 0 ? F.d_I.p : which == 1 ? F.d_proj.p : F.d_faces.p;
+        }
+        return which == 0 ? F.I.data() : which == 1 ? F.proj.data() : F.faces.data();
+    }
+    catch (const std::exception & e) {
+        set_last_error(e.what());
+        return nullptr;
+    }
+}
+int64_t cuddh_b200_facespace_n_faces(cuddh_facespace_t f) { return f->f->n_faces; }
+int cuddh_b200_face_linear_functional_assemble(cuddh_facespace_t f, int nq, const double * h_P, const double * d_g, double c, double * d_F,
+                                               void * stream)
+{
+    CB_TRY
+    face_linear_functional_assemble(f->f.get(), nq, h_P, d_g, c, d_F, S(stream));
+    CB_CATCH
+}
 int cuddh_b200_facespace_create(cuddh_h1space_t s, int64_t nf, const int * faces, cuddh_facespace_t * out)
 {
     CB_TRY
@@ -466,6 +532,55 @@ void cuddh_b200_operator_as_apply(void * h, const double * x, double * y)
 void cuddh_b200_ddh_as_apply(void * h, const float * x, float * y)
 {
     cuddh_b200_ddh_action((cuddh_ddh_t)h, x, y, nullptr);
+}
+
+// ---- EnsembleSpace ----
+int cuddh_b200_ensemble_create(cuddh_h1space_t s, int n_spaces, const int * labels, cuddh_ensemble_t * out)
+{
+    CB_TRY
+    *out = new cuddh_ensemble_s{std::unique_ptr<Ensemble>(new Ensemble(*s->s, n_spaces, labels))};
+    CB_CATCH
+}
+int cuddh_b200_ensemble_destroy(cuddh_ensemble_t e)
+{
+    delete e;
+    return 0;
+}
+int cuddh_b200_ensemble_info(cuddh_ensemble_t e, int64_t * info)
+{
+    CB_TRY
+    const Ensemble & E = *e->e;
+    info[0] = E.n_spaces;
+    info[1] = E.mx_elems;
+    info[2] = E.mx_faces;
+    info[3] = E.mx_ndof;
+    info[4] = E.mx_fdof;
+    info[5] = E.n_shared;
+    CB_CATCH
+}
+const int * cuddh_b200_ensemble_array(cuddh_ensemble_t e, const char * name, int64_t * count)
+{
+    const Ensemble & E = *e->e;
+    const std::string n(name);
+    const std::vector<int> * v = nullptr;
+    if (n == "gI") v = &E.gI;
+    else if (n == "sizes") v = &E.s_dof;
+    else if (n == "elements") v = &E.elems;
+    else if (n == "n_elems") v = &E.s_elems;
+    else if (n == "faces") v = &E.faces;
+    else if (n == "n_faces") v = &E.s_faces;
+    else if (n == "sI") v = &E.sI;
+    else if (n == "fI") v = &E.fI;
+    else if (n == "pI") v = &E.pI;
+    else if (n == "fsizes") v = &E.s_fdof;
+    else if (n == "cmap") v = &E.cmap;
+    if (!v) {
+        set_last_error("ensemble_array: unknown array name " + n);
+        return nullptr;
+    }
+    if (count)
+        *count = (int64_t)v->size();
+    return v->data();
 }
 
 // ---- DDH ----

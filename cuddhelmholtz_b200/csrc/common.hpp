@@ -166,6 +166,8 @@ namespace cb200
         DevBuf<int> d_I;
         DevBuf<double> d_xy, d_corners;  // d_corners: (8, n_elem)
         std::unique_ptr<Plan> plan;      // built lazily by the operators
+        DevBuf<int> d_tr_ptr, d_tr_src;  // transposed map DOF -> element-local entries (ordered assembly), lazy
+        void ensure_transpose();
 
         H1Space(const Mesh * mesh, int nb);
         const int * device_I();
@@ -189,6 +191,7 @@ namespace cb200
         std::vector<int> inc_ptr, inc;
         DevBuf<int> d_inc_ptr, d_inc;
         DevBuf<double> d_meas;     // (n_faces) StraightEdge::measure
+        DevBuf<int> d_faces;
         std::vector<double> h_meas;
         bool on_device = false;
 

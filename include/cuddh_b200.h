@@ -60,6 +60,8 @@ int cuddh_b200_mesh_sizes(cuddh_mesh_t m, int64_t * sizes);
 int cuddh_b200_mesh_edges(cuddh_mesh_t m, int * h_edges);
 int cuddh_b200_mesh_boundary_edges(cuddh_mesh_t m, int * h_list);     /* Mesh2D::boundary_edges() */
 int cuddh_b200_mesh_h(cuddh_mesh_t m, double * min_h, double * max_h); /* Mesh2D::min_h / max_h */
+int cuddh_b200_mesh_vertices(cuddh_mesh_t m, double * h_xy /* (2, n_nodes) */);
+int cuddh_b200_mesh_elements(cuddh_mesh_t m, int * h_elems /* (4, n_elem) */);
 
 /* ---- H1Space: include/H1Space.hpp:21-65 --------------------------------------------------------- */
 int cuddh_b200_h1space_create(cuddh_mesh_t mesh, int n_basis, cuddh_h1space_t * out);
@@ -70,12 +72,31 @@ int cuddh_b200_h1space_physical_coordinates(cuddh_h1space_t s, double * h_xy); /
 const int * cuddh_b200_h1space_device_indices(cuddh_h1space_t s);         /* global_indices(DEVICE) */
 const double * cuddh_b200_h1space_device_coordinates(cuddh_h1space_t s);  /* physical_coordinates(DEVICE) */
 
+/* raw views used by the C++ header layer (valid while the handle lives): global_indices(HOST), physical_coordinates(HOST),
+ * and the (8, n_elem) corner coordinates on the device */
+const int * cuddh_b200_h1space_host_indices(cuddh_h1space_t s);
+const double * cuddh_b200_h1space_host_coordinates(cuddh_h1space_t s);
+const double * cuddh_b200_h1space_device_corners(cuddh_h1space_t s);
+/* Mesh2D::ElementMetricCollection::{jacobians, measures, physical_coordinates}(DEVICE) (include/Mesh2D.hpp:33-41) on the
+ * tensor grid of the n_quad points h_xq: which = 0 -> J (2,2,nq,nq,nel), 1 -> detJ (nq,nq,nel), 2 -> x (2,nq,nq,nel) */
+int cuddh_b200_element_metrics(cuddh_h1space_t s, int n_quad, const double * h_xq, int which, double * d_out, void * stream);
+/* LinearFunctional::action (include/LinearFunctional.hpp:145-181): F += c * sum_e P^T g_e P scattered through the global map in a
+ * fixed order; d_g = w_i w_j detJ f(x_ij) on (nq,nq,nel). h_P == NULL: the "fast" collocated rule, d_g is (nb,nb,nel). */
+int cuddh_b200_linear_functional_assemble(cuddh_h1space_t s, int n_quad, const double * h_P, const double * d_g, double c, double * d_F,
+                                          void * stream);
+
 /* ---- FaceSpace: include/H1Space.hpp:69-147 ------------------------------------------------------ */
 int cuddh_b200_facespace_create(cuddh_h1space_t s, int64_t n_faces, const int * h_faces, cuddh_facespace_t * out);
 int cuddh_b200_facespace_destroy(cuddh_facespace_t f);
 int64_t cuddh_b200_facespace_size(cuddh_facespace_t f);
 int cuddh_b200_facespace_subspace_indices(cuddh_facespace_t f, int * h_I);   /* (nb, n_faces) */
 int cuddh_b200_facespace_global_indices(cuddh_facespace_t f, int * h_proj);  /* (fdof) */
+const int * cuddh_b200_facespace_indices_ptr(cuddh_facespace_t f, int which /* 0 subspace_indices, 1 global_indices, 2 faces */,
+                                             int device);
+int64_t cuddh_b200_facespace_n_faces(cuddh_facespace_t f);
+/* FaceLinearFunctional::action (include/FaceLinearFunctional.hpp:130-164): F += c * sum_f P^T g_f, d_g (nq, n_faces); h_P NULL = collocated */
+int cuddh_b200_face_linear_functional_assemble(cuddh_facespace_t f, int n_quad, const double * h_P, const double * d_g, double c,
+                                               double * d_F, void * stream);
 int cuddh_b200_facespace_restrict(cuddh_facespace_t f, const double * x, double * y, void * stream); /* y[i] = x[proj[i]] */
 int cuddh_b200_facespace_prolong(cuddh_facespace_t f, const double * x, double * y, void * stream);  /* y[proj[i]] += x[i] */
 int cuddh_b200_facespace_orth(cuddh_facespace_t f, double * x, void * stream);                        /* x[proj[i]] = 0 */
@@ -142,6 +163,15 @@ int cuddh_b200_gmres_f(int64_t n, float * x, cuddh_apply_f_fn A, void * A_ctx, c
 /* convenience trampolines so that a cuddh_operator_t / cuddh_ddh_t can be handed to gmres without a host callback */
 void cuddh_b200_operator_as_apply(void * op_handle, const double * x, double * y);
 void cuddh_b200_ddh_as_apply(void * ddh_handle, const float * x, float * y);
+
+/* ---- EnsembleSpace: include/EnsembleSpace.hpp:13-140 (host index maps of a labelled decomposition) ------------- */
+typedef struct cuddh_ensemble_s * cuddh_ensemble_t;
+int cuddh_b200_ensemble_create(cuddh_h1space_t s, int n_spaces, const int * h_labels, cuddh_ensemble_t * out);
+int cuddh_b200_ensemble_destroy(cuddh_ensemble_t e);
+/* info[0..5] = n_spaces, mx_elems, mx_faces, mx_ndof, mx_fdof, n_shared */
+int cuddh_b200_ensemble_info(cuddh_ensemble_t e, int64_t * info);
+/* "gI","sizes","elements","n_elems","faces","n_faces","sI","fI","pI","fsizes","cmap": pointer to the host array + element count */
+const int * cuddh_b200_ensemble_array(cuddh_ensemble_t e, const char * name, int64_t * count);
 
 /* ---- DDH: include/DDH.hpp:21-84 ----------------------------------------------------------------- */
 /* DDH(omega, h_a, fem, nx, ny): h_a HOST nodal coefficient (length ndof). block = 1-D node size of a subdomain
