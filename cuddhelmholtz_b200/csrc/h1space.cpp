@@ -11,6 +11,7 @@
 #include "common.hpp"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <numeric>
 
 namespace cb200
@@ -226,6 +227,10 @@ namespace cb200
         const int64_t nel = fem.n_elem;
         int px, py;
         pick_patch_shape(nb, px, py);
+        if (const char * e = getenv("CUDDH_B200_PX")) // experiment knobs (scripts/sweep_ops.py)
+            px = std::max(1, atoi(e));
+        if (const char * e = getenv("CUDDH_B200_PY"))
+            py = std::max(1, atoi(e));
         const int PE = px * py;
         plan.nb = nb;
         plan.PE = PE;
