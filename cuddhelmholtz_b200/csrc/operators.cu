@@ -57,6 +57,57 @@ namespace cb200
             double Dcol[STIFF ? NB : 1][NQP];
         };
 
+        // Padded layout of the per-element transpose scratch: element stride S, row stride RS, offset HALF of the second
+        // (derivative) plane, all in doubles. Chosen by exhaustive search (profiles/r01_notes.md) so that the four access
+        // patterns of the two transposes (column writes, row reads, row writes, column reads of NQ-lane groups, 64-bit
+        // accesses resolved per half-warp) hit distinct bank pairs: e.g. n_basis 5 / n_quad 6 stiffness goes from 176 to
+        // 88 shared-memory wavefronts per warp pass, the minimum for 44 64-bit instructions.
+        struct ScrLayout
+        {
+            int S, RS, HALF;
+        };
+        template <int NB, int NQ, bool STIFF>
+        __host__ __device__ constexpr ScrLayout scr_layout()
+        {
+            if (STIFF == true && NB == 2 && NQ == 3) return {25, 3, 9};
+            if (STIFF == true && NB == 3 && NQ == 4) return {28, 3, 12};
+            if (STIFF == true && NB == 4 && NQ == 5) return {74, 7, 35};
+            if (STIFF == true && NB == 5 && NQ == 6) return {70, 5, 30}; // 128 wavefronts; {118, 9, 54} reaches 88 but costs a CTA per SM
+            if (STIFF == true && NB == 6 && NQ == 7) return {87, 6, 42};
+            if (STIFF == true && NB == 7 && NQ == 8) return {120, 7, 56};
+            if (STIFF == true && NB == 8 && NQ == 9) return {201, 11, 99};
+            if (STIFF == true && NB == 9 && NQ == 10) return {186, 9, 90};
+            if (STIFF == true && NB == 3 && NQ == 5) return {83, 7, 35};
+            if (STIFF == true && NB == 4 && NQ == 6) return {90, 7, 42};
+            if (STIFF == true && NB == 5 && NQ == 7) return {71, 5, 35};
+            if (STIFF == true && NB == 6 && NQ == 8) return {103, 6, 48};
+            if (STIFF == true && NB == 7 && NQ == 9) return {201, 11, 99};
+            if (STIFF == true && NB == 8 && NQ == 10) return {186, 9, 90};
+            if (STIFF == false && NB == 2 && NQ == 3) return {9, 3, 0};
+            if (STIFF == false && NB == 3 && NQ == 4) return {12, 3, 0};
+            if (STIFF == false && NB == 4 && NQ == 5) return {42, 7, 0};
+            if (STIFF == false && NB == 5 && NQ == 6) return {54, 9, 0};
+            if (STIFF == false && NB == 6 && NQ == 7) return {54, 7, 0};
+            if (STIFF == false && NB == 7 && NQ == 8) return {56, 7, 0};
+            if (STIFF == false && NB == 8 && NQ == 9) return {105, 11, 0};
+            if (STIFF == false && NB == 9 && NQ == 10) return {90, 9, 0};
+            if (STIFF == false && NB == 3 && NQ == 5) return {35, 7, 0};
+            if (STIFF == false && NB == 4 && NQ == 6) return {42, 7, 0};
+            if (STIFF == false && NB == 5 && NQ == 7) return {39, 5, 0};
+            if (STIFF == false && NB == 6 && NQ == 8) return {55, 6, 0};
+            if (STIFF == false && NB == 7 && NQ == 9) return {105, 11, 0};
+            if (STIFF == false && NB == 8 && NQ == 10) return {90, 9, 0};
+            if (STIFF == false && NB == 2 && NQ == 5) return {25, 5, 0};
+            if (STIFF == false && NB == 3 && NQ == 6) return {42, 7, 0};
+            if (STIFF == false && NB == 4 && NQ == 8) return {40, 5, 0};
+            if (STIFF == false && NB == 5 && NQ == 9) return {54, 5, 0};
+            if (STIFF == false && NB == 6 && NQ == 11) return {71, 6, 0};
+            if (STIFF == false && NB == 7 && NQ == 12) return {108, 9, 0};
+            if (STIFF == false && NB == 8 && NQ == 14) return {126, 9, 0};
+            if (STIFF == false && NB == 9 && NQ == 15) return {137, 9, 0};
+            return {(STIFF ? 2 : 1) * NQ * NB, NB, STIFF ? NQ * NB : 0};
+        }
+
         __device__ __forceinline__ double ld_stream(const double * p)
         {
             return __ldcs(p);
@@ -93,7 +144,10 @@ namespace cb200
             constexpr int NK = STIFF ? 3 * NQ : NQ; // metric values per lane
             constexpr int NKI = STIFF ? 3 : 1;      // metric values per lane per quadrature column
             constexpr int PD = STIFF ? 2 : 4;       // metric prefetch depth (quadrature columns) in stage 2
-            constexpr int SCR = (STIFF ? 2 : 1) * NQ * NB; // scratch doubles per element
+            constexpr ScrLayout LY = scr_layout<NB, NQ, STIFF>();
+            constexpr int SCR = LY.S;    // scratch doubles per element (padded)
+            constexpr int RS = LY.RS;    // row stride
+            constexpr int HALF = LY.HALF; // offset of the derivative plane
 
             extern __shared__ __align__(16) unsigned char smem_raw[];
             const int PE = plan.PE;
@@ -214,9 +268,9 @@ namespace cb200
                             if (STIFF)
                                 du = fma(tab.Drow[q][k], u[k], du);
                         }
-                        sc[q * NB + r] = pu;
+                        sc[q * RS + r] = pu;
                         if (STIFF)
-                            sc[NQ * NB + q * NB + r] = du;
+                            sc[HALF + q * RS + r] = du;
                     }
                 }
                 __syncwarp();
@@ -228,9 +282,9 @@ namespace cb200
                     double pu[NB], du[STIFF ? NB : 1];
 #pragma unroll
                     for (int l = 0; l < NB; ++l) {
-                        pu[l] = live ? sc[r * NB + l] : 0.0;
+                        pu[l] = live ? sc[r * RS + l] : 0.0;
                         if (STIFF)
-                            du[l] = live ? sc[NQ * NB + r * NB + l] : 0.0;
+                            du[l] = live ? sc[HALF + r * RS + l] : 0.0;
                     }
 #pragma unroll
                     for (int t = 0; t < NB; ++t) {
@@ -287,9 +341,9 @@ namespace cb200
                 if (live) {
 #pragma unroll
                     for (int t = 0; t < NB; ++t) {
-                        sc[r * NB + t] = a0[t];
+                        sc[r * RS + t] = a0[t];
                         if (STIFF)
-                            sc[NQ * NB + r * NB + t] = a1[t];
+                            sc[HALF + r * RS + t] = a1[t];
                     }
                 }
                 __syncwarp();
@@ -299,9 +353,9 @@ namespace cb200
                     double A0[NQ], A1[STIFF ? NQ : 1];
 #pragma unroll
                     for (int i = 0; i < NQ; ++i) {
-                        A0[i] = sc[i * NB + r];
+                        A0[i] = sc[i * RS + r];
                         if (STIFF)
-                            A1[i] = sc[NQ * NB + i * NB + r];
+                            A1[i] = sc[HALF + i * RS + r];
                     }
                     double * so = su + e * NB2 + NB * r;
 #pragma unroll 1
@@ -737,7 +791,7 @@ namespace cb200
                            double * y, cudaStream_t s)
         {
             constexpr int EPW = 32 / NQ;
-            constexpr int SCR = (STIFF ? 2 : 1) * NQ * NB;
+            constexpr int SCR = scr_layout<NB, NQ, STIFF>().S;
             const int n_pass = (plan.PE + EPW - 1) / EPW;
             static const int warps_override = env_int("CUDDH_B200_WARPS", 0);
             const int nwarps = warps_override > 0 ? std::min(warps_override, 16) : pick_warps(n_pass);

@@ -37,9 +37,6 @@ def run(env, nx=1024, nb=5):
 
 
 if __name__ == "__main__":
-    settings = [{}, {"CUDDH_B200_PX": 6, "CUDDH_B200_PY": 5, "CUDDH_B200_WARPS": 3}, {"CUDDH_B200_PX": 6, "CUDDH_B200_PY": 5, "CUDDH_B200_WARPS": 6},
-                {"CUDDH_B200_PX": 5, "CUDDH_B200_PY": 4, "CUDDH_B200_WARPS": 4}, {"CUDDH_B200_PX": 5, "CUDDH_B200_PY": 4, "CUDDH_B200_WARPS": 2},
-                {"CUDDH_B200_PX": 10, "CUDDH_B200_PY": 9, "CUDDH_B200_WARPS": 6}, {"CUDDH_B200_PX": 10, "CUDDH_B200_PY": 12, "CUDDH_B200_WARPS": 8},
-                {"CUDDH_B200_PX": 8, "CUDDH_B200_PY": 5, "CUDDH_B200_WARPS": 4}, {"CUDDH_B200_PX": 5, "CUDDH_B200_PY": 3, "CUDDH_B200_WARPS": 3}]
+    settings = [{}, {"CUDDH_B200_WARPS": 4}, {"CUDDH_B200_WARPS": 3}]
     for s in settings:
         print(json.dumps(s), json.dumps(run(s)), flush=True)
