@@ -426,6 +426,16 @@ class DDH:
     def postprocess(self, lam, f, u):
         check(load().cuddh_b200_ddh_postprocess(self._h, _ptr(lam), _ptr(f), _ptr(u), _stream()))
 
+    # subdomain-range variants (multi-GPU sharding, see parallel.ShardedDDH)
+    def apply_T_range(self, x, t, dom_begin, dom_end):
+        check(load().cuddh_b200_ddh_apply_T_range(self._h, _ptr(x), _ptr(t), dom_begin, dom_end, _stream()))
+
+    def rhs_range(self, f, b, dom_begin, dom_end):
+        check(load().cuddh_b200_ddh_rhs_range(self._h, _ptr(f), _ptr(b), dom_begin, dom_end, _stream()))
+
+    def postprocess_range(self, lam, f, u, dom_begin, dom_end):
+        check(load().cuddh_b200_ddh_postprocess_range(self._h, _ptr(lam), _ptr(f), _ptr(u), dom_begin, dom_end, _stream()))
+
     def info(self):
         v = np.zeros(8, np.int64)
         dt = C.c_double()

@@ -111,6 +111,9 @@ def _proto(lib):
         "cuddh_b200_ddh_rhs": (C.c_int, [c_vp, c_dp, c_dp, c_vp]),
         "cuddh_b200_ddh_action": (C.c_int, [c_vp, c_dp, c_dp, c_vp]),
         "cuddh_b200_ddh_postprocess": (C.c_int, [c_vp, c_dp, c_dp, c_dp, c_vp]),
+        "cuddh_b200_ddh_apply_T_range": (C.c_int, [c_vp, c_dp, c_dp, C.c_int, C.c_int, c_vp]),
+        "cuddh_b200_ddh_rhs_range": (C.c_int, [c_vp, c_dp, c_dp, C.c_int, C.c_int, c_vp]),
+        "cuddh_b200_ddh_postprocess_range": (C.c_int, [c_vp, c_dp, c_dp, c_dp, C.c_int, C.c_int, c_vp]),
         "cuddh_b200_ddh_info": (C.c_int, [c_vp, c_vp, P(C.c_double)]),
         "cuddh_b200_ddh_get_array": (C.c_int, [c_vp, C.c_char_p, c_vp, c_i64, P(c_i64)]),
         "cuddh_b200_ddh_flops": (C.c_double, [c_vp]),

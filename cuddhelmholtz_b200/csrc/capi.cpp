@@ -614,6 +614,25 @@ int cuddh_b200_ddh_postprocess(cuddh_ddh_t d, const float * lambda, const double
     d->d->postprocess(lambda, f, u, S(stream));
     CB_CATCH
 }
+int cuddh_b200_ddh_apply_T_range(cuddh_ddh_t d, const float * x, float * t, int dom_begin, int dom_end, void * stream)
+{
+    CB_TRY
+    d->d->apply_T_range(x, t, dom_begin, dom_end, S(stream));
+    CB_CATCH
+}
+int cuddh_b200_ddh_rhs_range(cuddh_ddh_t d, const double * f, float * b, int dom_begin, int dom_end, void * stream)
+{
+    CB_TRY
+    d->d->rhs_range(f, b, dom_begin, dom_end, S(stream));
+    CB_CATCH
+}
+int cuddh_b200_ddh_postprocess_range(cuddh_ddh_t d, const float * lambda, const double * f, double * u, int dom_begin, int dom_end,
+                                     void * stream)
+{
+    CB_TRY
+    d->d->postprocess_range(lambda, f, u, dom_begin, dom_end, S(stream));
+    CB_CATCH
+}
 int cuddh_b200_ddh_info(cuddh_ddh_t d, int64_t * info, double * dt)
 {
     CB_TRY

@@ -44,6 +44,7 @@ namespace cb200
             int64_t g_ndof, n_lambda;
             int nt;
             float omega, dt;
+            int dom0;          // first subdomain of this launch (subdomain-range sharding across GPUs)
         };
 
         template <int NB, int NEL>
@@ -61,7 +62,7 @@ namespace cb200
             __shared__ float s_su[MX];
 
             const int tid = threadIdx.x;
-            const int dom = blockIdx.x;
+            const int dom = blockIdx.x + A.dom0;
             const int k = tid % NB;
             const int l = (tid / NB) % NB;
             const int el = tid / (NB * NB);
@@ -215,8 +216,11 @@ namespace cb200
         }
     } // namespace
 
-    void DDH::run(const double * x, double * y, const float * lambda, float * update, cudaStream_t s)
+    void DDH::run(const double * x, double * y, const float * lambda, float * update, cudaStream_t s, int dom_begin, int dom_end)
     {
+        if (dom_end < 0)
+            dom_end = n_domains;
+        CB_REQUIRE(0 <= dom_begin && dom_begin <= dom_end && dom_end <= n_domains, "DDH: subdomain range out of bounds");
         ensure_device();
         DDHArgs A;
         A.gid = d_gid.p;
@@ -240,26 +244,32 @@ namespace cb200
         A.nt = nt;
         A.omega = (float)omega;
         A.dt = (float)dt;
+        A.dom0 = dom_begin;
+        const int n_launch = dom_end - dom_begin;
         if (y) {
             if (!d_contrib.p)
                 d_contrib.alloc(2 * (size_t)n1 * n1 * n_domains);
             A.contrib = d_contrib.p;
+            if (n_launch != n_domains) // subdomains outside the range contribute zero to the ordered sum
+                CB_CUDA(cudaMemsetAsync(d_contrib.p, 0, d_contrib.n * sizeof(double), s));
         }
         if (update)
             CB_CUDA(cudaMemsetAsync(update, 0, sizeof(float) * 2 * (size_t)n_lambda, s));
 
         const int threads = block * block;
-        if (nb == 4 && block == 16)
-            ddh_kernel<4, 4><<<n_domains, threads, 0, s>>>(A);
-        else if (nb == 8 && block == 16)
-            ddh_kernel<8, 2><<<n_domains, threads, 0, s>>>(A);
-        else if (nb == 4 && block == 32)
-            ddh_kernel<4, 8><<<n_domains, threads, 0, s>>>(A);
-        else if (nb == 8 && block == 32)
-            ddh_kernel<8, 4><<<n_domains, threads, 0, s>>>(A);
-        else
-            throw Error(-1, "DDH::action only supports n_basis == 4 or 8.");
-        CB_LAUNCHED();
+        if (n_launch > 0) {
+            if (nb == 4 && block == 16)
+                ddh_kernel<4, 4><<<n_launch, threads, 0, s>>>(A);
+            else if (nb == 8 && block == 16)
+                ddh_kernel<8, 2><<<n_launch, threads, 0, s>>>(A);
+            else if (nb == 4 && block == 32)
+                ddh_kernel<4, 8><<<n_launch, threads, 0, s>>>(A);
+            else if (nb == 8 && block == 32)
+                ddh_kernel<8, 4><<<n_launch, threads, 0, s>>>(A);
+            else
+                throw Error(-1, "DDH::action only supports n_basis == 4 or 8.");
+            CB_LAUNCHED();
+        }
 
         if (y) {
             pou_gather_kernel<<<(unsigned)((g_ndof + 255) / 256), 256, 0, s>>>(g_ndof, d_asm_ptr.p, d_asm_src.p, d_contrib.p, y);
@@ -282,5 +292,15 @@ namespace cb200
     void DDH::postprocess(const float * lambda, const double * f, double * u, cudaStream_t s)
     {
         run(f, u, lambda, nullptr, s); // :669-695
+    }
+
+    // Subdomain-range variants for sharding across GPUs: rank r runs its contiguous range; `t` / `b` / `u` come out
+    // zero wherever another rank's subdomains write, so a sum-allreduce over ranks reproduces the full T(x), rhs and
+    // partition-of-unity sum (every lambda slot has exactly one writer).
+    void DDH::apply_T_range(const float * x, float * t, int dom_begin, int dom_end, cudaStream_t s) { run(nullptr, nullptr, x, t, s, dom_begin, dom_end); }
+    void DDH::rhs_range(const double * f, float * b, int dom_begin, int dom_end, cudaStream_t s) { run(f, nullptr, nullptr, b, s, dom_begin, dom_end); }
+    void DDH::postprocess_range(const float * lambda, const double * f, double * u, int dom_begin, int dom_end, cudaStream_t s)
+    {
+        run(f, u, lambda, nullptr, s, dom_begin, dom_end);
     }
 } // namespace cb200

@@ -54,10 +54,13 @@ namespace cb200
         void rhs(const double * f, float * b, cudaStream_t s);
         void action(const float * x, float * y, cudaStream_t s);
         void postprocess(const float * lambda, const double * f, double * u, cudaStream_t s);
+        void apply_T_range(const float * x, float * t, int dom_begin, int dom_end, cudaStream_t s);
+        void rhs_range(const double * f, float * b, int dom_begin, int dom_end, cudaStream_t s);
+        void postprocess_range(const float * lambda, const double * f, double * u, int dom_begin, int dom_end, cudaStream_t s);
         void get_array(const char * name, void * out, int64_t cap_bytes, int64_t * count) const;
         double flops() const;
 
     private:
-        void run(const double * x, double * y, const float * lambda, float * update, cudaStream_t s);
+        void run(const double * x, double * y, const float * lambda, float * update, cudaStream_t s, int dom_begin = 0, int dom_end = -1);
     };
 } // namespace cb200

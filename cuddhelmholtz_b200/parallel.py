@@ -111,3 +111,63 @@ class GpuSlabHelmholtz:
         """y = A x on [u; v] with x consistent on the interface rows; y comes out consistent as well."""
         self.op.action(x, y)
         self.exchange(y)
+
+
+def subdomain_range(n_domains, rank, world):
+    """contiguous block of subdomains of `rank` (subdomain ids are row-major over the subdomain grid -> row slabs)"""
+    base, rem = divmod(n_domains, world)
+    b = rank * base + min(rank, rem)
+    return b, b + base + (1 if rank < rem else 0)
+
+
+class ShardedDDH:
+    """Path B across GPUs (SURVEY §8e): the subdomain loop of DDH::{rhs, action, postprocess} is split into contiguous
+    subdomain ranges, one per rank; vectors (lambda, f, u) are replicated. A rank's kernel writes only the lambda slots
+    (resp. DOFs) its subdomains own and leaves zeros elsewhere; since every slot has exactly one writer, a sum-allreduce
+    (NCCL over NVLink) reproduces T(x) exactly — bit for bit the single-GPU vector — and action = x - allreduce(T_r(x)).
+    The Krylov vectors are replicated, so GMRES runs redundantly and identically on every rank with no further
+    communication (its vector work is negligible next to the WaveHoltz solves: 1e5 flops per lambda entry per action).
+    Objects of this class plug into cuddhelmholtz_b200.gmres as an operator over raw device pointers."""
+
+    def __init__(self, ddh, rank, world, group=None):
+        self.ddh, self.rank, self.world, self.group = ddh, rank, world, group
+        self.n = ddh.size()
+        self.range = subdomain_range(ddh.info()["n_domains"], rank, world)
+
+    def size(self):
+        return self.n
+
+    def _sum(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def apply_T(self, x, t):
+        self.ddh.apply_T_range(x, t, *self.range)
+        self._sum(t)
+
+    def action_tensors(self, x, y):
+        self.apply_T(x, y)
+        y.neg_().add_(x)  # y = x - T(x)   (source/DDH.cpp:638)
+
+    def action(self, xp, yp):
+        """operator interface used by gmres(): raw device addresses of float vectors of length size()"""
+        x = _as_tensor(xp, self.n, torch.float32)
+        y = _as_tensor(yp, self.n, torch.float32)
+        self.action_tensors(x, y)
+
+    def rhs(self, f, b):
+        self.ddh.rhs_range(f, b, *self.range)
+        self._sum(b)
+
+    def postprocess(self, lam, f, u):
+        self.ddh.postprocess_range(lam, f, u, *self.range)
+        self._sum(u)
+
+
+class _RawVec:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def _as_tensor(ptr, n, dtype):
+    return torch.as_tensor(_RawVec(ptr, n, "<f4" if dtype == torch.float32 else "<f8"), device="cuda")

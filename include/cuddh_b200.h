@@ -182,6 +182,13 @@ int64_t cuddh_b200_ddh_size(cuddh_ddh_t d);                                    /
 int cuddh_b200_ddh_rhs(cuddh_ddh_t d, const double * f, float * b, void * stream);                 /* DDH::rhs */
 int cuddh_b200_ddh_action(cuddh_ddh_t d, const float * x, float * y, void * stream);               /* DDH::action */
 int cuddh_b200_ddh_postprocess(cuddh_ddh_t d, const float * lambda, const double * f, double * u, void * stream); /* DDH::postprocess */
+/* Multi-GPU sharding of the subdomain loop (new: the reference is single-GPU). Rank r runs subdomains [dom_begin, dom_end):
+ * t = T(x) (resp. b, u) restricted to the slots / DOFs those subdomains write, zero elsewhere, so that a sum-allreduce over the
+ * ranks reproduces T(x), rhs and postprocess; DDH::action is then x - allreduce(t). */
+int cuddh_b200_ddh_apply_T_range(cuddh_ddh_t d, const float * x, float * t, int dom_begin, int dom_end, void * stream);
+int cuddh_b200_ddh_rhs_range(cuddh_ddh_t d, const double * f, float * b, int dom_begin, int dom_end, void * stream);
+int cuddh_b200_ddh_postprocess_range(cuddh_ddh_t d, const float * lambda, const double * f, double * u, int dom_begin, int dom_end,
+                                     void * stream);
 /* introspection for parity tests: info[0..7] = n_domains, n_shared, nt, mx_dof, mx_fdof, mx_elem_per_dom, n_basis, block ; dt */
 int cuddh_b200_ddh_info(cuddh_ddh_t d, int64_t * info, double * dt);
 /* host copies of the index / coefficient arrays in the reference's layouts (names as in source/DDH.cpp):

@@ -385,6 +385,53 @@ def test_ddh_gmres_solve_parity():
     assert rel(host(U), Uo) < 1e-3, rel(host(U), Uo)
 
 
+def test_ddh_subdomain_ranges_reproduce_the_full_operator():
+    # multi-GPU sharding of path B, emulated on one GPU: the per-rank partial vectors (zero outside the rank's slots)
+    # must sum to the single-GPU result exactly, for any rank count
+    from cuddhelmholtz_b200.parallel import ShardedDDH, subdomain_range
+    omega = 10.0
+    ofem, pfem, oD, pD, f = _ddh_pair(16, 4, omega)
+    n = pD.size()
+    nd = pD.info()["n_domains"]
+    df = dev(f)
+    lam = dev(np.random.default_rng(5).uniform(-1, 1, n).astype(np.float32), torch.float32)
+    full_T = torch.empty(n, dtype=torch.float32, device="cuda")
+    pD.apply_T_range(lam, full_T, 0, nd)
+    y = torch.empty_like(full_T)
+    pD.action(lam, y)
+    assert torch.equal(y, lam - full_T)
+    b = torch.empty_like(full_T)
+    pD.rhs(df, b)
+    u = torch.empty(2 * ofem.ndof, dtype=torch.float64, device="cuda")
+    pD.postprocess(lam, df, u)
+    for world in (2, 3, 5):
+        ranges = [subdomain_range(nd, r, world) for r in range(world)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == nd and all(a[1] == b_[0] for a, b_ in zip(ranges, ranges[1:]))
+        accT = torch.zeros_like(full_T)
+        accb = torch.zeros_like(b)
+        accu = torch.zeros_like(u)
+        part = torch.empty_like(full_T)
+        pu = torch.empty_like(u)
+        for (d0, d1) in ranges:
+            pD.apply_T_range(lam, part, d0, d1)
+            assert int((part != 0).sum()) <= int((full_T != 0).sum())
+            accT += part
+            pD.rhs_range(df, part, d0, d1)
+            accb += part
+            pD.postprocess_range(lam, df, pu, d0, d1)
+            accu += pu
+        assert torch.equal(accT, full_T)   # every slot has one writer: exact
+        assert torch.equal(accb, b)
+        assert rel(host(accu), host(u)) < 1e-14  # interface DOFs: same terms, different summation grouping
+    # world = 1 wrapper is the plain operator and works as a gmres operator over raw pointers
+    S1 = ShardedDDH(pD, 0, 1)
+    L = torch.zeros(n, dtype=torch.float32, device="cuda")
+    out = cb.gmres(n, L, S1, b, 20, 100, 1e-4)
+    L2 = torch.zeros_like(L)
+    out2 = cb.gmres(n, L2, pD, b, 20, 100, 1e-4)
+    assert out.num_iter == out2.num_iter and torch.equal(L, L2)
+
+
 def test_full_size_properties():
     # BASELINE config 2 size (uniform_rect(1024), n_basis 5): size-independent properties of the operators
     nx, nb = 1024, 5
