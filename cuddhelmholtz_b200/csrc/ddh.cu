@@ -199,6 +199,209 @@ namespace cb200
             }
         }
 
+        // ------------------------------------------------------------------------------------------------------
+        // Register-tiled variant for n_basis 4 / block 16 on meshes whose metric is diagonal and identical in every
+        // element (Mesh2D::uniform_rect — the only meshes DDH accepts): ONE THREAD PER ELEMENT. The element's 4x4 nodal
+        // values of p, q, u, v live in registers, the collocated stiffness (gradient, metric, divergence: 288 FMAs) runs
+        // entirely out of registers with D and the metric as constant-bank operands, and the only data exchange per
+        // stiffness is the assembly of the element-edge nodes with the four neighbours through warp shuffles
+        // (16 threads = one subdomain, two subdomains per warp): no shared-memory traffic and no barrier in the time
+        // loop. Every copy of a shared node applies the same commutative two-term sums (x neighbours first, then y), so
+        // all copies stay bitwise identical. Per-node constants (forcing, 1/(a^2 m), a*H) stream from shared memory.
+        // ------------------------------------------------------------------------------------------------------
+        struct DDHConst4
+        {
+            float D[4][4];   // D(k, i)
+            float gx[4][4];  // [l][k] metric, x-x entry (w_k w_l hy/hx)
+            float gz[4][4];  // [l][k] metric, y-y entry
+        };
+
+        constexpr int V2_THREADS = 128; // 8 subdomains per CTA
+
+        __global__ void __launch_bounds__(V2_THREADS)
+        ddh_kernel_reg4(const __grid_constant__ DDHConst4 C, const DDHArgs A, const int n_dom_launch)
+        {
+            constexpr int NB = 4, NEL = 4, N1 = NEL * (NB - 1) + 1, ND = N1 * N1, WH_MAXIT = 5;
+            // per-node constants, element-local copies: [array][row l][thread] as float4 over k -> conflict-free LDS.128
+            __shared__ float4 s_F[4][V2_THREADS], s_G[4][V2_THREADS], s_im[4][V2_THREADS], s_H[4][V2_THREADS];
+
+            const int tid = threadIdx.x;
+            const int sub = tid >> 4;                 // subdomain within the CTA
+            const int ex = tid & 3, ey = (tid >> 2) & 3;
+            const int dom_local = blockIdx.x * (V2_THREADS / 16) + sub;
+            const bool valid = dom_local < n_dom_launch;
+            const int dom = A.dom0 + (valid ? dom_local : 0);
+            const bool hasL = ex > 0, hasR = ex < NEL - 1, hasB = ey > 0, hasT = ey < NEL - 1;
+
+            float p[4][4], q[4][4], u[4][4], v[4][4];
+            float lam[4][4], mu[4][4], ai[4][4];
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                float Fr[4], Gr[4], im[4], Hr[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const size_t o = (size_t)((ey * 3 + l) * N1 + ex * 3 + k) + (size_t)ND * dom;
+                    const float a = __ldg(A.a + o), mi = __ldg(A.m + o);
+                    float F = 0.0f, G = 0.0f, Hi = __ldg(A.H + o);
+                    if (A.x) {
+                        const int gi = __ldg(A.gid + o);
+                        F = (float)A.x[gi];
+                        G = (float)A.x[A.g_ndof + gi];
+                    }
+                    float lm = 0.0f, mm = 0.0f;
+                    if (A.lambda) {
+                        const int idx = __ldg(A.bin + o);
+                        if (idx >= 0) {
+                            lm = A.lambda[idx];
+                            mm = A.lambda[A.n_lambda + idx];
+                            F += Hi * lm;
+                            G += Hi * mm;
+                        }
+                    }
+                    lam[l][k] = lm;
+                    mu[l][k] = mm;
+                    ai[l][k] = a;
+                    Fr[k] = F;
+                    Gr[k] = G;
+                    im[k] = 1.0f / (a * a * mi);
+                    Hr[k] = Hi * a;
+                    p[l][k] = q[l][k] = u[l][k] = v[l][k] = 0.0f;
+                }
+                s_F[l][tid] = make_float4(Fr[0], Fr[1], Fr[2], Fr[3]);
+                s_G[l][tid] = make_float4(Gr[0], Gr[1], Gr[2], Gr[3]);
+                s_im[l][tid] = make_float4(im[0], im[1], im[2], im[3]);
+                s_H[l][tid] = make_float4(Hr[0], Hr[1], Hr[2], Hr[3]);
+            }
+            // (each thread reads back only what it wrote: no barrier needed)
+
+            // z <- assembled S w  (w, z: [l][k])
+            auto stiffness = [&](const float (&w)[4][4], float (&z)[4][4]) {
+                float fx[4][4], fy[4][4];
+#pragma unroll
+                for (int l = 0; l < 4; ++l)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float Ux = 0.0f, Uy = 0.0f;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            Ux = fmaf(C.D[k][i], w[l][i], Ux);
+                            Uy = fmaf(C.D[l][i], w[i][k], Uy);
+                        }
+                        fx[l][k] = C.gx[l][k] * Ux;
+                        fy[l][k] = C.gz[l][k] * Uy;
+                    }
+#pragma unroll
+                for (int l = 0; l < 4; ++l)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float Su = 0.0f;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            Su = fmaf(C.D[i][k], fx[l][i], Su);
+                            Su = fmaf(C.D[i][l], fy[i][k], Su);
+                        }
+                        z[l][k] = Su;
+                    }
+                // assembly across element edges: x neighbours (lane -+ 1), then y neighbours (lane -+ 4) of the x-summed rows
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    const float fromL = __shfl_up_sync(0xffffffffu, z[l][3], 1, 16);
+                    const float fromR = __shfl_down_sync(0xffffffffu, z[l][0], 1, 16);
+                    z[l][0] += hasL ? fromL : 0.0f;
+                    z[l][3] += hasR ? fromR : 0.0f;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float fromB = __shfl_up_sync(0xffffffffu, z[3][k], 4, 16);
+                    const float fromT = __shfl_down_sync(0xffffffffu, z[0][k], 4, 16);
+                    z[0][k] += hasB ? fromB : 0.0f;
+                    z[3][k] += hasT ? fromT : 0.0f;
+                }
+            };
+
+            const float half_dt = 0.5f * A.dt, dt = A.dt;
+            for (int whit = 0; whit < WH_MAXIT; ++whit) {
+                const float dK0 = __ldg(A.whf);
+#pragma unroll
+                for (int l = 0; l < 4; ++l)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        p[l][k] = u[l][k];
+                        q[l][k] = v[l][k];
+                        u[l][k] *= dK0;
+                        v[l][k] *= dK0;
+                    }
+                for (int it = 1; it <= A.nt; ++it) {
+                    const float c0 = __ldg(A.cs + 2 * it - 2), s0 = __ldg(A.sn + 2 * it - 2);
+                    const float c1 = __ldg(A.cs + 2 * it - 1), s1 = __ldg(A.sn + 2 * it - 1);
+                    const float dK = __ldg(A.whf + it);
+                    float z[4][4], ph[4][4], qh[4][4];
+                    stiffness(p, z);
+#pragma unroll
+                    for (int l = 0; l < 4; ++l) {
+                        const float4 F4 = s_F[l][tid], G4 = s_G[l][tid], I4 = s_im[l][tid], H4 = s_H[l][tid];
+                        const float Fr[4] = {F4.x, F4.y, F4.z, F4.w}, Gr[4] = {G4.x, G4.y, G4.z, G4.w};
+                        const float im[4] = {I4.x, I4.y, I4.z, I4.w}, Hr[4] = {H4.x, H4.y, H4.z, H4.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float zz = z[l][k] - Hr[k] * q[l][k];
+                            float dq = zz + c0 * Fr[k];
+                            dq += s0 * Gr[k];
+                            dq *= im[k];
+                            ph[l][k] = p[l][k] - half_dt * q[l][k];
+                            qh[l][k] = q[l][k] + half_dt * dq;
+                            p[l][k] -= dt * qh[l][k];
+                        }
+                    }
+                    stiffness(ph, z);
+#pragma unroll
+                    for (int l = 0; l < 4; ++l) {
+                        const float4 F4 = s_F[l][tid], G4 = s_G[l][tid], I4 = s_im[l][tid], H4 = s_H[l][tid];
+                        const float Fr[4] = {F4.x, F4.y, F4.z, F4.w}, Gr[4] = {G4.x, G4.y, G4.z, G4.w};
+                        const float im[4] = {I4.x, I4.y, I4.z, I4.w}, Hr[4] = {H4.x, H4.y, H4.z, H4.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float zz = z[l][k] - Hr[k] * qh[l][k];
+                            float dq = zz + c1 * Fr[k];
+                            dq += s1 * Gr[k];
+                            dq *= im[k];
+                            q[l][k] += dt * dq;
+                            u[l][k] += dK * p[l][k];
+                            v[l][k] += dK * q[l][k];
+                        }
+                    }
+                }
+            }
+
+            const float rw = 1.0f / A.omega;
+            if (!valid)
+                return;
+#pragma unroll
+            for (int l = 0; l < 4; ++l)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    // one writer per node: the copy in the right / upper element owns a shared node
+                    const bool canon = (k < 3 || ex == NEL - 1) && (l < 3 || ey == NEL - 1);
+                    if (!canon)
+                        continue;
+                    const size_t o = (size_t)((ey * 3 + l) * N1 + ex * 3 + k) + (size_t)ND * dom;
+                    const float vv = v[l][k] * rw;
+                    if (A.contrib) {
+                        const float M = __ldg(A.pou + o);
+                        A.contrib[2 * o] = (double)(M * u[l][k]);
+                        A.contrib[2 * o + 1] = (double)(M * vv);
+                    }
+                    if (A.update) {
+                        const int idx = __ldg(A.bout + o);
+                        if (idx >= 0) {
+                            const float S = 2.0f * ai[l][k] * A.omega;
+                            A.update[idx] = -lam[l][k] - S * vv;
+                            A.update[A.n_lambda + idx] = -mu[l][k] + S * u[l][k];
+                        }
+                    }
+                }
+        }
+
         __global__ void pou_gather_kernel(const int64_t g_ndof, const int * __restrict__ ptr, const int * __restrict__ src,
                                           const double * __restrict__ contrib, double * __restrict__ y)
         {
@@ -258,7 +461,18 @@ namespace cb200
 
         const int threads = block * block;
         if (n_launch > 0) {
-            if (nb == 4 && block == 16)
+            if (nb == 4 && block == 16 && reg_tiled_ok) {
+                DDHConst4 C;
+                for (int k = 0; k < 4; ++k)
+                    for (int i = 0; i < 4; ++i) {
+                        C.D[k][i] = D[k + 4 * i];
+                        C.gx[i][k] = g[3 * (k + 4 * i) + 0];
+                        C.gz[i][k] = g[3 * (k + 4 * i) + 2];
+                    }
+                const int per_cta = V2_THREADS / 16;
+                ddh_kernel_reg4<<<(n_launch + per_cta - 1) / per_cta, V2_THREADS, 0, s>>>(C, A, n_launch);
+            }
+            else if (nb == 4 && block == 16)
                 ddh_kernel<4, 4><<<n_launch, threads, 0, s>>>(A);
             else if (nb == 8 && block == 16)
                 ddh_kernel<8, 2><<<n_launch, threads, 0, s>>>(A);

@@ -49,6 +49,8 @@ namespace cb200
         std::vector<float> hg_a, hg_m, hg_pou, hg_H;
         bool on_device = false;
         void ensure_device();
+        // metric diagonal and identical in every element (uniform_rect): enables the register-tiled kernel
+        bool reg_tiled_ok = false;
 
         DDH(double omega, const double * h_a, H1Space * fem, int nx, int ny, int block);
         void rhs(const double * f, float * b, cudaStream_t s);

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <unordered_set>
 
@@ -287,6 +288,14 @@ namespace cb200
                 const int g_el = E.elems[(size_t)el + (size_t)mx_elem * p];
                 std::memcpy(&g[3 * (size_t)nb2 * (el + (size_t)mx_elem * p)], &g_elem3[3 * (size_t)nb2 * g_el], sizeof(float) * 3 * nb2);
             }
+
+        // is the metric diagonal and the same in every element? (true for Mesh2D::uniform_rect; decides the kernel variant)
+        reg_tiled_ok = (getenv("CUDDH_B200_DDH_V1") == nullptr);
+        for (size_t t = 0; t < g.size() && reg_tiled_ok; ++t) {
+            const size_t within = t % ((size_t)3 * nb2);
+            if (within % 3 == 1 ? (g[t] != 0.0f) : (g[t] != g[within]))
+                reg_tiled_ok = false;
+        }
 
         // global inverse lumped mass (:556-565)
         std::vector<double> mi((size_t)g_ndof, 0.0);
