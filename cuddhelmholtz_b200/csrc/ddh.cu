@@ -216,7 +216,7 @@ namespace cb200
             float gz[4][4];  // [l][k] metric, y-y entry
         };
 
-        constexpr int V2_THREADS = 128; // 8 subdomains per CTA
+        constexpr int V2_THREADS = 64; // 4 subdomains per CTA
 
         __global__ void __launch_bounds__(V2_THREADS)
         ddh_kernel_reg4(const __grid_constant__ DDHConst4 C, const DDHArgs A, const int n_dom_launch)
