@@ -137,7 +137,7 @@ namespace cb200
     {
         int nb = 0, PE = 0;
         int64_t n_patches = 0, n_slots_total = 0, n_shared = 0;
-        int max_pdof = 0;
+        int max_pdof = 0, max_nsh = 0;   // largest patch: DOFs, shared DOFs
         std::vector<PatchHdr> hdr;
         std::vector<int> gid;              // patch-local -> global DOF, per patch ascending inside each class
         std::vector<int> slot;             // shared patch-local DOF -> index into the partial buffer

@@ -344,6 +344,7 @@ namespace cb200
                     plan.slot.push_back(next_slot[sh_index[v]]++);
                 }
             plan.max_pdof = std::max(plan.max_pdof, h.n_pdof);
+            plan.max_nsh = std::max(plan.max_nsh, h.n_pdof - h.n_int);
             for (int k = 0; k < h.n_elem; ++k) {
                 const int * Ie = &fem.I[(size_t)nb2 * plan.slot_elem[(size_t)p * PE + k]];
                 uint16_t * Le = &plan.L[((size_t)p * PE + k) * nb2];
@@ -360,6 +361,8 @@ namespace cb200
                 cnt[Lp[k] + 1]++;
             for (int d = 0; d < h.n_pdof; ++d)
                 cnt[d + 1] += cnt[d];
+            if (plan.cptr.size() & 1) // keep every patch's offsets 4-byte aligned (copied with 32-bit cp.async)
+                plan.cptr.push_back(0);
             h.cptr_begin = (int)plan.cptr.size();
             for (int d = 0; d <= h.n_pdof; ++d)
                 plan.cptr.push_back((uint16_t)cnt[d]);
@@ -378,6 +381,7 @@ namespace cb200
         d_gid.upload(gid);
         d_slot.upload(slot);
         d_L.upload(L);
+        cptr.resize(cptr.size() + 8, 0); // slack: the last patch's offsets are copied in 32-bit words
         d_cptr.upload(cptr);
         d_cent.upload(cent);
         d_slot_elem.upload(slot_elem);
