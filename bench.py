@@ -303,6 +303,11 @@ def extras(args, cb, torch):
         out["ddh"] = ddh_bench(cb, torch, drv if os.path.exists(drv) else None)
     except Exception as e:
         out["ddh"] = "failed: %r" % (e,)
+    try:  # BASELINE configs[2] size: one action of the 2048^2 / omega 100 / 262 144-subdomain operator (a solve is ~10^2-10^3 actions)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "config3.py"), "2048"], capture_output=True, text=True, timeout=900)
+        out["config3_2048"] = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:
+        out["config3_2048"] = "failed: %r" % (e,)
     return out
 
 

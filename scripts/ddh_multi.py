@@ -10,11 +10,13 @@ from cuddhelmholtz_b200.parallel import ShardedDDH
 
 nx = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 nb = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+omega_arg = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0     # 0: the examples' 2 pi nx / 10
+only_actions = int(sys.argv[4]) if len(sys.argv) > 4 else 0        # > 0: time this many actions instead of a full solve
 world, rank, lr = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lr)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-omega = 2 * np.pi * nx / 10
+omega = omega_arg if omega_arg > 0 else 2 * np.pi * nx / 10
 mesh = cb.Mesh2D.uniform_rect(nx, -1.0, 1.0, nx, -1.0, 1.0)
 fem = cb.H1Space(mesh, cb.Basis(nb))
 xy = fem.physical_coordinates()
@@ -40,7 +42,17 @@ e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
 e0.record()
 A.action_tensors(b, tmp)
 e1.record()
-out = cb.gmres(m, L, A, b, 20, 100, 1e-4)
+if only_actions > 0:
+    class _O:  # timing-only mode
+        num_iter = 0
+        num_matvec = only_actions
+        success = None
+    out = _O()
+    for _ in range(only_actions):
+        A.action_tensors(b, tmp)
+    L.copy_(tmp)
+else:
+    out = cb.gmres(m, L, A, b, 20, 100, 1e-4)
 e2.record()
 torch.cuda.synchronize()
 U = torch.empty(2 * n, dtype=torch.float64, device="cuda")
@@ -52,7 +64,7 @@ if world > 1:
 if rank == 0:
     info = D.info()
     print(json.dumps({"n_gpus": world, "nx": nx, "n_basis": nb, "n_domains": info["n_domains"], "nt": info["nt"], "n_lambda": m,
-                      "action_ms": float(t[0]), "gmres_seconds": float(t[1]) / 1e3, "restarts": out.num_iter, "matvec": out.num_matvec,
+                      "omega": omega, "action_ms": float(t[0]), "gmres_seconds": float(t[1]) / 1e3, "restarts": out.num_iter, "matvec": out.num_matvec,
                       "success": out.success, "u_norm": float(chk[0]), "action_fp32_tflops": D.flops() / (float(t[0]) * 1e-3) / 1e12}))
 if world > 1:
     dist.destroy_process_group()

@@ -117,11 +117,7 @@ def test_uniform_rect_2048_is_not_corrupt():
     I = fem.global_indices()
     assert I.min() == 0 and I.max() == fem.size() - 1
     # first-touch rule: the ids first seen in element e are consecutive and start where element e-1 stopped
-    first = np.full(fem.size(), -1, np.int64)
     flat = I.reshape(len(I), -1)
-    seen_max = -1
-    for e in range(0, len(flat), 997):
-        pass
     order = np.unique(flat.ravel(), return_index=True)[1]
     assert np.all(np.diff(order) > 0)  # id k first appears before id k+1 in the volume-index scan
 
