@@ -169,3 +169,35 @@ def test_vectors_must_be_device_pointers():
     x = torch.zeros(fem.size(), dtype=torch.float64)
     with pytest.raises(cb.CuddhError, match="DEVICE"):
         fs.restrict(x, x)
+
+
+def test_ensemble_c_abi_matches_reference(gold):
+    # EnsembleSpace through its own C-ABI entry points (what cuddhelmholtz_b200/cxx/include/EnsembleSpace.hpp calls)
+    import ctypes as C
+    lib = capi.load()
+    nx, nb = 8, 4
+    mesh = cb.Mesh2D.uniform_rect(nx, -1.0, 1.0, nx, -1.0, 1.0)
+    fem = cb.H1Space(mesh, cb.Basis(nb))
+    lab, nd = S.ddh_labels(nx, nx, nb)
+    lab = np.ascontiguousarray(lab, np.int32)
+    h = C.c_void_p()
+    capi.check(lib.cuddh_b200_ensemble_create(fem._h, nd, lab.ctypes.data_as(C.c_void_p), C.byref(h)))
+    try:
+        info = np.zeros(6, np.int64)
+        capi.check(lib.cuddh_b200_ensemble_info(h, info.ctypes.data_as(C.c_void_p)))
+        assert info[0] == nd and info[5] == 52
+        for name, key in [("gI", "gI"), ("sizes", "sizes"), ("elements", "elements"), ("faces", "faces"), ("sI", "sI"), ("fI", "fI"),
+                          ("pI", "pI"), ("fsizes", "fsizes"), ("cmap", "cmap"), ("n_elems", "n_elems"), ("n_faces", "n_faces")]:
+            cnt = C.c_int64()
+            ptr = lib.cuddh_b200_ensemble_array(h, name.encode(), C.byref(cnt))
+            arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_int)), shape=(cnt.value,)).copy()
+            assert np.array_equal(arr, gold.ens["ens_%d_%d_%s" % (nx, nb, key)]), name
+        assert lib.cuddh_b200_ensemble_array(h, b"nope", None) is None
+        # a label outside [0, n_spaces) is the reference's "illogically labeled" error
+        bad = lab.copy()
+        bad[0] = nd
+        h2 = C.c_void_p()
+        assert lib.cuddh_b200_ensemble_create(fem._h, nd, bad.ctypes.data_as(C.c_void_p), C.byref(h2)) != 0
+        assert b"illogically" in lib.cuddh_b200_last_error()
+    finally:
+        lib.cuddh_b200_ensemble_destroy(h)
