@@ -299,6 +299,24 @@ def extras(args, cb, torch):
             out["reference_gpu_kernels"] = json.loads(r.stdout.strip().splitlines()[-1])
         except Exception as e:
             out["reference_gpu_kernels"] = "failed: %r" % (e,)
+    try:  # the other reading of "p=4" (SURVEY R3): n_basis 4 (degree 3), the order the DDH configs use
+        peak, _ = measured_peaks()
+        mesh = cb.Mesh2D.uniform_rect(args.nx, -1.0, 1.0, args.nx, -1.0, 1.0)
+        fem = cb.H1Space(mesh, cb.Basis(4))
+        n4 = fem.size()
+        xx = torch.rand(n4, dtype=torch.float64, device="cuda") - 0.5
+        yy = torch.empty_like(xx)
+        aa = torch.rand(n4, dtype=torch.float64, device="cuda") + 0.5
+        res = {"ndof": n4}
+        for name, op in (("stiffness", cb.StiffnessMatrix(fem)), ("mass_weighted", cb.MassMatrix(aa, fem))):
+            op.action(xx, yy)
+            pms, sms = op.time_phases(xx, yy, 20)
+            res[name] = {"ms": pms + sms, "gdofs": n4 / ((pms + sms) * 1e-3) / 1e9, "hbm_frac_patch_kernel": op.algorithmic_bytes() / (pms * 1e-3) / 1e9 / peak}
+        out["n_basis_4"] = res
+        del mesh, fem, xx, yy, aa
+        torch.cuda.empty_cache()
+    except Exception as e:
+        out["n_basis_4"] = "failed: %r" % (e,)
     try:
         out["ddh"] = ddh_bench(cb, torch, drv if os.path.exists(drv) else None)
     except Exception as e:
