@@ -136,6 +136,7 @@ namespace cb200
     struct Plan
     {
         int nb = 0, PE = 0;
+        bool node_major = false;           // L / cent laid out (PE, nb*nb) per patch instead of (nb*nb, PE): thread-per-element kernels
         int64_t n_patches = 0, n_slots_total = 0, n_shared = 0;
         int max_pdof = 0, max_nsh = 0;   // largest patch: DOFs, shared DOFs
         std::vector<PatchHdr> hdr;
@@ -145,11 +146,16 @@ namespace cb200
         std::vector<uint16_t> cptr;        // per patch n_pdof+1 offsets into its slice of cent
         std::vector<uint16_t> cent;        // (nb*nb*PE, n_patches): element-local entries (slot*nb*nb + node) grouped by DOF
         std::vector<int> slot_elem;        // (PE, n_patches) global element id of each slot, -1 = padding
+        std::vector<int> Ig;               // node-major plans only: (PE, nb*nb, n_patches) global DOF of (slot, node), 0 = padding
+        std::vector<uint16_t> cent4;       // node-major plans only: per patch-local DOF (indexed like gid) its first four CSR entries,
+                                           // 0xFFFF = none; entry 3 == 0xFFFE: more than four, continue in cptr/cent from entry 3
+        std::vector<int> target;           // node-major plans only: per patch-local DOF the global DOF (private) or partial slot (shared)
         std::vector<int> sh_gid, sh_ptr;   // shared DOFs: global id, CSR into the partial buffer (patch order)
         // device mirrors
         DevBuf<PatchHdr> d_hdr;
-        DevBuf<int> d_gid, d_slot, d_slot_elem, d_sh_gid, d_sh_ptr;
-        DevBuf<uint16_t> d_L, d_cptr, d_cent;
+        DevBuf<int> d_gid, d_slot, d_slot_elem, d_sh_gid, d_sh_ptr, d_Ig;
+        DevBuf<uint16_t> d_L, d_cptr, d_cent, d_cent4;
+        DevBuf<int> d_target;
         bool on_device = false;
         void ensure_device();
     };
@@ -166,6 +172,7 @@ namespace cb200
         DevBuf<int> d_I;
         DevBuf<double> d_xy, d_corners;  // d_corners: (8, n_elem)
         std::unique_ptr<Plan> plan;      // built lazily by the operators
+        std::unique_ptr<Plan> plan_tpe;  // node-major plan with 32-multiple patches (thread-per-element kernels), lazy
         DevBuf<int> d_tr_ptr, d_tr_src;  // transposed map DOF -> element-local entries (ordered assembly), lazy
         void ensure_transpose();
 
@@ -175,6 +182,7 @@ namespace cb200
         const double * device_corners();
         Plan & get_plan();       // builds (once) and uploads
         Plan & get_plan_host();  // builds (once), host arrays only
+        Plan & get_plan_tpe();   // thread-per-element variant, builds (once) and uploads
     };
 
     // ---- face space: reference source/H1Space.cpp:129-219 ----
@@ -199,5 +207,5 @@ namespace cb200
         void ensure_device();
     };
 
-    void build_plan(H1Space & fem, Plan & plan);
+    void build_plan(H1Space & fem, Plan & plan, bool tpe = false);
 } // namespace cb200

@@ -127,6 +127,16 @@ namespace cb200
         return *plan;
     }
 
+    Plan & H1Space::get_plan_tpe()
+    {
+        if (!plan_tpe) {
+            plan_tpe.reset(new Plan);
+            build_plan(*this, *plan_tpe, true);
+        }
+        plan_tpe->ensure_device();
+        return *plan_tpe;
+    }
+
     // ---- FaceSpace: reference source/H1Space.cpp:129-187 ----
     FaceSpace::FaceSpace(H1Space * fem_, int64_t nf, const int * faces_) : fem(fem_), nb(fem_->nb), n_faces(nf)
     {
@@ -220,20 +230,32 @@ namespace cb200
         }
     } // namespace
 
-    void build_plan(H1Space & fem, Plan & plan)
+    void build_plan(H1Space & fem, Plan & plan, bool tpe)
     {
         const Mesh & mesh = *fem.mesh;
         const int nb = fem.nb, nb2 = nb * nb;
         const int64_t nel = fem.n_elem;
         int px, py;
         pick_patch_shape(nb, px, py);
-        if (const char * e = getenv("CUDDH_B200_PX")) // experiment knobs (scripts/sweep_ops.py)
-            px = std::max(1, atoi(e));
-        if (const char * e = getenv("CUDDH_B200_PY"))
-            py = std::max(1, atoi(e));
+        if (tpe) { // one thread per element: a patch is one warpgroup (128 threads) of elements, 16 x 8 tiles
+            px = 16;
+            py = 8;
+            if (const char * e = getenv("CUDDH_B200_TPE_PX"))
+                px = std::max(1, atoi(e));
+            if (const char * e = getenv("CUDDH_B200_TPE_PY"))
+                py = std::max(1, atoi(e));
+            CB_REQUIRE((px * py) % 32 == 0, "thread-per-element plan: patch size must be a multiple of 32");
+        }
+        else {
+            if (const char * e = getenv("CUDDH_B200_PX")) // experiment knobs (scripts/sweep_ops.py)
+                px = std::max(1, atoi(e));
+            if (const char * e = getenv("CUDDH_B200_PY"))
+                py = std::max(1, atoi(e));
+        }
         const int PE = px * py;
         plan.nb = nb;
         plan.PE = PE;
+        plan.node_major = tpe;
 
         // 1. patches -> element lists
         std::vector<std::vector<int>> pel;
@@ -319,6 +341,8 @@ namespace cb200
         plan.slot.clear();
         plan.L.assign((size_t)np * PE * nb2, 0);
         plan.cent.assign((size_t)np * PE * nb2, 0);
+        if (plan.node_major)
+            plan.Ig.assign((size_t)np * PE * nb2, 0);
         plan.cptr.clear();
         plan.cptr.reserve(plan.gid.capacity() + (size_t)np);
         std::vector<int> local((size_t)fem.ndof, -1);
@@ -345,20 +369,25 @@ namespace cb200
                 }
             plan.max_pdof = std::max(plan.max_pdof, h.n_pdof);
             plan.max_nsh = std::max(plan.max_nsh, h.n_pdof - h.n_int);
+            // entry id of (slot k, node a): element-major k*nb2 + a, or node-major a*PE + k (thread-per-element kernels)
+            auto entry = [&](int k, int a) { return plan.node_major ? a * PE + k : k * nb2 + a; };
             for (int k = 0; k < h.n_elem; ++k) {
                 const int * Ie = &fem.I[(size_t)nb2 * plan.slot_elem[(size_t)p * PE + k]];
-                uint16_t * Le = &plan.L[((size_t)p * PE + k) * nb2];
+                uint16_t * Lp = &plan.L[(size_t)p * PE * nb2];
                 for (int a = 0; a < nb2; ++a)
-                    Le[a] = (uint16_t)local[Ie[a]];
+                    Lp[entry(k, a)] = (uint16_t)local[Ie[a]];
+                if (plan.node_major)
+                    for (int a = 0; a < nb2; ++a)
+                        plan.Ig[(size_t)p * PE * nb2 + (size_t)a * PE + k] = Ie[a];
             }
             // CSR: patch-local DOF -> its element-local entries in ascending (slot, node) order. This fixes the
             // summation order of every DOF (deterministic assembly without atomics or colouring).
             CB_REQUIRE((size_t)PE * nb2 < 65536, "assembly plan: patch too large for 16-bit entry ids");
             cnt.assign((size_t)h.n_pdof + 1, 0);
             const uint16_t * Lp = &plan.L[(size_t)p * PE * nb2];
-            const int n_ent = h.n_elem * nb2;
-            for (int k = 0; k < n_ent; ++k)
-                cnt[Lp[k] + 1]++;
+            for (int k = 0; k < h.n_elem; ++k)
+                for (int a = 0; a < nb2; ++a)
+                    cnt[Lp[entry(k, a)] + 1]++;
             for (int d = 0; d < h.n_pdof; ++d)
                 cnt[d + 1] += cnt[d];
             if (plan.cptr.size() & 1) // keep every patch's offsets 4-byte aligned (copied with 32-bit cp.async)
@@ -367,8 +396,23 @@ namespace cb200
             for (int d = 0; d <= h.n_pdof; ++d)
                 plan.cptr.push_back((uint16_t)cnt[d]);
             uint16_t * ce = &plan.cent[(size_t)p * PE * nb2];
-            for (int k = 0; k < n_ent; ++k)
-                ce[cnt[Lp[k]]++] = (uint16_t)k;
+            for (int k = 0; k < h.n_elem; ++k)
+                for (int a = 0; a < nb2; ++a)
+                    ce[cnt[Lp[entry(k, a)]]++] = (uint16_t)entry(k, a);
+            if (plan.node_major) { // fixed-width records for the helper warps of volume_action_ws
+                plan.cent4.resize(plan.gid.size() * 4, 0xFFFF);
+                plan.target.resize(plan.gid.size(), 0);
+                const uint16_t * cp = &plan.cptr[h.cptr_begin];
+                for (int d = 0; d < h.n_pdof; ++d) {
+                    uint16_t * r = &plan.cent4[((size_t)h.pdof_begin + d) * 4];
+                    const int n = cp[d + 1] - cp[d];
+                    for (int k = 0; k < std::min(n, 4); ++k)
+                        r[k] = ce[cp[d] + k];
+                    if (n > 4)
+                        r[3] = 0xFFFE;
+                    plan.target[(size_t)h.pdof_begin + d] = d < h.n_int ? plan.gid[(size_t)h.pdof_begin + d] : plan.slot[(size_t)h.slot_begin + d - h.n_int];
+                }
+            }
         }
 
     }
@@ -385,6 +429,11 @@ namespace cb200
         d_cptr.upload(cptr);
         d_cent.upload(cent);
         d_slot_elem.upload(slot_elem);
+        if (node_major) {
+            d_Ig.upload(Ig);
+            d_cent4.upload(cent4);
+            d_target.upload(target);
+        }
         d_sh_gid.upload(sh_gid);
         d_sh_ptr.upload(sh_ptr);
         on_device = true;

@@ -41,6 +41,9 @@ namespace cb200
             const uint16_t * cptr;
             const uint16_t * cent;
             int PE;
+            const int * Ig; // node-major plans: global DOF of (patch, node, slot)
+            const uint2 * cent4; // node-major plans: first four CSR entries of every patch-local DOF (Plan::cent4)
+            const int * target;  // node-major plans: global DOF / partial slot of every patch-local DOF
         };
 
         // 1-D tables as a kernel parameter (constant bank). Both orientations are stored so that every inner loop
@@ -587,6 +590,489 @@ namespace cb200
             }
         }
 
+        // ------------------------------------------------------------------------------------------
+        // Thread-per-element action kernel (n_basis <= 5): the default for the headline orders.
+        //
+        // ncu on the lane-per-row kernel above (profiles/r01_notes.md) pins its plateau on the L1TEX / shared-memory pipe
+        // (two transposes per element through a per-warp scratch, partial warps, bank conflicts: ~69 wavefronts per element)
+        // and on instruction issue (one LDCU per DFMA pair, address arithmetic). Here ONE THREAD owns ONE ELEMENT:
+        //   * U (nb x nb) and the result (nb x nb) live in registers for the whole element; the sum-factorised contractions
+        //     are straight DFMA chains over register operands and uniform-register table values, no transposes, no scratch,
+        //     no __syncwarp, all 32 lanes busy (a patch is a whole number of warps of elements);
+        //   * every shared-memory access of the contraction phase is a full-warp, conflict-free, element-fastest access
+        //     (node-major local map L[k][e] and result array su[k][e]): 2 wavefronts per 32 elements per value;
+        //   * the metric data of an element is read as 128-bit loads from a [value pair][element] layout, one contiguous
+        //     512-byte run per warp instruction, one quadrature row ahead of its use.
+        // The outer quadrature loop is rolled and the tables are indexed through an opaque zero so that ptxas streams them
+        // through uniform registers (LDCU) next to the DFMAs instead of hoisting all 60 doubles into 120 registers.
+        // Staging (A) and deterministic assembly (C) are those of the kernel above, on a node-major plan.
+        // ------------------------------------------------------------------------------------------
+        template <int NB, int NQ, bool STIFF>
+        struct TpeCfg
+        {
+            static constexpr int NKI = STIFF ? 3 : 1;
+            static constexpr int KR = (NKI * NQ + 1) & ~1; // metric values per quadrature row, padded to even
+            static constexpr int NK2 = NQ * KR / 2;        // 16-byte pairs per element
+        };
+
+        template <int NB, int NQ, bool STIFF, int PE, int MINB>
+        __global__ void __launch_bounds__(PE, MINB)
+        volume_action_tpe(const __grid_constant__ Tables<NB, NQ, STIFF> tab, const PlanDev plan, const double2 * __restrict__ G,
+                          const double * __restrict__ x, double * __restrict__ y, double * __restrict__ partial, const double c,
+                          const int accumulate, const int max_pdof, const int n_patches, const int pf_dist, const int zero)
+        {
+            using Cfg = TpeCfg<NB, NQ, STIFF>;
+            constexpr int NB2 = NB * NB;
+            constexpr int NKI = Cfg::NKI, KR = Cfg::KR, NK2 = Cfg::NK2;
+
+            extern __shared__ __align__(16) unsigned char smem_raw[];
+            const int mpe = (max_pdof + 1) & ~1;
+            double * xloc = reinterpret_cast<double *>(smem_raw);        // [mpe]
+            double * su = xloc + mpe;                                     // [NB2][PE]
+            uint16_t * Ls = reinterpret_cast<uint16_t *>(su + NB2 * PE);  // [NB2][PE]
+            uint16_t * cents = Ls + NB2 * PE;                             // [NB2 * PE]
+            int * gids = reinterpret_cast<int *>(cents + NB2 * PE);       // [max_pdof]
+            uint16_t * cptrs = reinterpret_cast<uint16_t *>(gids + max_pdof); // [max_pdof + 1 (+1)]
+
+            const int tid = threadIdx.x;
+            const PatchHdr hdr = plan.hdr[blockIdx.x];
+
+            const int pnext = (pf_dist > 0 && (int)blockIdx.x + pf_dist < n_patches) ? (int)blockIdx.x + pf_dist : -1;
+            constexpr size_t g_patch = (size_t)NK2 * PE; // double2 per patch
+            if (tid == 0) {
+                bulk_prefetch_l2(G + (size_t)blockIdx.x * g_patch, g_patch * sizeof(double2));
+                if (pnext >= 0) {
+                    bulk_prefetch_l2(G + (size_t)pnext * g_patch, g_patch * sizeof(double2));
+                    bulk_prefetch_l2(plan.L + (size_t)pnext * PE * NB2, (size_t)PE * NB2 * sizeof(uint16_t));
+                    bulk_prefetch_l2(plan.cent + (size_t)pnext * PE * NB2, (size_t)PE * NB2 * sizeof(uint16_t));
+                }
+            }
+            PatchHdr hnext;
+            if (tid == 32 % PE && pnext >= 0)
+                hnext = plan.hdr[pnext];
+
+            // ---- A. stage the patch ----
+            {
+                constexpr int AU = 9;
+                const int * gidp = plan.gid + hdr.pdof_begin;
+                for (int base = tid; base < hdr.n_pdof; base += AU * PE) {
+                    int gi[AU];
+                    double xv[AU];
+#pragma unroll
+                    for (int a = 0; a < AU; ++a) {
+                        const int d = base + a * PE;
+                        gi[a] = (d < hdr.n_pdof) ? __ldg(gidp + d) : -1;
+                    }
+#pragma unroll
+                    for (int a = 0; a < AU; ++a)
+                        xv[a] = (gi[a] >= 0) ? __ldg(x + gi[a]) : 0.0;
+#pragma unroll
+                    for (int a = 0; a < AU; ++a) {
+                        const int d = base + a * PE;
+                        if (d < hdr.n_pdof) {
+                            xloc[d] = xv[a];
+                            gids[d] = gi[a];
+                        }
+                    }
+                }
+                // node-major local map and CSR entries: PE * NB2 * 2 bytes each, a multiple of 16
+                const uint4 * Lg = reinterpret_cast<const uint4 *>(plan.L + (size_t)hdr.elem_begin * NB2);
+                const uint4 * Cg = reinterpret_cast<const uint4 *>(plan.cent + (size_t)hdr.elem_begin * NB2);
+                uint4 * Ls4 = reinterpret_cast<uint4 *>(Ls);
+                uint4 * Cs4 = reinterpret_cast<uint4 *>(cents);
+                constexpr int n16 = PE * NB2 / 8;
+                for (int k = tid; k < n16; k += PE) {
+                    Ls4[k] = __ldg(Lg + k);
+                    Cs4[k] = __ldg(Cg + k);
+                }
+                const uint32_t * cpg = reinterpret_cast<const uint32_t *>(plan.cptr + hdr.cptr_begin); // cptr_begin is even
+                uint32_t * cps = reinterpret_cast<uint32_t *>(cptrs);
+                for (int k = tid; k < (hdr.n_pdof + 2) >> 1; k += PE)
+                    cps[k] = __ldg(cpg + k);
+            }
+            if (tid == 32 % PE && pnext >= 0) {
+                const int * g0 = plan.gid + (hnext.pdof_begin & ~3);
+                bulk_prefetch_l2(g0, ((size_t)hnext.n_pdof + 4) * sizeof(int));
+                const uint16_t * c0 = plan.cptr + (hnext.cptr_begin & ~7);
+                bulk_prefetch_l2(c0, ((size_t)hnext.n_pdof + 9) * sizeof(uint16_t));
+            }
+            __syncthreads();
+
+            // ---- B. one element per thread, everything in registers ----
+            {
+                const int e = tid;
+                double U[NB2], out[NB2];
+#pragma unroll
+                for (int k = 0; k < NB2; ++k)
+                    U[k] = xloc[Ls[k * PE + e]];
+#pragma unroll
+                for (int k = 0; k < NB2; ++k)
+                    out[k] = 0.0;
+                const double2 * gp = G + (size_t)blockIdx.x * g_patch + e;
+                double g[KR];
+#pragma unroll
+                for (int m = 0; m < KR / 2; ++m) {
+                    const double2 v = __ldcs(gp + m * PE);
+                    g[2 * m] = v.x;
+                    g[2 * m + 1] = v.y;
+                }
+#pragma unroll 1
+                for (int tx = 0; tx < NQ; ++tx) {
+                    const int z = tx * zero; // 0 at run time; keeps the ty-indexed table loads inside this loop (see header)
+                    // first-index contraction for quadrature row tx: pu[j] = sum_i P(tx,i) U[i][j] (and D)
+                    double pu[NB], du[STIFF ? NB : 1];
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) {
+                        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                        for (int i = 0; i < NB; ++i) {
+                            s0 = fma(tab.Prow[tx][i], U[i + NB * j], s0);
+                            if (STIFF)
+                                s1 = fma(tab.Drow[tx][i], U[i + NB * j], s1);
+                        }
+                        pu[j] = s0;
+                        if (STIFF)
+                            du[j] = s1;
+                    }
+                    double a0[NB], a1[STIFF ? NB : 1];
+#pragma unroll
+                    for (int t = 0; t < NB; ++t) {
+                        a0[t] = 0.0;
+                        if (STIFF)
+                            a1[t] = 0.0;
+                    }
+#pragma unroll
+                    for (int ty = 0; ty < NQ; ++ty) {
+                        if (STIFF) {
+                            double Dx = 0.0, Dy = 0.0;
+#pragma unroll
+                            for (int l = 0; l < NB; ++l) {
+                                Dx = fma(tab.Prow[ty + z][l], du[l], Dx);
+                                Dy = fma(tab.Drow[ty + z][l], pu[l], Dy);
+                            }
+                            const double A = g[NKI * ty], B = g[NKI * ty + (NKI > 1 ? 1 : 0)], C = g[NKI * ty + (NKI > 2 ? 2 : 0)];
+                            const double F0 = A * Dx + B * Dy;
+                            const double F1 = B * Dx + C * Dy;
+#pragma unroll
+                            for (int t = 0; t < NB; ++t) {
+                                a0[t] = fma(tab.Prow[ty + z][t], F0, a0[t]);
+                                a1[t] = fma(tab.Drow[ty + z][t], F1, a1[t]);
+                            }
+                        }
+                        else {
+                            double ppu = 0.0;
+#pragma unroll
+                            for (int l = 0; l < NB; ++l)
+                                ppu = fma(tab.Prow[ty + z][l], pu[l], ppu);
+                            const double val = g[ty] * ppu;
+#pragma unroll
+                            for (int t = 0; t < NB; ++t)
+                                a0[t] = fma(tab.Prow[ty + z][t], val, a0[t]);
+                        }
+                    }
+                    // next quadrature row's metric values: in flight during the back-contraction below and the next
+                    // row's first-index contraction
+                    if (tx + 1 < NQ) {
+#pragma unroll
+                        for (int m = 0; m < KR / 2; ++m) {
+                            const double2 v = __ldcs(gp + ((tx + 1) * (KR / 2) + m) * PE);
+                            g[2 * m] = v.x;
+                            g[2 * m + 1] = v.y;
+                        }
+                    }
+                    // first-index contraction back to the basis: out[i][t] += D(tx,i) a0[t] + P(tx,i) a1[t]
+#pragma unroll
+                    for (int t = 0; t < NB; ++t)
+#pragma unroll
+                        for (int i = 0; i < NB; ++i) {
+                            if (STIFF)
+                                out[i + NB * t] = fma(tab.Drow[tx][i], a0[t], fma(tab.Prow[tx][i], a1[t], out[i + NB * t]));
+                            else
+                                out[i + NB * t] = fma(tab.Prow[tx][i], a0[t], out[i + NB * t]);
+                        }
+                }
+#pragma unroll
+                for (int k = 0; k < NB2; ++k)
+                    su[k * PE + e] = out[k];
+            }
+            __syncthreads();
+
+            // ---- C. deterministic assembly + write-back (CSR order of the plan) ----
+            {
+                const int * slotp = plan.slot + hdr.slot_begin - hdr.n_int;
+                for (int d = tid; d < hdr.n_pdof; d += PE) {
+                    const int b = cptrs[d], e = cptrs[d + 1];
+                    double sum = 0.0;
+                    for (int k = b; k < e; ++k)
+                        sum += su[cents[k]];
+                    if (d < hdr.n_int) {
+                        const int gi = gids[d];
+                        const double v = c * sum;
+                        y[gi] = accumulate ? (y[gi] + v) : v;
+                    }
+                    else
+                        partial[__ldg(slotp + d)] = sum;
+                }
+            }
+        }
+
+        // ------------------------------------------------------------------------------------------
+        // Warp-specialised persistent version of the thread-per-element kernel (the default for n_basis <= 5).
+        //
+        // ncu on volume_action_tpe: half the instructions and 60 % of the shared-memory wavefronts of the lane-per-row
+        // kernel, but only 28 % of the warp samples are in the contraction phase: with 200+ registers per thread there are
+        // 8 warps per SM, and they spend most of their time in the latency-bound staging and assembly phases. So the phases
+        // are given to different warps of a persistent CTA (256 threads, 2 CTAs per SM):
+        //   * warpgroup 1 (compute, setmaxnreg 208): one element per thread. Waits for its patch buffer, pulls U[k][e] into
+        //     registers, runs the contractions (metric values straight from global memory, one quadrature row ahead,
+        //     L2 hits because the block was bulk-prefetched), writes the element results back INTO THE SAME BUFFER.
+        //   * warpgroup 0 (helper, setmaxnreg 48): for the next patch, gathers x through the node-major global index map
+        //     with 8-byte cp.async straight into that patch's buffer (no registers, no stall), prefetches index lists and
+        //     metric blocks into L2; for the previous patch, runs the deterministic CSR assembly out of its buffer and
+        //     writes y / the partial slots.
+        // Three patch buffers rotate: filling (i+1), computing (i), assembling (i-1). Hand-offs are named barriers
+        // (bar.arrive / bar.sync over the 256 threads); the helper warpgroup frees a buffer by its own program order.
+        // Summation order per DOF is the plan's CSR order, exactly as in the other kernels: bitwise reproducible.
+        // ------------------------------------------------------------------------------------------
+        __device__ __forceinline__ void named_sync(const int id, const int n)
+        {
+            asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+        }
+        __device__ __forceinline__ void named_arrive(const int id, const int n)
+        {
+            asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+        }
+        // 16-byte metric pairs of one quadrature row that are no longer needed after quadrature point ty
+        template <int NQ, int NKI, int KR>
+        __host__ __device__ constexpr int pairs_done(int ty)
+        {
+            return ty < 0 ? 0 : (ty + 1 >= NQ ? KR / 2 : (NKI * (ty + 1)) / 2);
+        }
+
+        template <int NB, int NQ, bool STIFF>
+        __global__ void __launch_bounds__(256, 2)
+        volume_action_ws(const __grid_constant__ Tables<NB, NQ, STIFF> tab, const PlanDev plan, const double2 * __restrict__ G,
+                         const double * __restrict__ x, double * __restrict__ y, double * __restrict__ partial, const double c,
+                         const int accumulate, const int n_patches, const int zero)
+        {
+            using Cfg = TpeCfg<NB, NQ, STIFF>;
+            constexpr int PE = 128;
+            constexpr int NB2 = NB * NB;
+            constexpr int NKI = Cfg::NKI, KR = Cfg::KR, NK2 = Cfg::NK2;
+            constexpr int BUF = NB2 * PE; // doubles per patch buffer
+            constexpr size_t g_patch = (size_t)NK2 * PE; // double2 per patch
+            constexpr int FULL = 1, READY = 4, HELPER = 7; // named barrier ids (0 is __syncthreads)
+
+            extern __shared__ __align__(16) unsigned char smem_raw[];
+            double * bufs = reinterpret_cast<double *>(smem_raw); // [3][NB2][PE]
+
+            const int wg = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 7), 0); // warp-uniform by construction
+            const int t = threadIdx.x & 127;
+            const int stride = gridDim.x;
+            const int n_iter = (n_patches - (int)blockIdx.x + stride - 1) / stride;
+
+            if (wg == 0) {
+                // =========================== helper warpgroup ===========================
+                asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+                auto issue_gather = [&](const int i) {
+                    const int p = (int)blockIdx.x + i * stride;
+                    double * b = bufs + (i % 3) * BUF + t;
+                    const int * ig = plan.Ig + (size_t)p * BUF + t;
+#pragma unroll
+                    constexpr int GU = 9; // index loads in flight per thread
+#pragma unroll
+                    for (int k0 = 0; k0 < NB2; k0 += GU) {
+                        int idx[GU];
+#pragma unroll
+                        for (int a = 0; a < GU; ++a)
+                            idx[a] = (k0 + a < NB2) ? __ldg(ig + (k0 + a) * PE) : 0;
+#pragma unroll
+                        for (int a = 0; a < GU; ++a)
+                            if (k0 + a < NB2)
+                                cp_async8(b + (k0 + a) * PE, x + idx[a]);
+                    }
+                    // L2 prefetch: this patch's metric block (read by the compute warpgroup next iteration) and the index
+                    // lists of the patch after it
+                    const int p2 = p + stride;
+                    if (t == 0)
+                        bulk_prefetch_l2(G + (size_t)p * g_patch, g_patch * sizeof(double2));
+                    if (t == 32 && p2 < n_patches) {
+                        bulk_prefetch_l2(plan.Ig + (size_t)p2 * BUF, (size_t)BUF * sizeof(int));
+                        const PatchHdr h2 = plan.hdr[p2];
+                        bulk_prefetch_l2(plan.target + (h2.pdof_begin & ~3), ((size_t)h2.n_pdof + 4) * sizeof(int));
+                        bulk_prefetch_l2(plan.cent4 + (h2.pdof_begin & ~1), ((size_t)h2.n_pdof + 2) * sizeof(uint2));
+                    }
+                };
+                auto assemble = [&](const int i) {
+                    const int p = (int)blockIdx.x + i * stride;
+                    const PatchHdr hdr = plan.hdr[p];
+                    const double * su = bufs + (i % 3) * BUF;
+                    const uint2 * recp = plan.cent4 + hdr.pdof_begin;
+                    const int * tgtp = plan.target + hdr.pdof_begin;
+                    constexpr int CU = 4; // DOFs in flight per thread: record and target loads of a batch are independent
+                    for (int base = t; base < hdr.n_pdof; base += CU * PE) {
+                        uint2 rec[CU];
+                        int tgt[CU];
+#pragma unroll
+                        for (int a = 0; a < CU; ++a) {
+                            const int d = base + a * PE;
+                            rec[a] = (d < hdr.n_pdof) ? __ldg(recp + d) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+                            tgt[a] = (d < hdr.n_pdof) ? __ldg(tgtp + d) : 0;
+                        }
+#pragma unroll
+                        for (int a = 0; a < CU; ++a) {
+                            const int d = base + a * PE;
+                            const unsigned c0 = rec[a].x & 0xFFFFu, c1 = rec[a].x >> 16, c2 = rec[a].y & 0xFFFFu, c3 = rec[a].y >> 16;
+                            // entries added left to right = the plan's CSR order (adding to 0.0 first is exact)
+                            double sum = c0 != 0xFFFFu ? su[c0] : 0.0;
+                            if (c1 != 0xFFFFu)
+                                sum += su[c1];
+                            if (c2 != 0xFFFFu)
+                                sum += su[c2];
+                            if (c3 < 0xFFFEu)
+                                sum += su[c3];
+                            else if (c3 == 0xFFFEu) { // more than four contributions (high-valence vertex): rest of the CSR row
+                                const uint16_t * cp = plan.cptr + hdr.cptr_begin;
+                                const uint16_t * ce = plan.cent + (size_t)hdr.elem_begin * NB2;
+                                for (int k = __ldg(cp + d) + 3, e = __ldg(cp + d + 1); k < e; ++k)
+                                    sum += su[__ldg(ce + k)];
+                            }
+                            if (d < hdr.n_int) {
+                                const double v = c * sum;
+                                y[tgt[a]] = accumulate ? (y[tgt[a]] + v) : v;
+                            }
+                            else if (d < hdr.n_pdof)
+                                partial[tgt[a]] = sum;
+                        }
+                    }
+                };
+
+                issue_gather(0);
+                cp_async_wait_all();
+                named_sync(HELPER, 128);
+                named_arrive(FULL + 0, 256);
+                for (int i = 0; i < n_iter; ++i) {
+                    if (i + 1 < n_iter)
+                        issue_gather(i + 1);
+                    if (i >= 1) {
+                        named_sync(READY + (i - 1) % 3, 256);
+                        assemble(i - 1);
+                    }
+                    cp_async_wait_all();
+                    named_sync(HELPER, 128); // every helper thread is done reading buffer i-1 and its copies for i+1 landed
+                    if (i + 1 < n_iter)
+                        named_arrive(FULL + (i + 1) % 3, 256);
+                }
+                named_sync(READY + (n_iter - 1) % 3, 256);
+                assemble(n_iter - 1);
+            }
+            else {
+                // =========================== compute warpgroup: one element per thread ===========================
+                asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+                const int e = t;
+                double g[KR];
+                {
+                    const double2 * gp0 = G + (size_t)blockIdx.x * g_patch + e;
+#pragma unroll
+                    for (int m = 0; m < KR / 2; ++m) {
+                        const double2 v = __ldcs(gp0 + m * PE);
+                        g[2 * m] = v.x;
+                        g[2 * m + 1] = v.y;
+                    }
+                }
+                for (int i = 0; i < n_iter; ++i) {
+                    const int p = (int)blockIdx.x + i * stride;
+                    double * b = bufs + (i % 3) * BUF + e;
+                    const double2 * gp = G + (size_t)p * g_patch + e;
+                    // first row of the next patch of this CTA (or of this one again at the end: a harmless reload)
+                    const double2 * gp_next_patch = (i + 1 < n_iter) ? gp + (size_t)stride * g_patch : gp;
+                    named_sync(FULL + i % 3, 256);
+                    double U[NB2], out[NB2];
+#pragma unroll
+                    for (int k = 0; k < NB2; ++k)
+                        U[k] = b[k * PE];
+#pragma unroll
+                    for (int k = 0; k < NB2; ++k)
+                        out[k] = 0.0;
+#pragma unroll 1
+                    for (int tx = 0; tx < NQ; ++tx) {
+                        const int z = tx * zero; // 0 at run time; keeps the ty-indexed table loads inside this loop
+                        const double2 * gnext = (tx + 1 < NQ) ? gp + (tx + 1) * (KR / 2) * PE : gp_next_patch;
+                        double pu[NB], du[STIFF ? NB : 1];
+#pragma unroll
+                        for (int j = 0; j < NB; ++j) {
+                            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                            for (int ii = 0; ii < NB; ++ii) {
+                                s0 = fma(tab.Prow[tx][ii], U[ii + NB * j], s0);
+                                if (STIFF)
+                                    s1 = fma(tab.Drow[tx][ii], U[ii + NB * j], s1);
+                            }
+                            pu[j] = s0;
+                            if (STIFF)
+                                du[j] = s1;
+                        }
+                        double a0[NB], a1[STIFF ? NB : 1];
+#pragma unroll
+                        for (int q = 0; q < NB; ++q) {
+                            a0[q] = 0.0;
+                            if (STIFF)
+                                a1[q] = 0.0;
+                        }
+#pragma unroll
+                        for (int ty = 0; ty < NQ; ++ty) {
+                            if (STIFF) {
+                                double Dx = 0.0, Dy = 0.0;
+#pragma unroll
+                                for (int l = 0; l < NB; ++l) {
+                                    Dx = fma(tab.Prow[ty + z][l], du[l], Dx);
+                                    Dy = fma(tab.Drow[ty + z][l], pu[l], Dy);
+                                }
+                                const double A = g[NKI * ty], B = g[NKI * ty + (NKI > 1 ? 1 : 0)], C = g[NKI * ty + (NKI > 2 ? 2 : 0)];
+                                const double F0 = A * Dx + B * Dy;
+                                const double F1 = B * Dx + C * Dy;
+#pragma unroll
+                                for (int q = 0; q < NB; ++q) {
+                                    a0[q] = fma(tab.Prow[ty + z][q], F0, a0[q]);
+                                    a1[q] = fma(tab.Drow[ty + z][q], F1, a1[q]);
+                                }
+                            }
+                            else {
+                                double ppu = 0.0;
+#pragma unroll
+                                for (int l = 0; l < NB; ++l)
+                                    ppu = fma(tab.Prow[ty + z][l], pu[l], ppu);
+                                const double val = g[ty] * ppu;
+#pragma unroll
+                                for (int q = 0; q < NB; ++q)
+                                    a0[q] = fma(tab.Prow[ty + z][q], val, a0[q]);
+                            }
+                            // metric values consumed so far are replaced by the next row's (a whole row iteration ahead)
+#pragma unroll
+                            for (int m = pairs_done<NQ, NKI, KR>(ty - 1); m < pairs_done<NQ, NKI, KR>(ty); ++m) {
+                                const double2 v = __ldcs(gnext + m * PE);
+                                g[2 * m] = v.x;
+                                g[2 * m + 1] = v.y;
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < NB; ++q)
+#pragma unroll
+                            for (int ii = 0; ii < NB; ++ii) {
+                                if (STIFF)
+                                    out[ii + NB * q] = fma(tab.Drow[tx][ii], a0[q], fma(tab.Prow[tx][ii], a1[q], out[ii + NB * q]));
+                                else
+                                    out[ii + NB * q] = fma(tab.Prow[tx][ii], a0[q], out[ii + NB * q]);
+                            }
+                    }
+#pragma unroll
+                    for (int k = 0; k < NB2; ++k)
+                        b[k * PE] = out[k];
+                    named_arrive(READY + i % 3, 256);
+                }
+            }
+        }
+
         // generic fallback for (nb, nq) pairs without a template instance: same algorithm and data layout
         // with EPW = 1 (one element per warp pass), runtime loops, tables in global memory.
         __global__ void __launch_bounds__(256)
@@ -738,6 +1224,21 @@ namespace cb200
             J[3] = 0.25 * ((1.0 - xi0) * (c[7] - c[1]) + (1.0 + xi0) * (c[5] - c[3]));
         }
 
+        // position of metric value (tx, ty, component a of NKI) of element slot e of patch p. EPW > 0: lane-major layout of
+        // volume_action_kernel; EPW == 0: thread-per-element layout [pair of values][element] of volume_action_tpe.
+        __device__ __forceinline__ size_t metric_index(const int64_t p, const int e, const int PE, const int NQ, const int EPW,
+                                                       const int n_pass, const int NKI, const int tx, const int ty, const int a)
+        {
+            if (EPW == 0) {
+                const int KR = (NKI * NQ + 1) & ~1;
+                const int NK2 = NQ * KR / 2;
+                const int k = tx * KR + ty * NKI + a;
+                return (((size_t)p * NK2 + (k >> 1)) * PE + e) * 2 + (k & 1);
+            }
+            const int LW = EPW * NQ, NK = NKI * NQ;
+            return ((size_t)(p * n_pass + e / EPW) * NK + (NKI * ty + a)) * LW + (size_t)(e % EPW) * NQ + tx;
+        }
+
         __global__ void setup_stiffness_kernel(const int64_t n_slots, const int PE, const int NQ, const int EPW,
                                                const int n_pass, const int * __restrict__ slot_elem,
                                                const double * __restrict__ corners, const double * __restrict__ xq,
@@ -753,8 +1254,6 @@ namespace cb200
             const int64_t p = slot / PE;
             const int e = (int)(slot - p * PE);
             const int el = slot_elem[slot];
-            const int LW = EPW * NQ, NK = 3 * NQ;
-            const size_t base = ((size_t)(p * n_pass + e / EPW) * NK) * LW + (size_t)(e % EPW) * NQ + i;
             double g0 = 0.0, g1 = 0.0, g2 = 0.0;
             if (el >= 0) {
                 double J[4];
@@ -766,9 +1265,9 @@ namespace cb200
                 g1 = -W * (Y_xi * Y_eta + X_xi * X_eta) / det;
                 g2 = W * (Y_xi * Y_xi + X_xi * X_xi) / det;
             }
-            G[base + (size_t)(3 * j + 0) * LW] = g0;
-            G[base + (size_t)(3 * j + 1) * LW] = g1;
-            G[base + (size_t)(3 * j + 2) * LW] = g2;
+            G[metric_index(p, e, PE, NQ, EPW, n_pass, 3, i, j, 0)] = g0;
+            G[metric_index(p, e, PE, NQ, EPW, n_pass, 3, i, j, 1)] = g1;
+            G[metric_index(p, e, PE, NQ, EPW, n_pass, 3, i, j, 2)] = g2;
         }
 
         __global__ void setup_mass_kernel(const int64_t n_slots, const int PE, const int NB, const int NQ, const int EPW,
@@ -788,8 +1287,7 @@ namespace cb200
             const int64_t p = slot / PE;
             const int e = (int)(slot - p * PE);
             const int el = slot_elem[slot];
-            const int LW = EPW * NQ, NK = NQ;
-            const size_t idx = ((size_t)(p * n_pass + e / EPW) * NK + ty) * LW + (size_t)(e % EPW) * NQ + tx;
+            const size_t idx = metric_index(p, e, PE, NQ, EPW, n_pass, 1, tx, ty, 0);
             double val = 0.0;
             if (el >= 0) {
                 double ppx = 0.0;
@@ -1051,7 +1549,110 @@ namespace cb200
             CB_LAUNCHED();
         }
 
+        template <int NB, int NQ, bool STIFF, int PE>
+        void launch_volume_tpe_pe(VolumeOp & op, const PlanDev & pd, const Plan & plan, double c, int accumulate, const double * x,
+                                  double * y, cudaStream_t s)
+        {
+            constexpr int MINB = 256 / PE; // 256 threads = 8 warps per SM: up to 255 registers per thread
+            const size_t mpe = ((size_t)plan.max_pdof + 1) & ~size_t(1);
+            size_t smem = sizeof(double) * (mpe + (size_t)PE * NB * NB) + sizeof(uint16_t) * ((size_t)2 * PE * NB * NB) +
+                          sizeof(int) * (size_t)plan.max_pdof + sizeof(uint16_t) * ((size_t)plan.max_pdof + 4);
+            smem = (smem + 15) & ~size_t(15);
+            Tables<NB, NQ, STIFF> tab;
+            std::memset(&tab, 0, sizeof(tab));
+            for (int q = 0; q < NQ; ++q)
+                for (int k = 0; k < NB; ++k) {
+                    tab.Prow[q][k] = op.P[q + NQ * k];
+                    tab.Pcol[k][q] = op.P[q + NQ * k];
+                    if (STIFF) {
+                        tab.Drow[q][k] = op.D[q + NQ * k];
+                        tab.Dcol[k][q] = op.D[q + NQ * k];
+                    }
+                }
+            auto kern = volume_action_tpe<NB, NQ, STIFF, PE, MINB>;
+            static size_t attr_smem = 0;
+            static int pf_dist = -1;
+            if (smem > attr_smem) {
+                CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)49152)));
+                CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                attr_smem = std::max(smem, (size_t)49152);
+                int dev = 0, sms = 148, occ = 1;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PE, smem);
+                pf_dist = env_int("CUDDH_B200_PFDIST", std::max(occ, 1) * sms);
+            }
+            kern<<<(unsigned)plan.n_patches, PE, smem, s>>>(tab, pd, reinterpret_cast<const double2 *>(op.d_G.p), x, y, op.d_partial.p, c,
+                                                            accumulate, plan.max_pdof, (int)plan.n_patches, pf_dist, 0);
+            CB_LAUNCHED();
+        }
+
+        template <int NB, int NQ, bool STIFF>
+        void launch_volume_ws(VolumeOp & op, const PlanDev & pd, const Plan & plan, double c, int accumulate, const double * x,
+                              double * y, cudaStream_t s)
+        {
+            CB_REQUIRE(plan.PE == 128, "warp-specialised kernel: patches must hold 128 elements");
+            const size_t smem = sizeof(double) * 3 * (size_t)NB * NB * 128;
+            Tables<NB, NQ, STIFF> tab;
+            std::memset(&tab, 0, sizeof(tab));
+            for (int q = 0; q < NQ; ++q)
+                for (int k = 0; k < NB; ++k) {
+                    tab.Prow[q][k] = op.P[q + NQ * k];
+                    tab.Pcol[k][q] = op.P[q + NQ * k];
+                    if (STIFF) {
+                        tab.Drow[q][k] = op.D[q + NQ * k];
+                        tab.Dcol[k][q] = op.D[q + NQ * k];
+                    }
+                }
+            auto kern = volume_action_ws<NB, NQ, STIFF>;
+            static int grid = 0;
+            if (!grid) {
+                CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)49152)));
+                CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                int dev = 0, sms = 148, occ = 1;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+                grid = std::max(1, occ) * sms;
+            }
+            const int g = (int)std::min<int64_t>(grid, plan.n_patches);
+            kern<<<g, 256, smem, s>>>(tab, pd, reinterpret_cast<const double2 *>(op.d_G.p), x, y, op.d_partial.p, c, accumulate,
+                                      (int)plan.n_patches, 0);
+            CB_LAUNCHED();
+        }
+
+        template <int NB, int NQ, bool STIFF>
+        void launch_volume_tpe(VolumeOp & op, const PlanDev & pd, const Plan & plan, double c, int accumulate, const double * x,
+                               double * y, cudaStream_t s)
+        {
+            static const int use_ws = env_int("CUDDH_B200_WS", 1);
+            if (use_ws && plan.PE == 128)
+                return launch_volume_ws<NB, NQ, STIFF>(op, pd, plan, c, accumulate, x, y, s);
+            if (plan.PE == 64)
+                launch_volume_tpe_pe<NB, NQ, STIFF, 64>(op, pd, plan, c, accumulate, x, y, s);
+            else if (plan.PE == 128)
+                launch_volume_tpe_pe<NB, NQ, STIFF, 128>(op, pd, plan, c, accumulate, x, y, s);
+            else
+                CB_REQUIRE(false, "thread-per-element kernel: patch size must be 64 or 128 elements");
+        }
+
         using LaunchFn = void (*)(VolumeOp &, const PlanDev &, const Plan &, double, int, const double *, double *, cudaStream_t);
+
+        // thread-per-element instances: n_basis <= 5 (U and the result fit in registers next to the row temporaries)
+        template <bool STIFF>
+        LaunchFn find_tpe_instance(int nb, int nq)
+        {
+#define CB_CASE(NB_, NQ_)                                                                                              \
+    if (nb == NB_ && nq == NQ_)                                                                                        \
+        return &launch_volume_tpe<NB_, NQ_, STIFF>;
+            CB_CASE(2, 3) CB_CASE(3, 4) CB_CASE(4, 5) CB_CASE(5, 6)
+            CB_CASE(3, 5) CB_CASE(4, 6) CB_CASE(5, 7)
+            if constexpr (!STIFF) {
+                CB_CASE(2, 5) CB_CASE(3, 6) CB_CASE(4, 8) CB_CASE(5, 9)
+            }
+#undef CB_CASE
+            return nullptr;
+        }
 
         template <bool STIFF>
         LaunchFn find_instance(int nb, int nq)
@@ -1073,9 +1674,11 @@ namespace cb200
 
     void VolumeOp::apply(double c, int accumulate, const double * x, double * y, cudaStream_t s, int phases)
     {
-        Plan & plan = fem->get_plan();
-        PlanDev pd{plan.d_hdr.p, plan.d_gid.p, plan.d_slot.p, plan.d_L.p, plan.d_cptr.p, plan.d_cent.p, plan.PE};
+        Plan & plan = *this->plan;
+        PlanDev pd{plan.d_hdr.p, plan.d_gid.p, plan.d_slot.p, plan.d_L.p, plan.d_cptr.p, plan.d_cent.p, plan.PE, plan.d_Ig.p, reinterpret_cast<const uint2 *>(plan.d_cent4.p), plan.d_target.p};
         LaunchFn fn = generic ? nullptr : (stiff ? find_instance<true>(nb, nq) : find_instance<false>(nb, nq));
+        if (tpe)
+            fn = stiff ? find_tpe_instance<true>(nb, nq) : find_tpe_instance<false>(nb, nq);
         if (!(phases & 1)) {
         }
         else if (fn)
@@ -1118,13 +1721,26 @@ namespace cb200
                                                     : "MassMatrix error: quadrature rules with more than 32 points not yet supported.");
             LaunchFn fn = stiff ? find_instance<true>(op.nb, nq) : find_instance<false>(op.nb, nq);
             op.generic = force_generic || (fn == nullptr);
-            op.epw = op.generic ? 1 : 32 / nq;
-            op.lw = op.epw * nq;
+            LaunchFn ft = stiff ? find_tpe_instance<true>(op.nb, nq) : find_tpe_instance<false>(op.nb, nq);
+            op.tpe = !op.generic && ft != nullptr && env_int("CUDDH_B200_TPE", 1) != 0;
             op.nk = (stiff ? 3 : 1) * nq;
-            Plan & plan = fem->get_plan();
-            op.n_pass = (plan.PE + op.epw - 1) / op.epw;
+            if (op.tpe) { // thread-per-element layout: [pair of metric values][element], see volume_action_tpe
+                op.plan = &fem->get_plan_tpe();
+                op.epw = 0;
+                op.lw = 0;
+                op.n_pass = 0;
+                const int KR = (op.nk + 1) & ~1;
+                op.d_G.alloc((size_t)op.plan->n_patches * (size_t)(nq * KR) * op.plan->PE);
+            }
+            else {
+                op.plan = &fem->get_plan();
+                op.epw = op.generic ? 1 : 32 / nq;
+                op.lw = op.epw * nq;
+                op.n_pass = (op.plan->PE + op.epw - 1) / op.epw;
+                op.d_G.alloc((size_t)op.plan->n_patches * op.n_pass * op.nk * op.lw);
+            }
+            Plan & plan = *op.plan;
             op.d_partial.alloc((size_t)std::max<int64_t>(plan.n_slots_total, 1));
-            op.d_G.alloc((size_t)plan.n_patches * op.n_pass * op.nk * op.lw);
             CB_CUDA(cudaMemset(op.d_G.p, 0, op.d_G.n * sizeof(double)));
         }
     } // namespace
@@ -1147,7 +1763,7 @@ namespace cb200
         DevBuf<double> d_x, d_w;
         d_x.upload(xq);
         d_w.upload(wq);
-        Plan & plan = fem->get_plan();
+        Plan & plan = *op->plan;
         const int64_t n_slots = plan.n_patches * plan.PE;
         setup_stiffness_kernel<<<blocks_for(n_slots * nq * nq, 256), 256>>>(n_slots, plan.PE, nq, op->epw, op->n_pass, plan.d_slot_elem.p,
                                                                             fem->device_corners(), d_x.p, d_w.p, op->d_G.p);
@@ -1170,7 +1786,7 @@ namespace cb200
         DevBuf<double> d_x, d_w;
         d_x.upload(xq);
         d_w.upload(wq);
-        Plan & plan = fem->get_plan();
+        Plan & plan = *op->plan;
         const int64_t n_slots = plan.n_patches * plan.PE;
         setup_mass_kernel<<<blocks_for(n_slots * nq * nq, 256), 256>>>(n_slots, plan.PE, fem->nb, nq, op->epw, op->n_pass, plan.d_slot_elem.p,
                                                                        fem->device_corners(), fem->device_I(), d_coef, op->d_P.p, d_x.p,

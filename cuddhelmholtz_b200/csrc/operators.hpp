@@ -17,6 +17,8 @@ namespace cb200
         DevBuf<double> d_partial;     // partial sums of patch-boundary DOFs
         int epw = 0, lw = 0, n_pass = 0, nk = 0;  // layout constants (see operators.cu)
         bool generic = false;
+        bool tpe = false;             // thread-per-element kernel + node-major plan (n_basis <= 5)
+        Plan * plan = nullptr;        // the assembly plan this operator was laid out for (owned by fem)
 
         // phases: bit 0 = patch kernel, bit 1 = shared-DOF assembly pass (3 = the full action)
         void apply(double c, int accumulate, const double * x, double * y, cudaStream_t s, int phases = 3);
