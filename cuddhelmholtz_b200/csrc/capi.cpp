@@ -377,18 +377,24 @@ int cuddh_b200_operator_time_phases(cuddh_operator_t op, const double * x, doubl
                                     void * stream)
 {
     CB_TRY
-    CB_REQUIRE(op->vol != nullptr && reps > 0, "operator_time_phases: needs a stiffness / mass handle and reps > 0");
+    CB_REQUIRE((op->vol != nullptr || op->helm != nullptr) && reps > 0, "operator_time_phases: needs a stiffness / mass / Helmholtz handle and reps > 0");
+    auto run = [&](int phases) {
+        if (op->vol)
+            op->vol->apply(1.0, 0, x, y, S(stream), phases);
+        else
+            op->helm->apply(x, y, S(stream), phases);
+    };
     cudaEvent_t e0, e1, e2;
     CB_CUDA(cudaEventCreate(&e0));
     CB_CUDA(cudaEventCreate(&e1));
     CB_CUDA(cudaEventCreate(&e2));
-    op->vol->apply(1.0, 0, x, y, S(stream), 3); // warm
+    run(3); // warm
     CB_CUDA(cudaEventRecord(e0, S(stream)));
     for (int i = 0; i < reps; ++i)
-        op->vol->apply(1.0, 0, x, y, S(stream), 1);
+        run(1);
     CB_CUDA(cudaEventRecord(e1, S(stream)));
     for (int i = 0; i < reps; ++i)
-        op->vol->apply(1.0, 0, x, y, S(stream), 2);
+        run(2);
     CB_CUDA(cudaEventRecord(e2, S(stream)));
     CB_CUDA(cudaEventSynchronize(e2));
     float a = 0, b = 0;

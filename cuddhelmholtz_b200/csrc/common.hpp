@@ -146,7 +146,9 @@ namespace cb200
         std::vector<uint16_t> cptr;        // per patch n_pdof+1 offsets into its slice of cent
         std::vector<uint16_t> cent;        // (nb*nb*PE, n_patches): element-local entries (slot*nb*nb + node) grouped by DOF
         std::vector<int> slot_elem;        // (PE, n_patches) global element id of each slot, -1 = padding
-        std::vector<int> Ig;               // node-major plans only: (PE, nb*nb, n_patches) global DOF of (slot, node), 0 = padding
+        // node-major plans (volume_action_ws) list only the DOFs on element boundaries; the nodes strictly inside an element are
+        // written by the thread that owns the element:
+        std::vector<int> Ig;               // (4, PE, ceil(nb*nb/4), n_patches) global DOF of (node % 4, slot, node / 4), 0 = padding
         std::vector<uint16_t> cent4;       // node-major plans only: per patch-local DOF (indexed like gid) its first four CSR entries,
                                            // 0xFFFF = none; entry 3 == 0xFFFE: more than four, continue in cptr/cent from entry 3
         std::vector<int> target;           // node-major plans only: per patch-local DOF the global DOF (private) or partial slot (shared)

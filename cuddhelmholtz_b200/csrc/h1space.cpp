@@ -303,6 +303,9 @@ namespace cb200
         }
 
         // 3. patch-local DOF lists; a DOF touched by more than one patch is "shared"
+        // node (i, j) strictly inside an element belongs to that element alone on any conforming mesh
+        auto interior = [nb](int a) { const int i = a % nb, j = a / nb; return i > 0 && i < nb - 1 && j > 0 && j < nb - 1; };
+        const int NG = (nb2 + 3) / 4;
         std::vector<uint8_t> touch((size_t)fem.ndof, 0);
         std::vector<std::vector<int>> pg(np);
         for (int64_t p = 0; p < np; ++p) {
@@ -310,7 +313,13 @@ namespace cb200
             g.reserve((size_t)plan.hdr[p].n_elem * nb2);
             for (int k = 0; k < plan.hdr[p].n_elem; ++k) {
                 const int * Ie = &fem.I[(size_t)nb2 * plan.slot_elem[(size_t)p * PE + k]];
-                g.insert(g.end(), Ie, Ie + nb2);
+                if (plan.node_major) { // element-interior nodes are written by the compute threads themselves
+                    for (int a = 0; a < nb2; ++a)
+                        if (!interior(a))
+                            g.push_back(Ie[a]);
+                }
+                else
+                    g.insert(g.end(), Ie, Ie + nb2);
             }
             std::sort(g.begin(), g.end());
             g.erase(std::unique(g.begin(), g.end()), g.end());
@@ -341,8 +350,9 @@ namespace cb200
         plan.slot.clear();
         plan.L.assign((size_t)np * PE * nb2, 0);
         plan.cent.assign((size_t)np * PE * nb2, 0);
-        if (plan.node_major)
-            plan.Ig.assign((size_t)np * PE * nb2, 0);
+        if (plan.node_major) {
+            plan.Ig.assign((size_t)np * PE * NG * 4, 0);
+        }
         plan.cptr.clear();
         plan.cptr.reserve(plan.gid.capacity() + (size_t)np);
         std::vector<int> local((size_t)fem.ndof, -1);
@@ -353,7 +363,7 @@ namespace cb200
             h.pdof_begin = (int)plan.gid.size();
             h.slot_begin = (int)plan.slot.size();
             h.n_pdof = (int)g.size();
-            CB_REQUIRE(g.size() < 65535, "assembly plan: patch has too many DOFs for 16-bit local ids");
+            CB_REQUIRE(g.size() < 65534, "assembly plan: patch has too many DOFs for 16-bit local ids");
             int n = 0;
             for (int v : g)
                 if (sh_index[v] < 0) {
@@ -375,10 +385,11 @@ namespace cb200
                 const int * Ie = &fem.I[(size_t)nb2 * plan.slot_elem[(size_t)p * PE + k]];
                 uint16_t * Lp = &plan.L[(size_t)p * PE * nb2];
                 for (int a = 0; a < nb2; ++a)
-                    Lp[entry(k, a)] = (uint16_t)local[Ie[a]];
-                if (plan.node_major)
-                    for (int a = 0; a < nb2; ++a)
-                        plan.Ig[(size_t)p * PE * nb2 + (size_t)a * PE + k] = Ie[a];
+                    Lp[entry(k, a)] = (plan.node_major && interior(a)) ? (uint16_t)0xFFFF : (uint16_t)local[Ie[a]];
+                if (plan.node_major) {
+                    for (int a = 0; a < nb2; ++a) // groups of four nodes per 16-byte load: ((p, a / 4), slot, a % 4)
+                        plan.Ig[(((size_t)p * NG + a / 4) * PE + k) * 4 + a % 4] = Ie[a];
+                }
             }
             // CSR: patch-local DOF -> its element-local entries in ascending (slot, node) order. This fixes the
             // summation order of every DOF (deterministic assembly without atomics or colouring).
@@ -387,7 +398,8 @@ namespace cb200
             const uint16_t * Lp = &plan.L[(size_t)p * PE * nb2];
             for (int k = 0; k < h.n_elem; ++k)
                 for (int a = 0; a < nb2; ++a)
-                    cnt[Lp[entry(k, a)] + 1]++;
+                    if (Lp[entry(k, a)] != 0xFFFF)
+                        cnt[Lp[entry(k, a)] + 1]++;
             for (int d = 0; d < h.n_pdof; ++d)
                 cnt[d + 1] += cnt[d];
             if (plan.cptr.size() & 1) // keep every patch's offsets 4-byte aligned (copied with 32-bit cp.async)
@@ -398,7 +410,8 @@ namespace cb200
             uint16_t * ce = &plan.cent[(size_t)p * PE * nb2];
             for (int k = 0; k < h.n_elem; ++k)
                 for (int a = 0; a < nb2; ++a)
-                    ce[cnt[Lp[entry(k, a)]]++] = (uint16_t)entry(k, a);
+                    if (Lp[entry(k, a)] != 0xFFFF)
+                        ce[cnt[Lp[entry(k, a)]]++] = (uint16_t)entry(k, a);
             if (plan.node_major) { // fixed-width records for the helper warps of volume_action_ws
                 plan.cent4.resize(plan.gid.size() * 4, 0xFFFF);
                 plan.target.resize(plan.gid.size(), 0);

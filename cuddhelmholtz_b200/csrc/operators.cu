@@ -41,7 +41,7 @@ namespace cb200
             const uint16_t * cptr;
             const uint16_t * cent;
             int PE;
-            const int * Ig; // node-major plans: global DOF of (patch, node, slot)
+            const int * Ig; // node-major plans: global DOF of (patch, node / 4, slot, node % 4)
             const uint2 * cent4; // node-major plans: first four CSR entries of every patch-local DOF (Plan::cent4)
             const int * target;  // node-major plans: global DOF / partial slot of every patch-local DOF
         };
@@ -590,23 +590,7 @@ namespace cb200
             }
         }
 
-        // ------------------------------------------------------------------------------------------
-        // Thread-per-element action kernel (n_basis <= 5): the default for the headline orders.
-        //
-        // ncu on the lane-per-row kernel above (profiles/r01_notes.md) pins its plateau on the L1TEX / shared-memory pipe
-        // (two transposes per element through a per-warp scratch, partial warps, bank conflicts: ~69 wavefronts per element)
-        // and on instruction issue (one LDCU per DFMA pair, address arithmetic). Here ONE THREAD owns ONE ELEMENT:
-        //   * U (nb x nb) and the result (nb x nb) live in registers for the whole element; the sum-factorised contractions
-        //     are straight DFMA chains over register operands and uniform-register table values, no transposes, no scratch,
-        //     no __syncwarp, all 32 lanes busy (a patch is a whole number of warps of elements);
-        //   * every shared-memory access of the contraction phase is a full-warp, conflict-free, element-fastest access
-        //     (node-major local map L[k][e] and result array su[k][e]): 2 wavefronts per 32 elements per value;
-        //   * the metric data of an element is read as 128-bit loads from a [value pair][element] layout, one contiguous
-        //     512-byte run per warp instruction, one quadrature row ahead of its use.
-        // The outer quadrature loop is rolled and the tables are indexed through an opaque zero so that ptxas streams them
-        // through uniform registers (LDCU) next to the DFMAs instead of hoisting all 60 doubles into 120 registers.
-        // Staging (A) and deterministic assembly (C) are those of the kernel above, on a node-major plan.
-        // ------------------------------------------------------------------------------------------
+        // metric layout of the thread-per-element kernel below: [pair of values][element], rows padded to an even count
         template <int NB, int NQ, bool STIFF>
         struct TpeCfg
         {
@@ -615,221 +599,27 @@ namespace cb200
             static constexpr int NK2 = NQ * KR / 2;        // 16-byte pairs per element
         };
 
-        template <int NB, int NQ, bool STIFF, int PE, int MINB>
-        __global__ void __launch_bounds__(PE, MINB)
-        volume_action_tpe(const __grid_constant__ Tables<NB, NQ, STIFF> tab, const PlanDev plan, const double2 * __restrict__ G,
-                          const double * __restrict__ x, double * __restrict__ y, double * __restrict__ partial, const double c,
-                          const int accumulate, const int max_pdof, const int n_patches, const int pf_dist, const int zero)
-        {
-            using Cfg = TpeCfg<NB, NQ, STIFF>;
-            constexpr int NB2 = NB * NB;
-            constexpr int NKI = Cfg::NKI, KR = Cfg::KR, NK2 = Cfg::NK2;
-
-            extern __shared__ __align__(16) unsigned char smem_raw[];
-            const int mpe = (max_pdof + 1) & ~1;
-            double * xloc = reinterpret_cast<double *>(smem_raw);        // [mpe]
-            double * su = xloc + mpe;                                     // [NB2][PE]
-            uint16_t * Ls = reinterpret_cast<uint16_t *>(su + NB2 * PE);  // [NB2][PE]
-            uint16_t * cents = Ls + NB2 * PE;                             // [NB2 * PE]
-            int * gids = reinterpret_cast<int *>(cents + NB2 * PE);       // [max_pdof]
-            uint16_t * cptrs = reinterpret_cast<uint16_t *>(gids + max_pdof); // [max_pdof + 1 (+1)]
-
-            const int tid = threadIdx.x;
-            const PatchHdr hdr = plan.hdr[blockIdx.x];
-
-            const int pnext = (pf_dist > 0 && (int)blockIdx.x + pf_dist < n_patches) ? (int)blockIdx.x + pf_dist : -1;
-            constexpr size_t g_patch = (size_t)NK2 * PE; // double2 per patch
-            if (tid == 0) {
-                bulk_prefetch_l2(G + (size_t)blockIdx.x * g_patch, g_patch * sizeof(double2));
-                if (pnext >= 0) {
-                    bulk_prefetch_l2(G + (size_t)pnext * g_patch, g_patch * sizeof(double2));
-                    bulk_prefetch_l2(plan.L + (size_t)pnext * PE * NB2, (size_t)PE * NB2 * sizeof(uint16_t));
-                    bulk_prefetch_l2(plan.cent + (size_t)pnext * PE * NB2, (size_t)PE * NB2 * sizeof(uint16_t));
-                }
-            }
-            PatchHdr hnext;
-            if (tid == 32 % PE && pnext >= 0)
-                hnext = plan.hdr[pnext];
-
-            // ---- A. stage the patch ----
-            {
-                constexpr int AU = 9;
-                const int * gidp = plan.gid + hdr.pdof_begin;
-                for (int base = tid; base < hdr.n_pdof; base += AU * PE) {
-                    int gi[AU];
-                    double xv[AU];
-#pragma unroll
-                    for (int a = 0; a < AU; ++a) {
-                        const int d = base + a * PE;
-                        gi[a] = (d < hdr.n_pdof) ? __ldg(gidp + d) : -1;
-                    }
-#pragma unroll
-                    for (int a = 0; a < AU; ++a)
-                        xv[a] = (gi[a] >= 0) ? __ldg(x + gi[a]) : 0.0;
-#pragma unroll
-                    for (int a = 0; a < AU; ++a) {
-                        const int d = base + a * PE;
-                        if (d < hdr.n_pdof) {
-                            xloc[d] = xv[a];
-                            gids[d] = gi[a];
-                        }
-                    }
-                }
-                // node-major local map and CSR entries: PE * NB2 * 2 bytes each, a multiple of 16
-                const uint4 * Lg = reinterpret_cast<const uint4 *>(plan.L + (size_t)hdr.elem_begin * NB2);
-                const uint4 * Cg = reinterpret_cast<const uint4 *>(plan.cent + (size_t)hdr.elem_begin * NB2);
-                uint4 * Ls4 = reinterpret_cast<uint4 *>(Ls);
-                uint4 * Cs4 = reinterpret_cast<uint4 *>(cents);
-                constexpr int n16 = PE * NB2 / 8;
-                for (int k = tid; k < n16; k += PE) {
-                    Ls4[k] = __ldg(Lg + k);
-                    Cs4[k] = __ldg(Cg + k);
-                }
-                const uint32_t * cpg = reinterpret_cast<const uint32_t *>(plan.cptr + hdr.cptr_begin); // cptr_begin is even
-                uint32_t * cps = reinterpret_cast<uint32_t *>(cptrs);
-                for (int k = tid; k < (hdr.n_pdof + 2) >> 1; k += PE)
-                    cps[k] = __ldg(cpg + k);
-            }
-            if (tid == 32 % PE && pnext >= 0) {
-                const int * g0 = plan.gid + (hnext.pdof_begin & ~3);
-                bulk_prefetch_l2(g0, ((size_t)hnext.n_pdof + 4) * sizeof(int));
-                const uint16_t * c0 = plan.cptr + (hnext.cptr_begin & ~7);
-                bulk_prefetch_l2(c0, ((size_t)hnext.n_pdof + 9) * sizeof(uint16_t));
-            }
-            __syncthreads();
-
-            // ---- B. one element per thread, everything in registers ----
-            {
-                const int e = tid;
-                double U[NB2], out[NB2];
-#pragma unroll
-                for (int k = 0; k < NB2; ++k)
-                    U[k] = xloc[Ls[k * PE + e]];
-#pragma unroll
-                for (int k = 0; k < NB2; ++k)
-                    out[k] = 0.0;
-                const double2 * gp = G + (size_t)blockIdx.x * g_patch + e;
-                double g[KR];
-#pragma unroll
-                for (int m = 0; m < KR / 2; ++m) {
-                    const double2 v = __ldcs(gp + m * PE);
-                    g[2 * m] = v.x;
-                    g[2 * m + 1] = v.y;
-                }
-#pragma unroll 1
-                for (int tx = 0; tx < NQ; ++tx) {
-                    const int z = tx * zero; // 0 at run time; keeps the ty-indexed table loads inside this loop (see header)
-                    // first-index contraction for quadrature row tx: pu[j] = sum_i P(tx,i) U[i][j] (and D)
-                    double pu[NB], du[STIFF ? NB : 1];
-#pragma unroll
-                    for (int j = 0; j < NB; ++j) {
-                        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                        for (int i = 0; i < NB; ++i) {
-                            s0 = fma(tab.Prow[tx][i], U[i + NB * j], s0);
-                            if (STIFF)
-                                s1 = fma(tab.Drow[tx][i], U[i + NB * j], s1);
-                        }
-                        pu[j] = s0;
-                        if (STIFF)
-                            du[j] = s1;
-                    }
-                    double a0[NB], a1[STIFF ? NB : 1];
-#pragma unroll
-                    for (int t = 0; t < NB; ++t) {
-                        a0[t] = 0.0;
-                        if (STIFF)
-                            a1[t] = 0.0;
-                    }
-#pragma unroll
-                    for (int ty = 0; ty < NQ; ++ty) {
-                        if (STIFF) {
-                            double Dx = 0.0, Dy = 0.0;
-#pragma unroll
-                            for (int l = 0; l < NB; ++l) {
-                                Dx = fma(tab.Prow[ty + z][l], du[l], Dx);
-                                Dy = fma(tab.Drow[ty + z][l], pu[l], Dy);
-                            }
-                            const double A = g[NKI * ty], B = g[NKI * ty + (NKI > 1 ? 1 : 0)], C = g[NKI * ty + (NKI > 2 ? 2 : 0)];
-                            const double F0 = A * Dx + B * Dy;
-                            const double F1 = B * Dx + C * Dy;
-#pragma unroll
-                            for (int t = 0; t < NB; ++t) {
-                                a0[t] = fma(tab.Prow[ty + z][t], F0, a0[t]);
-                                a1[t] = fma(tab.Drow[ty + z][t], F1, a1[t]);
-                            }
-                        }
-                        else {
-                            double ppu = 0.0;
-#pragma unroll
-                            for (int l = 0; l < NB; ++l)
-                                ppu = fma(tab.Prow[ty + z][l], pu[l], ppu);
-                            const double val = g[ty] * ppu;
-#pragma unroll
-                            for (int t = 0; t < NB; ++t)
-                                a0[t] = fma(tab.Prow[ty + z][t], val, a0[t]);
-                        }
-                    }
-                    // next quadrature row's metric values: in flight during the back-contraction below and the next
-                    // row's first-index contraction
-                    if (tx + 1 < NQ) {
-#pragma unroll
-                        for (int m = 0; m < KR / 2; ++m) {
-                            const double2 v = __ldcs(gp + ((tx + 1) * (KR / 2) + m) * PE);
-                            g[2 * m] = v.x;
-                            g[2 * m + 1] = v.y;
-                        }
-                    }
-                    // first-index contraction back to the basis: out[i][t] += D(tx,i) a0[t] + P(tx,i) a1[t]
-#pragma unroll
-                    for (int t = 0; t < NB; ++t)
-#pragma unroll
-                        for (int i = 0; i < NB; ++i) {
-                            if (STIFF)
-                                out[i + NB * t] = fma(tab.Drow[tx][i], a0[t], fma(tab.Prow[tx][i], a1[t], out[i + NB * t]));
-                            else
-                                out[i + NB * t] = fma(tab.Prow[tx][i], a0[t], out[i + NB * t]);
-                        }
-                }
-#pragma unroll
-                for (int k = 0; k < NB2; ++k)
-                    su[k * PE + e] = out[k];
-            }
-            __syncthreads();
-
-            // ---- C. deterministic assembly + write-back (CSR order of the plan) ----
-            {
-                const int * slotp = plan.slot + hdr.slot_begin - hdr.n_int;
-                for (int d = tid; d < hdr.n_pdof; d += PE) {
-                    const int b = cptrs[d], e = cptrs[d + 1];
-                    double sum = 0.0;
-                    for (int k = b; k < e; ++k)
-                        sum += su[cents[k]];
-                    if (d < hdr.n_int) {
-                        const int gi = gids[d];
-                        const double v = c * sum;
-                        y[gi] = accumulate ? (y[gi] + v) : v;
-                    }
-                    else
-                        partial[__ldg(slotp + d)] = sum;
-                }
-            }
-        }
-
         // ------------------------------------------------------------------------------------------
-        // Warp-specialised persistent version of the thread-per-element kernel (the default for n_basis <= 5).
+        // Warp-specialised persistent thread-per-element kernel (the default for n_basis <= 5).
         //
-        // ncu on volume_action_tpe: half the instructions and 60 % of the shared-memory wavefronts of the lane-per-row
-        // kernel, but only 28 % of the warp samples are in the contraction phase: with 200+ registers per thread there are
-        // 8 warps per SM, and they spend most of their time in the latency-bound staging and assembly phases. So the phases
-        // are given to different warps of a persistent CTA (256 threads, 2 CTAs per SM):
+        // ncu on the lane-per-row kernel above (profiles/r01_notes.md) pins its plateau on the L1TEX / shared-memory pipe
+        // (two transposes per element through a per-warp scratch, partial warps, bank conflicts: ~69 wavefronts per element)
+        // and on instruction issue. Here ONE THREAD owns ONE ELEMENT: U (nb x nb) and the result live in registers, the
+        // sum-factorised contractions are DFMA chains over register operands and uniform-register table values (rolled outer
+        // quadrature loop + an opaque zero in the inner table index so that ptxas streams the tables through LDCU instead of
+        // hoisting 60 doubles into registers): no transposes, no scratch, all lanes busy, half the instructions. A plain
+        // one-CTA-per-patch version of that idea was SLOWER (0.65 ms): with ~200 registers per thread there are 8 warps per SM
+        // and only 28 % of their samples were in the contractions, the rest in the latency-bound staging / assembly phases.
+        // So the phases are given to different warps of a persistent CTA (256 threads, 2 CTAs per SM):
         //   * warpgroup 1 (compute, setmaxnreg 208): one element per thread. Waits for its patch buffer, pulls U[k][e] into
         //     registers, runs the contractions (metric values straight from global memory, one quadrature row ahead,
-        //     L2 hits because the block was bulk-prefetched), writes the element results back INTO THE SAME BUFFER.
+        //     L2 hits because the block was bulk-prefetched), writes the results of the element-boundary nodes back INTO THE
+        //     SAME BUFFER and those of the nodes strictly inside the element (one contributor by construction) straight to y.
         //   * warpgroup 0 (helper, setmaxnreg 48): for the next patch, gathers x through the node-major global index map
         //     with 8-byte cp.async straight into that patch's buffer (no registers, no stall), prefetches index lists and
-        //     metric blocks into L2; for the previous patch, runs the deterministic CSR assembly out of its buffer and
-        //     writes y / the partial slots.
+        //     metric blocks into L2; for the previous patch, runs the deterministic assembly of the element-boundary DOFs out
+        //     of its buffer (fixed-width records of up to four contributions in the plan's CSR order) and writes y / the
+        //     partial slots.
         // Three patch buffers rotate: filling (i+1), computing (i), assembling (i-1). Hand-offs are named barriers
         // (bar.arrive / bar.sync over the 256 threads); the helper warpgroup frees a buffer by its own program order.
         // Summation order per DOF is the plan's CSR order, exactly as in the other kernels: bitwise reproducible.
@@ -849,62 +639,221 @@ namespace cb200
             return ty < 0 ? 0 : (ty + 1 >= NQ ? KR / 2 : (NKI * (ty + 1)) / 2);
         }
 
-        template <int NB, int NQ, bool STIFF>
-        __global__ void __launch_bounds__(256, 2)
-        volume_action_ws(const __grid_constant__ Tables<NB, NQ, STIFF> tab, const PlanDev plan, const double2 * __restrict__ G,
-                         const double * __restrict__ x, double * __restrict__ y, double * __restrict__ partial, const double c,
-                         const int accumulate, const int n_patches, const int zero)
+        // The quadrature rows of one operator ("phase") for the element of this thread. Row tx re-reads U from the patch buffer
+        // (conflict-free, element-fastest) and accumulates into out[]. The metric values of two rows (even / odd) sit in g0 / g1;
+        // every 16-byte pair is replaced, as soon as it has been used, by the pair of the NEXT ROW OF THE SAME PARITY: row
+        // tx + 2 of this phase, or row (tx & 1) of the phase that follows (gp_next, NPN pairs per row) - two row iterations
+        // ahead of its use. Mass values are scaled by msc (Helmholtz: -omega^2).
+        template <int NB, int NQ, bool STIFF, int GK, int NPN, int PE>
+        __device__ __forceinline__ void contract_phase(const Tables<NB, NQ, STIFF> & tab, const double * b, double (&g0)[GK], double (&g1)[GK],
+                                                       const double2 * gp, const double2 * gp_next, double (&out)[NB * NB],
+                                                       const double msc, const int zero)
         {
             using Cfg = TpeCfg<NB, NQ, STIFF>;
+            constexpr int NKI = Cfg::NKI, KR = Cfg::KR;
+            constexpr int NPR = KR / 2; // pairs per row of this phase
+            static_assert(GK >= KR && GK >= 2 * NPN, "metric register buffer too small");
+            auto do_row = [&](const int tx, double(&g)[GK], const double2 * gnext, const int npn /* pairs per row of the target */) {
+                const int z = tx * zero; // 0 at run time; keeps the ty-indexed table loads inside the rolled loop
+                // pairs the next row needs beyond what this row frees (mass -> stiffness): those slots are idle, load at once
+#pragma unroll
+                for (int m = NPR; m < GK / 2; ++m)
+                    if (m < npn) {
+                        const double2 v = __ldcs(gnext + m * PE);
+                        g[2 * m] = v.x;
+                        g[2 * m + 1] = v.y;
+                    }
+                double pu[NB], du[STIFF ? NB : 1];
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int ii = 0; ii < NB; ++ii) {
+                        const double u = b[(ii + NB * j) * PE];
+                        s0 = fma(tab.Prow[tx][ii], u, s0);
+                        if (STIFF)
+                            s1 = fma(tab.Drow[tx][ii], u, s1);
+                    }
+                    pu[j] = s0;
+                    if (STIFF)
+                        du[j] = s1;
+                }
+                double a0[NB], a1[STIFF ? NB : 1];
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    a0[q] = 0.0;
+                    if (STIFF)
+                        a1[q] = 0.0;
+                }
+#pragma unroll
+                for (int ty = 0; ty < NQ; ++ty) {
+                    if (STIFF) {
+                        double Dx = 0.0, Dy = 0.0;
+#pragma unroll
+                        for (int l = 0; l < NB; ++l) {
+                            Dx = fma(tab.Prow[ty + z][l], du[l], Dx);
+                            Dy = fma(tab.Drow[ty + z][l], pu[l], Dy);
+                        }
+                        const double A = g[NKI * ty], B = g[NKI * ty + (NKI > 1 ? 1 : 0)], C = g[NKI * ty + (NKI > 2 ? 2 : 0)];
+                        const double F0 = A * Dx + B * Dy;
+                        const double F1 = B * Dx + C * Dy;
+#pragma unroll
+                        for (int q = 0; q < NB; ++q) {
+                            a0[q] = fma(tab.Prow[ty + z][q], F0, a0[q]);
+                            a1[q] = fma(tab.Drow[ty + z][q], F1, a1[q]);
+                        }
+                    }
+                    else {
+                        double ppu = 0.0;
+#pragma unroll
+                        for (int l = 0; l < NB; ++l)
+                            ppu = fma(tab.Prow[ty + z][l], pu[l], ppu);
+                        const double val = (g[ty] * msc) * ppu;
+#pragma unroll
+                        for (int q = 0; q < NB; ++q)
+                            a0[q] = fma(tab.Prow[ty + z][q], val, a0[q]);
+                    }
+#pragma unroll
+                    for (int m = pairs_done<NQ, NKI, KR>(ty - 1); m < pairs_done<NQ, NKI, KR>(ty); ++m)
+                        if (m < npn) {
+                            const double2 v = __ldcs(gnext + m * PE);
+                            g[2 * m] = v.x;
+                            g[2 * m + 1] = v.y;
+                        }
+                }
+#pragma unroll
+                for (int q = 0; q < NB; ++q)
+#pragma unroll
+                    for (int ii = 0; ii < NB; ++ii) {
+                        if (STIFF)
+                            out[ii + NB * q] = fma(tab.Drow[tx][ii], a0[q], fma(tab.Prow[tx][ii], a1[q], out[ii + NB * q]));
+                        else
+                            out[ii + NB * q] = fma(tab.Prow[tx][ii], a0[q], out[ii + NB * q]);
+                    }
+            };
+#pragma unroll 1
+            for (int tx = 0; tx < NQ; tx += 2) {
+                const bool in0 = tx + 2 < NQ;
+                do_row(tx, g0, in0 ? gp + (tx + 2) * NPR * PE : gp_next, in0 ? NPR : NPN);
+                if (tx + 1 < NQ) {
+                    const bool in1 = tx + 3 < NQ;
+                    do_row(tx + 1, g1, in1 ? gp + (tx + 3) * NPR * PE : gp_next + NPN * PE, in1 ? NPR : NPN);
+                }
+            }
+        }
+
+        // second-phase placeholder for the single-operator instances
+        struct NoTables
+        {
+            double pad;
+        };
+        template <int NB, int NQ2>
+        struct Phase2
+        {
+            using type = Tables<NB, (NQ2 > 0 ? NQ2 : 1), false>;
+        };
+
+        // NQ2 > 0: a weighted-mass phase (scale msc) follows the first operator on the same element data - the Helmholtz
+        // composite S - omega^2 M. n_fields = 2 walks [u; v] (x, y, partial strided by field, sign[f] on the result).
+        struct WsArgs
+        {
+            const double2 * G1;
+            const double2 * G2;
+            const double * x;
+            double * y;
+            double * partial;
+            long long x_stride, y_stride, partial_stride; // per field
+            double c[2];                                  // result scale per field
+            double msc;                                   // scale of the second (mass) phase
+            int accumulate, n_patches, n_fields, zero;
+        };
+
+        template <int NB, int NQ, bool STIFF, int NQ2>
+        __global__ void __launch_bounds__(256, 2)
+        volume_action_ws(const __grid_constant__ Tables<NB, NQ, STIFF> tab, const __grid_constant__ typename Phase2<NB, NQ2>::type tab2,
+                         const PlanDev plan, const __grid_constant__ WsArgs args)
+        {
+            using Cfg = TpeCfg<NB, NQ, STIFF>;
+            using Cfg2 = TpeCfg<NB, (NQ2 > 0 ? NQ2 : 1), false>;
             constexpr int PE = 128;
             constexpr int NB2 = NB * NB;
-            constexpr int NKI = Cfg::NKI, KR = Cfg::KR, NK2 = Cfg::NK2;
+            constexpr int NPR1 = Cfg::KR / 2, NPR2 = NQ2 > 0 ? Cfg2::KR / 2 : 0;
+            constexpr int GK = 2 * (NPR1 > NPR2 ? NPR1 : NPR2); // metric registers per row buffer
             constexpr int BUF = NB2 * PE; // doubles per patch buffer
-            constexpr size_t g_patch = (size_t)NK2 * PE; // double2 per patch
+            constexpr size_t g_patch1 = (size_t)Cfg::NK2 * PE, g_patch2 = NQ2 > 0 ? (size_t)Cfg2::NK2 * PE : 0; // double2 per patch
             constexpr int FULL = 1, READY = 4, HELPER = 7; // named barrier ids (0 is __syncthreads)
+            constexpr int NG = (NB2 + 3) / 4;                // groups of four nodes in the global index map
+            constexpr int NI = (NB > 2 ? NB - 2 : 0) * (NB > 2 ? NB - 2 : 0); // element-interior nodes
 
             extern __shared__ __align__(16) unsigned char smem_raw[];
             double * bufs = reinterpret_cast<double *>(smem_raw); // [3][NB2][PE]
+            int * gints = reinterpret_cast<int *>(bufs + 3 * BUF);  // [3][NI][PE] global DOFs of the element-interior nodes
 
             const int wg = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 7), 0); // warp-uniform by construction
             const int t = threadIdx.x & 127;
             const int stride = gridDim.x;
-            const int n_iter = (n_patches - (int)blockIdx.x + stride - 1) / stride;
+            const int NF = args.n_fields;
+            const int n_iter = ((args.n_patches - (int)blockIdx.x + stride - 1) / stride) * NF; // units = (patch, field)
+            const int accumulate = args.accumulate;
 
             if (wg == 0) {
                 // =========================== helper warpgroup ===========================
                 asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
                 auto issue_gather = [&](const int i) {
-                    const int p = (int)blockIdx.x + i * stride;
+                    const int p = (int)blockIdx.x + (i / NF) * stride, f = i % NF;
+                    const double * x = args.x + f * args.x_stride;
                     double * b = bufs + (i % 3) * BUF + t;
-                    const int * ig = plan.Ig + (size_t)p * BUF + t;
+                    const int4 * ig = reinterpret_cast<const int4 *>(plan.Ig) + (size_t)p * (NG * PE) + t;
+                    int4 idx[NG]; // all index loads of the element in flight at once
 #pragma unroll
-                    constexpr int GU = 9; // index loads in flight per thread
+                    for (int gq = 0; gq < NG; ++gq)
+                        idx[gq] = __ldg(ig + gq * PE);
+                    // hand the global DOFs of the element-interior nodes (written by the compute thread itself) over in shared memory
+                    if (NI > 0) {
+                        const int n_el = __ldg(&plan.hdr[p].n_elem);
+                        int * gs = gints + (i % 3) * (NI * PE) + t;
 #pragma unroll
-                    for (int k0 = 0; k0 < NB2; k0 += GU) {
-                        int idx[GU];
-#pragma unroll
-                        for (int a = 0; a < GU; ++a)
-                            idx[a] = (k0 + a < NB2) ? __ldg(ig + (k0 + a) * PE) : 0;
-#pragma unroll
-                        for (int a = 0; a < GU; ++a)
-                            if (k0 + a < NB2)
-                                cp_async8(b + (k0 + a) * PE, x + idx[a]);
+                        for (int k = 0; k < NB2; ++k) {
+                            const int ki = k % NB, kj = k / NB;
+                            if (ki > 0 && ki < NB - 1 && kj > 0 && kj < NB - 1) {
+                                const int4 q4 = idx[k / 4];
+                                const int gi = (k % 4 == 0) ? q4.x : (k % 4 == 1) ? q4.y : (k % 4 == 2) ? q4.z : q4.w;
+                                gs[((ki - 1) + (NB - 2) * (kj - 1)) * PE] = (t < n_el) ? gi : -1;
+                            }
+                        }
                     }
-                    // L2 prefetch: this patch's metric block (read by the compute warpgroup next iteration) and the index
+#pragma unroll
+                    for (int gq = 0; gq < NG; ++gq) {
+                        cp_async8(b + (4 * gq) * PE, x + idx[gq].x);
+                        if (4 * gq + 1 < NB2)
+                            cp_async8(b + (4 * gq + 1) * PE, x + idx[gq].y);
+                        if (4 * gq + 2 < NB2)
+                            cp_async8(b + (4 * gq + 2) * PE, x + idx[gq].z);
+                        if (4 * gq + 3 < NB2)
+                            cp_async8(b + (4 * gq + 3) * PE, x + idx[gq].w);
+                    }
+                    // L2 prefetch: this patch's metric blocks (read by the compute warpgroup next iteration) and the index
                     // lists of the patch after it
-                    const int p2 = p + stride;
-                    if (t == 0)
-                        bulk_prefetch_l2(G + (size_t)p * g_patch, g_patch * sizeof(double2));
-                    if (t == 32 && p2 < n_patches) {
-                        bulk_prefetch_l2(plan.Ig + (size_t)p2 * BUF, (size_t)BUF * sizeof(int));
-                        const PatchHdr h2 = plan.hdr[p2];
-                        bulk_prefetch_l2(plan.target + (h2.pdof_begin & ~3), ((size_t)h2.n_pdof + 4) * sizeof(int));
-                        bulk_prefetch_l2(plan.cent4 + (h2.pdof_begin & ~1), ((size_t)h2.n_pdof + 2) * sizeof(uint2));
+                    if (f == 0) {
+                        const int p2 = p + stride;
+                        if (t == 0) {
+                            bulk_prefetch_l2(args.G1 + (size_t)p * g_patch1, g_patch1 * sizeof(double2));
+                            if (NQ2 > 0)
+                                bulk_prefetch_l2(args.G2 + (size_t)p * g_patch2, g_patch2 * sizeof(double2));
+                        }
+                        if (t == 32 && p2 < args.n_patches) {
+                            bulk_prefetch_l2(plan.Ig + (size_t)p2 * (NG * PE * 4), (size_t)NG * PE * 4 * sizeof(int));
+                            const PatchHdr h2 = plan.hdr[p2];
+                            bulk_prefetch_l2(plan.target + (h2.pdof_begin & ~3), ((size_t)h2.n_pdof + 4) * sizeof(int));
+                            bulk_prefetch_l2(plan.cent4 + (h2.pdof_begin & ~1), ((size_t)h2.n_pdof + 2) * sizeof(uint2));
+                        }
                     }
                 };
                 auto assemble = [&](const int i) {
-                    const int p = (int)blockIdx.x + i * stride;
+                    const int p = (int)blockIdx.x + (i / NF) * stride, f = i % NF;
+                    double * y = args.y + f * args.y_stride;
+                    double * partial = args.partial + f * args.partial_stride;
+                    const double c = args.c[f];
                     const PatchHdr hdr = plan.hdr[p];
                     const double * su = bufs + (i % 3) * BUF;
                     const uint2 * recp = plan.cent4 + hdr.pdof_begin;
@@ -970,104 +919,63 @@ namespace cb200
                 // =========================== compute warpgroup: one element per thread ===========================
                 asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
                 const int e = t;
-                double g[KR];
+                double g0[GK], g1[GK];
                 {
-                    const double2 * gp0 = G + (size_t)blockIdx.x * g_patch + e;
+                    const double2 * gpi = args.G1 + (size_t)blockIdx.x * g_patch1 + e;
 #pragma unroll
-                    for (int m = 0; m < KR / 2; ++m) {
-                        const double2 v = __ldcs(gp0 + m * PE);
-                        g[2 * m] = v.x;
-                        g[2 * m + 1] = v.y;
+                    for (int m = 0; m < NPR1; ++m) {
+                        const double2 v = __ldcs(gpi + m * PE);
+                        g0[2 * m] = v.x;
+                        g0[2 * m + 1] = v.y;
+                        const double2 w = __ldcs(gpi + (NPR1 + m) * PE);
+                        g1[2 * m] = w.x;
+                        g1[2 * m + 1] = w.y;
                     }
                 }
                 for (int i = 0; i < n_iter; ++i) {
-                    const int p = (int)blockIdx.x + i * stride;
+                    const int p = (int)blockIdx.x + (i / NF) * stride, f = i % NF;
                     double * b = bufs + (i % 3) * BUF + e;
-                    const double2 * gp = G + (size_t)p * g_patch + e;
-                    // first row of the next patch of this CTA (or of this one again at the end: a harmless reload)
-                    const double2 * gp_next_patch = (i + 1 < n_iter) ? gp + (size_t)stride * g_patch : gp;
+                    // first phase of the next unit of this CTA (same patch for the second field; at the very end this one again:
+                    // a harmless reload)
+                    const int pn = (i + 1 < n_iter) ? (int)blockIdx.x + ((i + 1) / NF) * stride : p;
+                    const double2 * gp1 = args.G1 + (size_t)p * g_patch1 + e;
+                    const double2 * gp1_next = args.G1 + (size_t)pn * g_patch1 + e;
                     named_sync(FULL + i % 3, 256);
-                    double U[NB2], out[NB2];
-#pragma unroll
-                    for (int k = 0; k < NB2; ++k)
-                        U[k] = b[k * PE];
+                    double out[NB2];
 #pragma unroll
                     for (int k = 0; k < NB2; ++k)
                         out[k] = 0.0;
-#pragma unroll 1
-                    for (int tx = 0; tx < NQ; ++tx) {
-                        const int z = tx * zero; // 0 at run time; keeps the ty-indexed table loads inside this loop
-                        const double2 * gnext = (tx + 1 < NQ) ? gp + (tx + 1) * (KR / 2) * PE : gp_next_patch;
-                        double pu[NB], du[STIFF ? NB : 1];
-#pragma unroll
-                        for (int j = 0; j < NB; ++j) {
-                            double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                            for (int ii = 0; ii < NB; ++ii) {
-                                s0 = fma(tab.Prow[tx][ii], U[ii + NB * j], s0);
-                                if (STIFF)
-                                    s1 = fma(tab.Drow[tx][ii], U[ii + NB * j], s1);
-                            }
-                            pu[j] = s0;
-                            if (STIFF)
-                                du[j] = s1;
-                        }
-                        double a0[NB], a1[STIFF ? NB : 1];
-#pragma unroll
-                        for (int q = 0; q < NB; ++q) {
-                            a0[q] = 0.0;
-                            if (STIFF)
-                                a1[q] = 0.0;
-                        }
-#pragma unroll
-                        for (int ty = 0; ty < NQ; ++ty) {
-                            if (STIFF) {
-                                double Dx = 0.0, Dy = 0.0;
-#pragma unroll
-                                for (int l = 0; l < NB; ++l) {
-                                    Dx = fma(tab.Prow[ty + z][l], du[l], Dx);
-                                    Dy = fma(tab.Drow[ty + z][l], pu[l], Dy);
-                                }
-                                const double A = g[NKI * ty], B = g[NKI * ty + (NKI > 1 ? 1 : 0)], C = g[NKI * ty + (NKI > 2 ? 2 : 0)];
-                                const double F0 = A * Dx + B * Dy;
-                                const double F1 = B * Dx + C * Dy;
-#pragma unroll
-                                for (int q = 0; q < NB; ++q) {
-                                    a0[q] = fma(tab.Prow[ty + z][q], F0, a0[q]);
-                                    a1[q] = fma(tab.Drow[ty + z][q], F1, a1[q]);
-                                }
-                            }
-                            else {
-                                double ppu = 0.0;
-#pragma unroll
-                                for (int l = 0; l < NB; ++l)
-                                    ppu = fma(tab.Prow[ty + z][l], pu[l], ppu);
-                                const double val = g[ty] * ppu;
-#pragma unroll
-                                for (int q = 0; q < NB; ++q)
-                                    a0[q] = fma(tab.Prow[ty + z][q], val, a0[q]);
-                            }
-                            // metric values consumed so far are replaced by the next row's (a whole row iteration ahead)
-#pragma unroll
-                            for (int m = pairs_done<NQ, NKI, KR>(ty - 1); m < pairs_done<NQ, NKI, KR>(ty); ++m) {
-                                const double2 v = __ldcs(gnext + m * PE);
-                                g[2 * m] = v.x;
-                                g[2 * m + 1] = v.y;
-                            }
-                        }
-#pragma unroll
-                        for (int q = 0; q < NB; ++q)
-#pragma unroll
-                            for (int ii = 0; ii < NB; ++ii) {
-                                if (STIFF)
-                                    out[ii + NB * q] = fma(tab.Drow[tx][ii], a0[q], fma(tab.Prow[tx][ii], a1[q], out[ii + NB * q]));
-                                else
-                                    out[ii + NB * q] = fma(tab.Prow[tx][ii], a0[q], out[ii + NB * q]);
-                            }
+                    if constexpr (NQ2 > 0) {
+                        const double2 * gp2 = args.G2 + (size_t)p * g_patch2 + e;
+                        contract_phase<NB, NQ, STIFF, GK, NPR2, PE>(tab, b, g0, g1, gp1, gp2, out, 1.0, args.zero);
+                        contract_phase<NB, NQ2, false, GK, NPR1, PE>(tab2, b, g0, g1, gp2, gp1_next, out, args.msc, args.zero);
                     }
+                    else
+                        contract_phase<NB, NQ, STIFF, GK, NPR1, PE>(tab, b, g0, g1, gp1, gp1_next, out, 1.0, args.zero);
+
+                    double * y = args.y + f * args.y_stride;
+                    const double c = args.c[f];
+                    int gint[NI > 0 ? NI : 1]; // global DOFs of this element's interior nodes (-1: padding slot)
 #pragma unroll
-                    for (int k = 0; k < NB2; ++k)
-                        b[k * PE] = out[k];
+                    for (int m = 0; m < NI; ++m)
+                        gint[m] = gints[(i % 3) * (NI * PE) + m * PE + e];
+#pragma unroll
+                    for (int k = 0; k < NB2; ++k) {
+                        const int ki = k % NB, kj = k / NB;
+                        if (ki > 0 && ki < NB - 1 && kj > 0 && kj < NB - 1) {
+                            // single contributor: y (+)= c * value is exact and order-free, also as a reduction
+                            const int gi = gint[(ki - 1) + (NB - 2) * (kj - 1)];
+                            if (gi >= 0) {
+                                const double v = c * out[k];
+                                if (accumulate)
+                                    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(y + gi), "d"(v) : "memory");
+                                else
+                                    y[gi] = v;
+                            }
+                        }
+                        else
+                            b[k * PE] = out[k];
+                    }
                     named_arrive(READY + i % 3, 256);
                 }
             }
@@ -1225,7 +1133,7 @@ namespace cb200
         }
 
         // position of metric value (tx, ty, component a of NKI) of element slot e of patch p. EPW > 0: lane-major layout of
-        // volume_action_kernel; EPW == 0: thread-per-element layout [pair of values][element] of volume_action_tpe.
+        // volume_action_kernel; EPW == 0: thread-per-element layout [pair of values][element] of volume_action_ws.
         __device__ __forceinline__ size_t metric_index(const int64_t p, const int e, const int PE, const int NQ, const int EPW,
                                                        const int n_pass, const int NKI, const int tx, const int ty, const int a)
         {
@@ -1549,16 +1457,9 @@ namespace cb200
             CB_LAUNCHED();
         }
 
-        template <int NB, int NQ, bool STIFF, int PE>
-        void launch_volume_tpe_pe(VolumeOp & op, const PlanDev & pd, const Plan & plan, double c, int accumulate, const double * x,
-                                  double * y, cudaStream_t s)
+        template <int NB, int NQ, bool STIFF>
+        void fill_tables(Tables<NB, NQ, STIFF> & tab, const VolumeOp & op)
         {
-            constexpr int MINB = 256 / PE; // 256 threads = 8 warps per SM: up to 255 registers per thread
-            const size_t mpe = ((size_t)plan.max_pdof + 1) & ~size_t(1);
-            size_t smem = sizeof(double) * (mpe + (size_t)PE * NB * NB) + sizeof(uint16_t) * ((size_t)2 * PE * NB * NB) +
-                          sizeof(int) * (size_t)plan.max_pdof + sizeof(uint16_t) * ((size_t)plan.max_pdof + 4);
-            smem = (smem + 15) & ~size_t(15);
-            Tables<NB, NQ, STIFF> tab;
             std::memset(&tab, 0, sizeof(tab));
             for (int q = 0; q < NQ; ++q)
                 for (int k = 0; k < NB; ++k) {
@@ -1569,42 +1470,21 @@ namespace cb200
                         tab.Dcol[k][q] = op.D[q + NQ * k];
                     }
                 }
-            auto kern = volume_action_tpe<NB, NQ, STIFF, PE, MINB>;
-            static size_t attr_smem = 0;
-            static int pf_dist = -1;
-            if (smem > attr_smem) {
-                CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)49152)));
-                CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-                attr_smem = std::max(smem, (size_t)49152);
-                int dev = 0, sms = 148, occ = 1;
-                cudaGetDevice(&dev);
-                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PE, smem);
-                pf_dist = env_int("CUDDH_B200_PFDIST", std::max(occ, 1) * sms);
-            }
-            kern<<<(unsigned)plan.n_patches, PE, smem, s>>>(tab, pd, reinterpret_cast<const double2 *>(op.d_G.p), x, y, op.d_partial.p, c,
-                                                            accumulate, plan.max_pdof, (int)plan.n_patches, pf_dist, 0);
-            CB_LAUNCHED();
         }
 
-        template <int NB, int NQ, bool STIFF>
-        void launch_volume_ws(VolumeOp & op, const PlanDev & pd, const Plan & plan, double c, int accumulate, const double * x,
-                              double * y, cudaStream_t s)
+        template <int NB, int NQ, bool STIFF, int NQ2>
+        void launch_ws(const VolumeOp & op, const VolumeOp * op2, const PlanDev & pd, const Plan & plan, const WsArgs & args, cudaStream_t s)
         {
             CB_REQUIRE(plan.PE == 128, "warp-specialised kernel: patches must hold 128 elements");
-            const size_t smem = sizeof(double) * 3 * (size_t)NB * NB * 128;
+            constexpr int NI = (NB > 2 ? NB - 2 : 0) * (NB > 2 ? NB - 2 : 0);
+            const size_t smem = sizeof(double) * 3 * (size_t)NB * NB * 128 + sizeof(int) * 3 * (size_t)NI * 128;
             Tables<NB, NQ, STIFF> tab;
-            std::memset(&tab, 0, sizeof(tab));
-            for (int q = 0; q < NQ; ++q)
-                for (int k = 0; k < NB; ++k) {
-                    tab.Prow[q][k] = op.P[q + NQ * k];
-                    tab.Pcol[k][q] = op.P[q + NQ * k];
-                    if (STIFF) {
-                        tab.Drow[q][k] = op.D[q + NQ * k];
-                        tab.Dcol[k][q] = op.D[q + NQ * k];
-                    }
-                }
-            auto kern = volume_action_ws<NB, NQ, STIFF>;
+            fill_tables(tab, op);
+            typename Phase2<NB, NQ2>::type tab2;
+            std::memset(&tab2, 0, sizeof(tab2));
+            if constexpr (NQ2 > 0)
+                fill_tables(tab2, *op2);
+            auto kern = volume_action_ws<NB, NQ, STIFF, NQ2>;
             static int grid = 0;
             if (!grid) {
                 CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)49152)));
@@ -1616,24 +1496,26 @@ namespace cb200
                 grid = std::max(1, occ) * sms;
             }
             const int g = (int)std::min<int64_t>(grid, plan.n_patches);
-            kern<<<g, 256, smem, s>>>(tab, pd, reinterpret_cast<const double2 *>(op.d_G.p), x, y, op.d_partial.p, c, accumulate,
-                                      (int)plan.n_patches, 0);
+            kern<<<g, 256, smem, s>>>(tab, tab2, pd, args);
             CB_LAUNCHED();
         }
 
         template <int NB, int NQ, bool STIFF>
-        void launch_volume_tpe(VolumeOp & op, const PlanDev & pd, const Plan & plan, double c, int accumulate, const double * x,
-                               double * y, cudaStream_t s)
+        void launch_volume_ws(VolumeOp & op, const PlanDev & pd, const Plan & plan, double c, int accumulate, const double * x,
+                              double * y, cudaStream_t s)
         {
-            static const int use_ws = env_int("CUDDH_B200_WS", 1);
-            if (use_ws && plan.PE == 128)
-                return launch_volume_ws<NB, NQ, STIFF>(op, pd, plan, c, accumulate, x, y, s);
-            if (plan.PE == 64)
-                launch_volume_tpe_pe<NB, NQ, STIFF, 64>(op, pd, plan, c, accumulate, x, y, s);
-            else if (plan.PE == 128)
-                launch_volume_tpe_pe<NB, NQ, STIFF, 128>(op, pd, plan, c, accumulate, x, y, s);
-            else
-                CB_REQUIRE(false, "thread-per-element kernel: patch size must be 64 or 128 elements");
+            WsArgs a{};
+            a.G1 = reinterpret_cast<const double2 *>(op.d_G.p);
+            a.G2 = nullptr;
+            a.x = x;
+            a.y = y;
+            a.partial = op.d_partial.p;
+            a.c[0] = a.c[1] = c;
+            a.msc = 1.0;
+            a.accumulate = accumulate;
+            a.n_patches = (int)plan.n_patches;
+            a.n_fields = 1;
+            launch_ws<NB, NQ, STIFF, 0>(op, nullptr, pd, plan, a, s);
         }
 
         using LaunchFn = void (*)(VolumeOp &, const PlanDev &, const Plan &, double, int, const double *, double *, cudaStream_t);
@@ -1644,7 +1526,7 @@ namespace cb200
         {
 #define CB_CASE(NB_, NQ_)                                                                                              \
     if (nb == NB_ && nq == NQ_)                                                                                        \
-        return &launch_volume_tpe<NB_, NQ_, STIFF>;
+        return &launch_volume_ws<NB_, NQ_, STIFF>;
             CB_CASE(2, 3) CB_CASE(3, 4) CB_CASE(4, 5) CB_CASE(5, 6)
             CB_CASE(3, 5) CB_CASE(4, 6) CB_CASE(5, 7)
             if constexpr (!STIFF) {
@@ -1667,6 +1549,17 @@ namespace cb200
             if constexpr (!STIFF) { // weighted mass: nq = 1 + 3nb/2 + 1 (MassMatrix.cpp:108)
                 CB_CASE(2, 5) CB_CASE(3, 6) CB_CASE(4, 8) CB_CASE(5, 9) CB_CASE(6, 11) CB_CASE(7, 12) CB_CASE(8, 14) CB_CASE(9, 15)
             }
+#undef CB_CASE
+            return nullptr;
+        }
+        using FusedFn = void (*)(const VolumeOp &, const VolumeOp *, const PlanDev &, const Plan &, const WsArgs &, cudaStream_t);
+        FusedFn find_fused_instance(int nb, int nqs, int nqm)
+        {
+#define CB_CASE(NB_, NQS_, NQM_)                                                                                       \
+    if (nb == NB_ && nqs == NQS_ && nqm == NQM_)                                                                       \
+        return &launch_ws<NB_, NQS_, true, NQM_>;
+            // default stiffness rule nq = nb + 1 with the weighted-mass rule nq = 1 + 3nb/2 + 1 (examples/Helmholtz.hpp)
+            CB_CASE(2, 3, 5) CB_CASE(3, 4, 6) CB_CASE(4, 5, 8) CB_CASE(5, 6, 9)
 #undef CB_CASE
             return nullptr;
         }
@@ -1724,7 +1617,7 @@ namespace cb200
             LaunchFn ft = stiff ? find_tpe_instance<true>(op.nb, nq) : find_tpe_instance<false>(op.nb, nq);
             op.tpe = !op.generic && ft != nullptr && env_int("CUDDH_B200_TPE", 1) != 0;
             op.nk = (stiff ? 3 : 1) * nq;
-            if (op.tpe) { // thread-per-element layout: [pair of metric values][element], see volume_action_tpe
+            if (op.tpe) { // thread-per-element layout: [pair of metric values][element], see volume_action_ws
                 op.plan = &fem->get_plan_tpe();
                 op.epw = 0;
                 op.lw = 0;
@@ -1934,18 +1827,58 @@ namespace cb200
         op->S = make_stiffness(fem, 0, GAUSS_LEGENDRE);
         op->M = make_mass(fem, d_a2, 0);
         op->H = make_facemass(fs, d_a, 0);
+        op->fused = op->S->tpe && op->M->tpe && op->S->plan == op->M->plan && find_fused_instance(op->S->nb, op->S->nq, op->M->nq) != nullptr &&
+                    env_int("CUDDH_B200_FUSED", 1) != 0;
+        if (op->fused)
+            op->d_partial2.alloc(2 * (size_t)std::max<int64_t>(op->S->plan->n_slots_total, 1));
         return op;
     }
 
-    void HelmholtzOp::apply(const double * x, double * y, cudaStream_t s)
+    void HelmholtzOp::apply(const double * x, double * y, cudaStream_t s, int phases)
     {
         // examples/Helmholtz.hpp:28-56:  Au = S u - w^2 M u - w H v ;  Av = -(S v - w^2 M v + w H u)
-        // 6 launches + 4 tiny assembly passes instead of the reference's 11 kernels + 4 memsets.
         const int64_t n = fem->ndof;
         const double * u = x;
         const double * v = x + n;
         double * Au = y;
         double * Av = y + n;
+        if (fused) {
+            // one warp-specialised kernel walks (patch, field) units: S and M share the gather, the index lists and the
+            // assembly, the sign of the second block row is applied on write: 1 + 2 + 2 launches instead of 11 + 4 memsets
+            Plan & plan = *S->plan;
+            PlanDev pd{plan.d_hdr.p, plan.d_gid.p, plan.d_slot.p, plan.d_L.p, plan.d_cptr.p, plan.d_cent.p, plan.PE, plan.d_Ig.p,
+                       reinterpret_cast<const uint2 *>(plan.d_cent4.p), plan.d_target.p};
+            WsArgs a{};
+            a.G1 = reinterpret_cast<const double2 *>(S->d_G.p);
+            a.G2 = reinterpret_cast<const double2 *>(M->d_G.p);
+            a.x = x;
+            a.y = y;
+            a.partial = d_partial2.p;
+            a.x_stride = a.y_stride = n;
+            a.partial_stride = std::max<int64_t>(plan.n_slots_total, 1);
+            a.c[0] = 1.0;
+            a.c[1] = -1.0;
+            a.msc = -omega * omega;
+            a.accumulate = 0;
+            a.n_patches = (int)plan.n_patches;
+            a.n_fields = 2;
+            if (phases & 1)
+                find_fused_instance(S->nb, S->nq, M->nq)(*S, M.get(), pd, plan, a, s);
+            if (!(phases & 2))
+                return;
+            if (plan.n_shared > 0) {
+                assemble_shared_kernel<<<blocks_for(plan.n_shared, 256), 256, 0, s>>>(plan.n_shared, plan.d_sh_gid.p, plan.d_sh_ptr.p,
+                                                                                      d_partial2.p, Au, 1.0, 0);
+                CB_LAUNCHED();
+                assemble_shared_kernel<<<blocks_for(plan.n_shared, 256), 256, 0, s>>>(plan.n_shared, plan.d_sh_gid.p, plan.d_sh_ptr.p,
+                                                                                      d_partial2.p + a.partial_stride, Av, -1.0, 0);
+                CB_LAUNCHED();
+            }
+            H->apply_h1(-omega, v, Au, s);
+            H->apply_h1(-omega, u, Av, s);
+            return;
+        }
+        // 7 launches + 4 tiny assembly passes instead of the reference's 11 kernels + 4 memsets.
         S->apply(1.0, 0, u, Au, s);
         S->apply(1.0, 0, v, Av, s);
         M->apply(-omega * omega, 1, u, Au, s);
@@ -1954,5 +1887,12 @@ namespace cb200
         H->apply_h1(omega, u, Av, s);
         negate_kernel<<<blocks_for(n, 256), 256, 0, s>>>(n, Av);
         CB_LAUNCHED();
+    }
+
+    size_t HelmholtzOp::algorithmic_bytes() const
+    {
+        // SURVEY §8(d), fused complex apply: metric data and index map read once for u and v
+        const size_t nb = S->nb, nqs = S->nq, nqm = M->nq;
+        return (24 * nqs * nqs + 8 * nqm * nqm + 4 * nb * nb + 32 * (nb - 1) * (nb - 1)) * (size_t)fem->n_elem;
     }
 } // namespace cb200

@@ -61,7 +61,11 @@ namespace cb200
         FaceSpace * fs = nullptr;
         std::unique_ptr<VolumeOp> S, M;
         std::unique_ptr<FaceMassOp> H;
-        void apply(const double * x, double * y, cudaStream_t s);
+        DevBuf<double> d_partial2;    // fused path: partial sums of patch-boundary DOFs for both fields
+        bool fused = false;           // S - omega^2 M on u and v in one warp-specialised kernel (n_basis <= 5)
+        // phases (fused path only): bit 0 = the fused volume kernel, bit 1 = shared-DOF assembly + face terms
+        void apply(const double * x, double * y, cudaStream_t s, int phases = 3);
+        size_t algorithmic_bytes() const;
     };
     std::unique_ptr<HelmholtzOp> make_helmholtz(double omega, const double * d_a2, const double * d_a, H1Space * fem, FaceSpace * fs);
 } // namespace cb200
