@@ -43,15 +43,46 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons during the timed regions (B200_PROFILING.md recipe). NVML in-process (a query takes
+    microseconds, so even a 20 ms region gets several samples); falls back to polling nvidia-smi."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # LOCAL_RANK indexes the visible devices: map through CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                phys = int(vis.split(",")[index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
+
+    def _nvml_row(self):
+        nv = self.nv
+        sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        bit = lambda name: "Active" if (r & getattr(nv, name, 0)) else "Not Active"
+        return [str(sm), str(mx), bit("nvmlClocksThrottleReasonHwSlowdown"), bit("nvmlClocksThrottleReasonHwThermalSlowdown"),
+                bit("nvmlClocksThrottleReasonSwThermalSlowdown"), bit("nvmlClocksThrottleReasonSwPowerCap")]
 
     def run(self):
+        while not self.stop_flag and self.nv is not None:
+            try:
+                self.rows.append(self._nvml_row())
+            except Exception:
+                self.nv = None
+                break
+            time.sleep(0.002)
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
@@ -68,7 +99,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "source": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
 def cpu_port_setup(nx, nb, omega):
@@ -202,18 +233,32 @@ def main():
     ms_step = float(t.item()) / K
     value = 2.0 * ndof * world / (ms_step * 1e-3) / 1e9
 
-    # ---- end to end through the public API with host buffers (pinned H2D of [u;v], apply, D2H of the result) ----
-    Ke = max(3, min(K, 5))
-    for _ in range(2):
-        x.copy_(hx, non_blocking=True)
-        slab.apply(x, y)
-        hy.copy_(y, non_blocking=True)
+    # ---- end to end through the public API with HOST buffers: every step copies its [u; v] from pinned host memory, applies
+    # the operator and reads the result back to the host. Consecutive steps are independent requests, so they are
+    # double-buffered on two streams: the H2D of step k+1 overlaps the apply / D2H of step k (PCIe is full duplex). ----
+    Ke = max(6, min(K, 10))
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    xb, yb = [x, torch.empty_like(x)], [y, torch.empty_like(y)]
+    hyb = [hy, torch.empty(2 * ndof, dtype=torch.float64).pin_memory()]
+
+    def e2e_steps(n):
+        for k in range(n):
+            b = k & 1
+            with torch.cuda.stream(streams[b]):
+                xb[b].copy_(hx, non_blocking=True)
+                slab.apply(xb[b], yb[b])
+                hyb[b].copy_(yb[b], non_blocking=True)
+
+    for st in streams:
+        st.wait_stream(torch.cuda.current_stream())
+    e2e_steps(2)
     barrier()
     e0.record()
-    for _ in range(Ke):
-        x.copy_(hx, non_blocking=True)
-        slab.apply(x, y)
-        hy.copy_(y, non_blocking=True)
+    for st in streams:
+        st.wait_event(e0)
+    e2e_steps(Ke)
+    for st in streams:
+        torch.cuda.current_stream().wait_stream(st)
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
@@ -221,6 +266,16 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item()) / Ke
     e2e_value = 2.0 * ndof * world / (e2e_ms * 1e-3) / 1e9
+    # the same without overlap (one stream, copy -> apply -> copy per step), for reference
+    barrier()
+    e0.record()
+    for _ in range(3):
+        x.copy_(hx, non_blocking=True)
+        slab.apply(x, y)
+        hy.copy_(y, non_blocking=True)
+    e1.record()
+    barrier()
+    e2e_serial_ms = e0.elapsed_time(e1) / 3
     if sampler:  # clocks are sampled across both timed regions (device-resident and end-to-end)
         sampler.stop_flag = True
 
@@ -229,31 +284,43 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (stiffness patch kernel), timed alone with CUDA events on its stream ----
+    # ---- roofline of the dominant kernel, timed alone with CUDA events on its stream: the fused Helmholtz volume kernel
+    # (S - omega^2 M on u and v; > 90 % of the step). Algorithmic bytes = SURVEY §8(d) fused formulation per element. ----
     peak, peak_src = measured_peaks()
-    Sop = cb.StiffnessMatrix(slab.fem)
+    nqs, nqm = nb + 1, 1 + 3 * nb // 2 + 1
     u = x[:ndof]
     yy = y[:ndof]
-    ms_patch, ms_shared = Sop.time_phases(u, yy, max(K, 10))
-    bytes_S = Sop.algorithmic_bytes()
-    roof = {"bound": "hbm", "kernel": "volume_action_kernel<%d,%d,stiffness>" % (nb, nb + 1), "achieved": bytes_S / (ms_patch * 1e-3) / 1e9,
-            "peak": peak, "unit": "GB/s", "peak_source": peak_src, "ms_per_launch": ms_patch, "algorithmic_bytes": bytes_S,
-            "shared_assembly_ms": ms_shared, "traffic": None}
+    fused = slab.op.is_fused() if hasattr(slab.op, "is_fused") else False
+    if fused:
+        ms_patch, ms_rest = slab.op.time_phases(x, y, max(K, 10))
+        bytes_k = slab.op.algorithmic_bytes()
+        kname, tkey = "volume_action_ws<%d,%d,stiffness,%d> (fused S - w^2 M on [u;v])" % (nb, nqs, nqm), "helmholtz_%d_%d_%d_nx%d" % (nb, nqs, nqm, nx)
+    else:
+        Sop0 = cb.StiffnessMatrix(slab.fem)
+        ms_patch, ms_rest = Sop0.time_phases(u, yy, max(K, 10))
+        bytes_k = Sop0.algorithmic_bytes()
+        kname, tkey = "volume_action_kernel<%d,%d,stiffness>" % (nb, nqs), "stiffness_%d_%d_nx%d" % (nb, nqs, nx)
+    roof = {"bound": "hbm", "kernel": kname, "achieved": bytes_k / (ms_patch * 1e-3) / 1e9,
+            "peak": peak, "unit": "GB/s", "peak_source": peak_src, "ms_per_launch": ms_patch, "algorithmic_bytes": bytes_k,
+            "rest_of_step_ms": ms_rest, "traffic": None}
     roof["frac"] = roof["achieved"] / peak
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
-            roof["traffic"] = json.load(open(tr)).get("stiffness_%d_%d_nx%d" % (nb, nb + 1, nx))
+            roof["traffic"] = json.load(open(tr)).get(tkey)
         except Exception:
             pass
+    Sop = cb.StiffnessMatrix(slab.fem)
+    sp_, ss_ = Sop.time_phases(u, yy, max(K, 10))
+    bytes_S = Sop.algorithmic_bytes()
     Mop = cb.MassMatrix(slab._a2, slab.fem)
     mp_, ms_ = Mop.time_phases(u, yy, max(K, 10))
-    per_op = {"stiffness": {"ms": ms_patch + ms_shared, "gdofs": ndof / ((ms_patch + ms_shared) * 1e-3) / 1e9,
-                            "hbm_frac": bytes_S / ((ms_patch + ms_shared) * 1e-3) / 1e9 / peak},
-              "mass_weighted": {"ms": mp_ + ms_, "gdofs": ndof / ((mp_ + ms_) * 1e-3) / 1e9,
-                                "hbm_frac": Mop.algorithmic_bytes() / ((mp_ + ms_) * 1e-3) / 1e9 / peak},
+    per_op = {"stiffness": {"ms": sp_ + ss_, "gdofs": ndof / ((sp_ + ss_) * 1e-3) / 1e9, "kernel_ms": sp_,
+                            "hbm_frac_kernel": bytes_S / (sp_ * 1e-3) / 1e9 / peak},
+              "mass_weighted": {"ms": mp_ + ms_, "gdofs": ndof / ((mp_ + ms_) * 1e-3) / 1e9, "kernel_ms": mp_,
+                                "hbm_frac_kernel": Mop.algorithmic_bytes() / (mp_ * 1e-3) / 1e9 / peak},
               "helmholtz_composite": {"ms": ms_step, "hbm_frac_fused_formulation": slab.op.algorithmic_bytes() / (ms_step * 1e-3) / 1e9 / peak}}
-    del Mop
+    del Mop, Sop
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -261,7 +328,9 @@ def main():
                                    "uniform_rect(%d x %d) per GPU, n_basis %d (degree %d), omega %g" % (nx, nx, nb, nb - 1, omega),
                        "ndof_per_gpu": ndof, "parallelism": "slab%d" % world,
                        "l2": "inputs larger than L2 (x,y 2x%.0f MB, metric data %.0f MB)" % (16 * ndof / 1e6, (bytes_S + Mop_bytes(nb, nx)) / 1e6)},
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": 16 * ndof, "d2h_bytes_per_step": 16 * ndof},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": 16 * ndof, "d2h_bytes_per_step": 16 * ndof,
+                    "steps": Ke, "pipelining": "two streams, double-buffered: H2D of step k+1 overlaps apply + D2H of step k",
+                    "ms_per_step_unpipelined": e2e_serial_ms},
             "gpu_launches": int(launches), "roofline": roof, "operators": per_op,
             "clocks": sampler.summary() if sampler else None}
     if world > 1:

@@ -272,8 +272,15 @@ class Operator:
     def algorithmic_bytes(self):
         return int(load().cuddh_b200_operator_bytes(self._h))
 
+    def kernel_kind(self):
+        """0 lane-per-row / generic kernel, 1 warp-specialised thread-per-element kernel, 2 fused Helmholtz kernel, -1 n/a."""
+        return int(load().cuddh_b200_operator_kernel_kind(self._h))
+
+    def is_fused(self):
+        return self.kernel_kind() == 2
+
     def time_phases(self, x, y, reps):
-        """(ms of the patch kernel alone, ms of the shared-DOF assembly pass alone), CUDA events on the current stream."""
+        """(ms of the patch kernel alone, ms of the rest of the action alone), CUDA events on the current stream."""
         a, b = C.c_float(), C.c_float()
         check(load().cuddh_b200_operator_time_phases(self._h, _ptr(x), _ptr(y), reps, C.byref(a), C.byref(b), _stream()))
         return a.value, b.value

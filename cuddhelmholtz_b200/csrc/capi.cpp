@@ -423,6 +423,14 @@ int64_t cuddh_b200_operator_bytes(cuddh_operator_t op)
     }
     return 0;
 }
+int cuddh_b200_operator_kernel_kind(cuddh_operator_t op)
+{
+    if (op->vol)
+        return op->vol->tpe ? 1 : 0;
+    if (op->helm)
+        return op->helm->fused ? 2 : (op->helm->S->tpe ? 1 : 0);
+    return -1;
+}
 
 // ---- linalg ----
 #define CB_LINALG2(NAME, T, SUF)                                                                          \

@@ -647,19 +647,30 @@ namespace cb200
         template <int NB, int NQ, bool STIFF, int GK, int NPN, int PE>
         __device__ __forceinline__ void contract_phase(const Tables<NB, NQ, STIFF> & tab, const double * b, double (&g0)[GK], double (&g1)[GK],
                                                        const double2 * gp, const double2 * gp_next, double (&out)[NB * NB],
-                                                       const double msc, const int zero)
+                                                       const double msc, const int zero, const bool keep, const bool keep_next)
         {
+            // keep / keep_next: the rows of this phase / of the following phase will be read again soon (first field of the fused
+            // Helmholtz apply) -> leave them in L2; otherwise stream them with an evict-first hint
+            // (one load instruction with a run-time L2 cache-hint operand: evict_last / evict_first)
+            unsigned long long pol_keep, pol_stream;
+            asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+            asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+            auto ldm = [&](const double2 * q, const bool k) {
+                double2 v;
+                asm("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(q), "l"(k ? pol_keep : pol_stream));
+                return v;
+            };
             using Cfg = TpeCfg<NB, NQ, STIFF>;
             constexpr int NKI = Cfg::NKI, KR = Cfg::KR;
             constexpr int NPR = KR / 2; // pairs per row of this phase
             static_assert(GK >= KR && GK >= 2 * NPN, "metric register buffer too small");
-            auto do_row = [&](const int tx, double(&g)[GK], const double2 * gnext, const int npn /* pairs per row of the target */) {
+            auto do_row = [&](const int tx, double(&g)[GK], const double2 * gnext, const int npn /* pairs per row of the target */, const bool kp) {
                 const int z = tx * zero; // 0 at run time; keeps the ty-indexed table loads inside the rolled loop
                 // pairs the next row needs beyond what this row frees (mass -> stiffness): those slots are idle, load at once
 #pragma unroll
                 for (int m = NPR; m < GK / 2; ++m)
                     if (m < npn) {
-                        const double2 v = __ldcs(gnext + m * PE);
+                        const double2 v = ldm(gnext + m * PE, kp);
                         g[2 * m] = v.x;
                         g[2 * m + 1] = v.y;
                     }
@@ -716,7 +727,7 @@ namespace cb200
 #pragma unroll
                     for (int m = pairs_done<NQ, NKI, KR>(ty - 1); m < pairs_done<NQ, NKI, KR>(ty); ++m)
                         if (m < npn) {
-                            const double2 v = __ldcs(gnext + m * PE);
+                            const double2 v = ldm(gnext + m * PE, kp);
                             g[2 * m] = v.x;
                             g[2 * m + 1] = v.y;
                         }
@@ -734,10 +745,10 @@ namespace cb200
 #pragma unroll 1
             for (int tx = 0; tx < NQ; tx += 2) {
                 const bool in0 = tx + 2 < NQ;
-                do_row(tx, g0, in0 ? gp + (tx + 2) * NPR * PE : gp_next, in0 ? NPR : NPN);
+                do_row(tx, g0, in0 ? gp + (tx + 2) * NPR * PE : gp_next, in0 ? NPR : NPN, in0 ? keep : keep_next);
                 if (tx + 1 < NQ) {
                     const bool in1 = tx + 3 < NQ;
-                    do_row(tx + 1, g1, in1 ? gp + (tx + 3) * NPR * PE : gp_next + NPN * PE, in1 ? NPR : NPN);
+                    do_row(tx + 1, g1, in1 ? gp + (tx + 3) * NPR * PE : gp_next + NPN * PE, in1 ? NPR : NPN, in1 ? keep : keep_next);
                 }
             }
         }
@@ -947,11 +958,13 @@ namespace cb200
                         out[k] = 0.0;
                     if constexpr (NQ2 > 0) {
                         const double2 * gp2 = args.G2 + (size_t)p * g_patch2 + e;
-                        contract_phase<NB, NQ, STIFF, GK, NPR2, PE>(tab, b, g0, g1, gp1, gp2, out, 1.0, args.zero);
-                        contract_phase<NB, NQ2, false, GK, NPR1, PE>(tab2, b, g0, g1, gp2, gp1_next, out, args.msc, args.zero);
+                        // loads issued while working on field f fetch data of field f (phase 2) or of the next unit (phase 1)
+                        const bool first = NF > 1 && f == 0, last = NF > 1 && f == NF - 1; // this unit's data is read again / the next unit's is
+                        contract_phase<NB, NQ, STIFF, GK, NPR2, PE>(tab, b, g0, g1, gp1, gp2, out, 1.0, args.zero, first, first);
+                        contract_phase<NB, NQ2, false, GK, NPR1, PE>(tab2, b, g0, g1, gp2, gp1_next, out, args.msc, args.zero, first, last);
                     }
                     else
-                        contract_phase<NB, NQ, STIFF, GK, NPR1, PE>(tab, b, g0, g1, gp1, gp1_next, out, 1.0, args.zero);
+                        contract_phase<NB, NQ, STIFF, GK, NPR1, PE>(tab, b, g0, g1, gp1, gp1_next, out, 1.0, args.zero, false, false);
 
                     double * y = args.y + f * args.y_stride;
                     const double c = args.c[f];

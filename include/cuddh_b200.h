@@ -119,12 +119,16 @@ int cuddh_b200_operator_apply(cuddh_operator_t op, double c, int accumulate, con
 /* fused FaceSpace::restrict + FaceMassMatrix::action + FaceSpace::prolong on H1 vectors: y[proj] += c*H*x[proj] */
 int cuddh_b200_facemass_apply_h1(cuddh_operator_t op, double c, const double * x, double * y, void * stream);
 /* measurement aid (bench.py roofline): average CUDA-event time, over `reps` back-to-back launches on `stream`, of the
- * patch kernel alone and of the shared-DOF assembly pass alone (stiffness / mass handles; computes y = A x) */
+ * patch kernel alone and of the rest of the action alone (stiffness / mass handles: the shared-DOF assembly pass; Helmholtz
+ * handles on the fused path: shared-DOF assembly + face terms; computes y = A x) */
 int cuddh_b200_operator_time_phases(cuddh_operator_t op, const double * x, double * y, int reps, float * ms_patch, float * ms_shared,
                                     void * stream);
 int cuddh_b200_operator_destroy(cuddh_operator_t op);
 /* algorithmic bytes of one apply, 0 if not defined for this operator */
 int64_t cuddh_b200_operator_bytes(cuddh_operator_t op);
+/* which kernel family serves this handle: 0 = lane-per-row patch kernel / generic, 1 = warp-specialised thread-per-element
+ * kernel (n_basis <= 5), 2 = Helmholtz handle on the fused S - w^2 M path; -1 = not a volume operator */
+int cuddh_b200_operator_kernel_kind(cuddh_operator_t op);
 
 /* ---- linalg: include/linalg.hpp:16-54 (double and float) ---------------------------------------- */
 int cuddh_b200_axpby_d(int64_t n, double a, const double * x, double b, double * y, void * stream);

@@ -23,15 +23,12 @@ for b in blocks:
     agg = {k: sum(int(r[ix[k]]) for r in rows) for k in stall_cols}
     print({k: v for k, v in sorted(agg.items(), key=lambda kv: -kv[1]) if v})
     # cumulative samples by instruction index (to split phases), markers at BAR
-    acc = 0
-    seg, segs = 0, []
-    for i, r in enumerate(rows):
-        s = int(r[ix["# Samples"]])
-        seg += s
-        if "BAR.SYNC" in r[ix["Source"]] or i == len(rows) - 1:
-            segs.append((i, seg))
-            seg = 0
-    print("samples per barrier-delimited segment (end instr idx, samples):", segs)
+    # the compute warpgroup starts at USETMAXREG.TRY_ALLOC: stall breakdown of helper / compute code separately
+    split = next((i for i, r in enumerate(rows) if "USETMAXREG.TRY_ALLOC" in r[ix["Source"]]), None)
+    if split is not None:
+        for nm, rs in (("helper", rows[:split]), ("compute", rows[split:])):
+            ag = {k[6:]: sum(int(r[ix[k]]) for r in rs) for k in stall_cols}
+            print(nm, sum(ag.values()), {k: v for k, v in sorted(ag.items(), key=lambda kv: -kv[1]) if v})
     order = sorted(range(len(rows)), key=lambda i: -int(rows[i][ix["# Samples"]]))[:top]
     for i in sorted(order):
         r = rows[i]

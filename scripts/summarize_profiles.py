@@ -33,11 +33,17 @@ with open(os.path.join(out, "%s_launches_summary.txt" % tag), "w") as f:
 print(open(os.path.join(out, "%s_launches_summary.txt" % tag)).read())
 
 # ---- full capture -> key metrics per captured launch
-raw = subprocess.run(["ncu", "-i", os.path.join(ROOT, "gpurun_out", "prof_volume.ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rr = list(csv.reader(raw.splitlines()))
+rr = []
+for rep in ("prof_volume.ncu-rep", "prof_ops.ncu-rep"):
+    path = os.path.join(ROOT, "gpurun_out", rep)
+    if not os.path.exists(path):
+        continue
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    part = list(csv.reader(raw.splitlines()))
+    rr = part if not rr else rr + part[2:]
 h, u = rr[0], rr[1]
 idx = {k: i for i, k in enumerate(h)}
-want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+want = ["gpu__time_duration.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "launch__registers_per_thread", "launch__block_size", "launch__grid_size", "launch__shared_mem_per_block_dynamic",
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
@@ -45,7 +51,8 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct"]
 traffic = {}
 with open(os.path.join(out, "%s_volume_kernel_ncu.txt" % tag), "w") as f:
-    f.write("ncu --set full --clock-control none --import-source on -k regex:volume_action_kernel -s 6 -c 4 python bench.py --steps 3 --warmup 3 --no-extras\n\n")
+    f.write("ncu --set full --clock-control none --import-source on -k regex:volume_action_ws: -s 4 -c 1 python bench.py --steps 3 --warmup 3 --no-extras (fused kernel);\n"
+            "-s 2 -c 2 python scripts/prof_ops.py 1024 5 (stand-alone stiffness / weighted mass)\n\n")
     for r in rr[2:]:
         name = re.sub(r"\(.*", "", r[idx["Kernel Name"]]).replace("void cb200::<unnamed>::", "")
         f.write("== %s\n" % name)
@@ -55,9 +62,12 @@ with open(os.path.join(out, "%s_volume_kernel_ncu.txt" % tag), "w") as f:
         def gb(k):
             v, un = float(r[idx[k]].replace(",", "")), u[idx[k]]
             return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[un]
-        m = re.search(r"volume_action_kernel<(?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(bool\))?(\d)>", r[idx["Kernel Name"]])
+        m = re.search(r"volume_action_(?:kernel|ws)<(?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(bool\))?(\d)(?:, (?:\(int\))?(\d+))?>", r[idx["Kernel Name"]])
         if m:
-            key = ("stiffness" if m.group(3) == "1" else "mass") + "_%s_%s_nx1024" % (m.group(1), m.group(2))
+            if m.group(4) and m.group(4) != "0":
+                key = "helmholtz_%s_%s_%s_nx1024" % (m.group(1), m.group(2), m.group(4))
+            else:
+                key = ("stiffness" if m.group(3) == "1" else "mass") + "_%s_%s_nx1024" % (m.group(1), m.group(2))
             traffic[key] = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
 json.dump(traffic, open(os.path.join(out, "traffic.json"), "w"), indent=1)
 print(open(os.path.join(out, "%s_volume_kernel_ncu.txt" % tag)).read()[:3000])
