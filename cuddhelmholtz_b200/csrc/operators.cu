@@ -632,6 +632,10 @@ namespace cb200
         {
             asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
         }
+        __device__ __forceinline__ void cluster_sync_all()
+        {
+            asm volatile("barrier.cluster.arrive.relaxed.aligned;\nbarrier.cluster.wait.aligned;" ::: "memory");
+        }
         // 16-byte metric pairs of one quadrature row that are no longer needed after quadrature point ty
         template <int NQ, int NKI, int KR>
         __host__ __device__ constexpr int pairs_done(int ty)
@@ -649,11 +653,11 @@ namespace cb200
                                                        const double2 * gp, const double2 * gp_next, double (&out)[NB * NB],
                                                        const double msc, const int zero, const bool keep, const bool keep_next)
         {
-            // keep / keep_next: the rows of this phase / of the following phase will be read again soon (first field of the fused
-            // Helmholtz apply) -> leave them in L2; otherwise stream them with an evict-first hint
-            // (one load instruction with a run-time L2 cache-hint operand: evict_last / evict_first)
+            // keep / keep_next: the rows of this phase / of the following phase are read by a second CTA at about the same time
+            // (other field of the fused Helmholtz apply) -> normal L2 priority; otherwise stream them with an evict-first hint
+            // (one load instruction with a run-time L2 cache-hint operand)
             unsigned long long pol_keep, pol_stream;
-            asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+            asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
             asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
             auto ldm = [&](const double2 * q, const bool k) {
                 double2 v;
@@ -802,16 +806,21 @@ namespace cb200
 
             const int wg = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 7), 0); // warp-uniform by construction
             const int t = threadIdx.x & 127;
-            const int stride = gridDim.x;
+            // Fields (u, v of the fused Helmholtz apply) are dealt to the two CTAs of a thread-block cluster: CTA 2c works on u
+            // and CTA 2c + 1 on v of the SAME patch sequence, kept in step by one cluster barrier per patch, so the second
+            // reader of a metric block finds it in L2 (or in flight) instead of ~200 KB per CTA having to survive in L2 for a
+            // whole unit (ncu: 4.4 GB of DRAM reads per apply without this, against 2.2 GB algorithmic).
             const int NF = args.n_fields;
-            const int n_iter = ((args.n_patches - (int)blockIdx.x + stride - 1) / stride) * NF; // units = (patch, field)
+            const int f = (int)blockIdx.x % NF, cta = (int)blockIdx.x / NF;
+            const int stride = (int)gridDim.x / NF;
+            const int n_iter = (args.n_patches - cta + stride - 1) / stride;
             const int accumulate = args.accumulate;
 
             if (wg == 0) {
                 // =========================== helper warpgroup ===========================
                 asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
                 auto issue_gather = [&](const int i) {
-                    const int p = (int)blockIdx.x + (i / NF) * stride, f = i % NF;
+                    const int p = cta + i * stride;
                     const double * x = args.x + f * args.x_stride;
                     double * b = bufs + (i % 3) * BUF + t;
                     const int4 * ig = reinterpret_cast<const int4 *>(plan.Ig) + (size_t)p * (NG * PE) + t;
@@ -861,7 +870,7 @@ namespace cb200
                     }
                 };
                 auto assemble = [&](const int i) {
-                    const int p = (int)blockIdx.x + (i / NF) * stride, f = i % NF;
+                    const int p = cta + i * stride;
                     double * y = args.y + f * args.y_stride;
                     double * partial = args.partial + f * args.partial_stride;
                     const double c = args.c[f];
@@ -912,6 +921,8 @@ namespace cb200
                 named_sync(HELPER, 128);
                 named_arrive(FULL + 0, 256);
                 for (int i = 0; i < n_iter; ++i) {
+                    if (NF > 1)
+                        cluster_sync_all(); // both CTAs of the pair (all 512 threads) start patch i together
                     if (i + 1 < n_iter)
                         issue_gather(i + 1);
                     if (i >= 1) {
@@ -932,7 +943,7 @@ namespace cb200
                 const int e = t;
                 double g0[GK], g1[GK];
                 {
-                    const double2 * gpi = args.G1 + (size_t)blockIdx.x * g_patch1 + e;
+                    const double2 * gpi = args.G1 + (size_t)cta * g_patch1 + e;
 #pragma unroll
                     for (int m = 0; m < NPR1; ++m) {
                         const double2 v = __ldcs(gpi + m * PE);
@@ -944,11 +955,12 @@ namespace cb200
                     }
                 }
                 for (int i = 0; i < n_iter; ++i) {
-                    const int p = (int)blockIdx.x + (i / NF) * stride, f = i % NF;
+                    const int p = cta + i * stride;
                     double * b = bufs + (i % 3) * BUF + e;
-                    // first phase of the next unit of this CTA (same patch for the second field; at the very end this one again:
-                    // a harmless reload)
-                    const int pn = (i + 1 < n_iter) ? (int)blockIdx.x + ((i + 1) / NF) * stride : p;
+                    // first phase of the next patch of this CTA (at the very end this one again: a harmless reload)
+                    const int pn = (i + 1 < n_iter) ? p + stride : p;
+                    if (NF > 1)
+                        cluster_sync_all();
                     const double2 * gp1 = args.G1 + (size_t)p * g_patch1 + e;
                     const double2 * gp1_next = args.G1 + (size_t)pn * g_patch1 + e;
                     named_sync(FULL + i % 3, 256);
@@ -959,9 +971,9 @@ namespace cb200
                     if constexpr (NQ2 > 0) {
                         const double2 * gp2 = args.G2 + (size_t)p * g_patch2 + e;
                         // loads issued while working on field f fetch data of field f (phase 2) or of the next unit (phase 1)
-                        const bool first = NF > 1 && f == 0, last = NF > 1 && f == NF - 1; // this unit's data is read again / the next unit's is
-                        contract_phase<NB, NQ, STIFF, GK, NPR2, PE>(tab, b, g0, g1, gp1, gp2, out, 1.0, args.zero, first, first);
-                        contract_phase<NB, NQ2, false, GK, NPR1, PE>(tab2, b, g0, g1, gp2, gp1_next, out, args.msc, args.zero, first, last);
+                        const bool shared_read = NF > 1; // another CTA reads the same block at about the same time
+                        contract_phase<NB, NQ, STIFF, GK, NPR2, PE>(tab, b, g0, g1, gp1, gp2, out, 1.0, args.zero, shared_read, shared_read);
+                        contract_phase<NB, NQ2, false, GK, NPR1, PE>(tab2, b, g0, g1, gp2, gp1_next, out, args.msc, args.zero, shared_read, shared_read);
                     }
                     else
                         contract_phase<NB, NQ, STIFF, GK, NPR1, PE>(tab, b, g0, g1, gp1, gp1_next, out, 1.0, args.zero, false, false);
@@ -1507,9 +1519,44 @@ namespace cb200
                 cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
                 CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
                 grid = std::max(1, occ) * sms;
+                if (NQ2 > 0) { // launched as clusters of two CTAs: ask how many of those are co-resident
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3((unsigned)grid);
+                    cfg.blockDim = dim3(256);
+                    cfg.dynamicSmemBytes = smem;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeClusterDimension;
+                    at[0].val.clusterDim.x = 2;
+                    at[0].val.clusterDim.y = 1;
+                    at[0].val.clusterDim.z = 1;
+                    cfg.attrs = at;
+                    cfg.numAttrs = 1;
+                    int ncl = 0;
+                    if (cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg) == cudaSuccess && ncl > 0)
+                        grid = std::min(grid, 2 * ncl);
+                    else
+                        cudaGetLastError();
+                }
             }
-            const int g = (int)std::min<int64_t>(grid, plan.n_patches);
-            kern<<<g, 256, smem, s>>>(tab, tab2, pd, args);
+            const int nf = std::max(args.n_fields, 1);
+            const int g = (int)std::min<int64_t>(grid / nf, plan.n_patches) * nf;
+            if (nf > 1) { // one cluster = the CTAs that walk the same patches, one field each
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)g);
+                cfg.blockDim = dim3(256);
+                cfg.dynamicSmemBytes = smem;
+                cfg.stream = s;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = (unsigned)nf;
+                at[0].val.clusterDim.y = 1;
+                at[0].val.clusterDim.z = 1;
+                cfg.attrs = at;
+                cfg.numAttrs = 1;
+                CB_CUDA(cudaLaunchKernelEx(&cfg, kern, tab, tab2, pd, args));
+            }
+            else
+                kern<<<g, 256, smem, s>>>(tab, tab2, pd, args);
             CB_LAUNCHED();
         }
 
