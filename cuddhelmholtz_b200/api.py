@@ -190,6 +190,13 @@ class H1Space:
     def size(self):
         return int(load().cuddh_b200_h1space_size(self._h))
 
+    def check_plan(self, node_major):
+        """host-only self check of the assembly plan (include/cuddh_b200.h): dict of plan sizes and 'mismatches' (0 = ok)."""
+        st = (C.c_int64 * 8)()
+        check(load().cuddh_b200_h1space_check_plan(self._h, int(node_major), st))
+        keys = ("n_patches", "patch_elems", "listed_dofs", "shared_dofs", "max_pdof", "dofs_over_four", "mismatches")
+        return dict(zip(keys, [int(v) for v in st[:7]]))
+
     def mesh(self):
         return self._mesh
 

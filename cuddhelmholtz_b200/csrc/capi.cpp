@@ -156,6 +156,12 @@ int cuddh_b200_h1space_destroy(cuddh_h1space_t s)
     return 0;
 }
 int64_t cuddh_b200_h1space_size(cuddh_h1space_t s) { return s->s->ndof; }
+int cuddh_b200_h1space_check_plan(cuddh_h1space_t s, int node_major, int64_t * stats)
+{
+    CB_TRY
+    plan_self_check(*s->s, node_major != 0, stats);
+    CB_CATCH
+}
 int cuddh_b200_h1space_global_indices(cuddh_h1space_t s, int * I)
 {
     CB_TRY

@@ -210,4 +210,5 @@ namespace cb200
     };
 
     void build_plan(H1Space & fem, Plan & plan, bool tpe = false);
+    void plan_self_check(H1Space & fem, bool tpe, int64_t stats[8]); // host-only, see h1space.cpp
 } // namespace cb200

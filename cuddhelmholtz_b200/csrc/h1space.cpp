@@ -430,6 +430,91 @@ namespace cb200
 
     }
 
+    // Host-only self check of an assembly plan (no GPU): plays the kernels' gather / assembly with integer-valued element
+    // contributions v(el, a) and compares with the direct sum over I. Exercises both layouts; used by the CPU test-suite.
+    // stats: n_patches, PE, listed patch DOFs, shared DOFs, max_pdof, entries beyond four per DOF, mismatches, reserved
+    void plan_self_check(H1Space & fem, bool tpe, int64_t stats[8])
+    {
+        Plan plan;
+        build_plan(fem, plan, tpe);
+        const int nb = fem.nb, nb2 = nb * nb, PE = plan.PE, NG = (nb2 + 3) / 4;
+        auto val = [](int64_t el, int a) { return (double)((el * 31 + a * 7) % 1009 + 1); };
+        std::vector<double> expect((size_t)fem.ndof, 0.0), y((size_t)fem.ndof, -1.0), partial((size_t)std::max<int64_t>(plan.n_slots_total, 1), -1.0);
+        for (int64_t el = 0; el < fem.n_elem; ++el)
+            for (int a = 0; a < nb2; ++a)
+                expect[fem.I[(size_t)nb2 * el + a]] += val(el, a);
+        auto interior = [nb](int a) { const int i = a % nb, j = a / nb; return i > 0 && i < nb - 1 && j > 0 && j < nb - 1; };
+        int64_t listed = 0, over4 = 0, bad = 0;
+        for (int64_t p = 0; p < plan.n_patches; ++p) {
+            const PatchHdr & h = plan.hdr[p];
+            auto entry_val = [&](int ent) { // value the compute phase leaves at entry `ent` of the patch buffer
+                const int k = plan.node_major ? ent % PE : ent / nb2, a = plan.node_major ? ent / PE : ent % nb2;
+                if (k >= h.n_elem)
+                    return 1e300; // a padding slot must never be referenced
+                return val(plan.slot_elem[(size_t)p * PE + k], a);
+            };
+            if (plan.node_major) {
+                for (int k = 0; k < h.n_elem; ++k) {
+                    const int64_t el = plan.slot_elem[(size_t)p * PE + k];
+                    for (int a = 0; a < nb2; ++a) {
+                        const int gi = plan.Ig[(((size_t)p * NG + a / 4) * PE + k) * 4 + a % 4];
+                        if (gi != fem.I[(size_t)nb2 * el + a])
+                            ++bad;
+                        if (interior(a)) // written by the element thread itself: must be the only contribution
+                            y[gi] = (y[gi] == -1.0) ? val(el, a) : 1e300;
+                    }
+                }
+            }
+            listed += h.n_pdof;
+            const uint16_t * cp = &plan.cptr[h.cptr_begin];
+            const uint16_t * ce = &plan.cent[(size_t)p * PE * nb2];
+            for (int d = 0; d < h.n_pdof; ++d) {
+                double sum = 0.0;
+                if (plan.node_major) {
+                    const uint16_t * r = &plan.cent4[((size_t)h.pdof_begin + d) * 4];
+                    for (int k = 0; k < 3; ++k)
+                        if (r[k] != 0xFFFF)
+                            sum += entry_val(r[k]);
+                    if (r[3] < 0xFFFE)
+                        sum += entry_val(r[3]);
+                    else if (r[3] == 0xFFFE) {
+                        ++over4;
+                        for (int k = cp[d] + 3; k < cp[d + 1]; ++k)
+                            sum += entry_val(ce[k]);
+                    }
+                }
+                else
+                    for (int k = cp[d]; k < cp[d + 1]; ++k)
+                        sum += entry_val(ce[k]);
+                const bool priv = d < h.n_int;
+                const int tgt = plan.node_major ? plan.target[(size_t)h.pdof_begin + d]
+                                                : (priv ? plan.gid[(size_t)h.pdof_begin + d] : plan.slot[(size_t)h.slot_begin + d - h.n_int]);
+                if (priv)
+                    y[tgt] = (y[tgt] == -1.0) ? sum : 1e300;
+                else
+                    partial[tgt] = (partial[tgt] == -1.0) ? sum : 1e300;
+            }
+        }
+        for (int64_t sidx = 0; sidx < plan.n_shared; ++sidx) {
+            double sum = 0.0;
+            for (int k = plan.sh_ptr[sidx]; k < plan.sh_ptr[sidx + 1]; ++k)
+                sum += partial[k];
+            const int gi = plan.sh_gid[sidx];
+            y[gi] = (y[gi] == -1.0) ? sum : 1e300;
+        }
+        for (int64_t g = 0; g < fem.ndof; ++g)
+            if (y[g] != expect[g])
+                ++bad;
+        stats[0] = plan.n_patches;
+        stats[1] = PE;
+        stats[2] = listed;
+        stats[3] = plan.n_shared;
+        stats[4] = plan.max_pdof;
+        stats[5] = over4;
+        stats[6] = bad;
+        stats[7] = 0;
+    }
+
     void Plan::ensure_device()
     {
         if (on_device)

@@ -799,6 +799,7 @@ namespace cb200
             constexpr int FULL = 1, READY = 4, HELPER = 7; // named barrier ids (0 is __syncthreads)
             constexpr int NG = (NB2 + 3) / 4;                // groups of four nodes in the global index map
             constexpr int NI = (NB > 2 ? NB - 2 : 0) * (NB > 2 ? NB - 2 : 0); // element-interior nodes
+            constexpr bool HEAVY = STIFF && NB >= 5 && NQ2 > 0;
 
             extern __shared__ __align__(16) unsigned char smem_raw[];
             double * bufs = reinterpret_cast<double *>(smem_raw); // [3][NB2][PE]
@@ -818,7 +819,12 @@ namespace cb200
 
             if (wg == 0) {
                 // =========================== helper warpgroup ===========================
-                asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+                // register split of the 2 x 32768 budget: the stiffness contraction at n_basis 5 needs every register it can get
+                // (216 / 40); the lighter instances are helper-bound and prefer 208 / 48 (measured both ways)
+                if constexpr (HEAVY)
+                    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+                else
+                    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
                 auto issue_gather = [&](const int i) {
                     const int p = cta + i * stride;
                     const double * x = args.x + f * args.x_stride;
@@ -939,7 +945,10 @@ namespace cb200
             }
             else {
                 // =========================== compute warpgroup: one element per thread ===========================
-                asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+                if constexpr (HEAVY)
+                    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+                else
+                    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
                 const int e = t;
                 double g0[GK], g1[GK];
                 {

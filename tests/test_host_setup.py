@@ -201,3 +201,25 @@ def test_ensemble_c_abi_matches_reference(gold):
         assert b"illogically" in lib.cuddh_b200_last_error()
     finally:
         lib.cuddh_b200_ensemble_destroy(h)
+
+
+@pytest.mark.parametrize("tag,nb", [("rect2", 3), ("rect10", 2), ("rect10", 4), ("rect10", 5), ("rect37", 5), ("rect37", 4), ("rect6", 8),
+                                    ("unstr", 2), ("unstr", 3), ("unstr", 4), ("unstr", 5), ("unstr", 9)])
+@pytest.mark.parametrize("node_major", [0, 1])
+def test_assembly_plan_self_check(tag, nb, node_major):
+    """the deterministic assembly plans behind Operator::action (both layouts) reproduce the plain sum over global_indices:
+    every element node is either written once by its element (interior nodes, node-major plan) or listed exactly once per
+    patch with all its contributions; shared DOFs get one partial slot per touching patch. Host only (no GPU)."""
+    mesh = cb.Mesh2D.uniform_rect(37, -1.0, 1.0, 29, 0.0, 2.0) if tag == "rect37" else _meshes(tag)
+    fem = cb.H1Space(mesh, cb.Basis(nb))
+    st = fem.check_plan(node_major)
+    assert st["mismatches"] == 0, st
+    nel = mesh.n_elem()
+    assert st["n_patches"] * st["patch_elems"] >= nel
+    if node_major:
+        assert st["patch_elems"] % 32 == 0
+        # only element-boundary DOFs are listed: strictly fewer than all DOFs as soon as elements have interior nodes
+        if nb > 2:
+            assert st["listed_dofs"] - st["shared_dofs"] < fem.size()
+    if tag == "unstr":
+        assert st["dofs_over_four"] >= 0  # the unstructured mesh has valence-5 vertices: the overflow path is exercised when > 0
