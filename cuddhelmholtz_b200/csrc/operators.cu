@@ -422,172 +422,13 @@ namespace cb200
             }
         }
 
-        // ------------------------------------------------------------------------------------------
-        // Persistent, software-pipelined variant of the action kernel (opt-in experiment). ncu on the one-CTA-per-patch kernel
-        // above shows 40 % of all warp stalls on the long scoreboard: the staging phase is a chain of three dependent
-        // global loads (header -> DOF list -> x values) during which the whole CTA waits. Here a CTA loops over patches
-        // p_i = blockIdx.x + i * gridDim.x and, while it contracts patch p_i, the data of the next patches streams into
-        // shared memory with cp.async (no registers, no stalls):
-        //     iteration i issues   header of p_{i+3}  ->  DOF list (gid) of p_{i+2}  ->  x gather, local maps, assembly lists
-        //     of p_{i+1}, then computes p_i and waits for the copies only at the end of the iteration.
-        // Buffers: gid x3, header x4, everything else x2. Same plan, same arithmetic, same summation order as above.
-        // ------------------------------------------------------------------------------------------
-        __device__ __forceinline__ void cp_async4(void * smem, const void * g)
-        {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
-        }
         __device__ __forceinline__ void cp_async8(void * smem, const void * g)
         {
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
         }
-        __device__ __forceinline__ void cp_async16(void * smem, const void * g)
-        {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
-        }
         __device__ __forceinline__ void cp_async_wait_all()
         {
             asm volatile("cp.async.commit_group;\ncp.async.wait_all;" ::: "memory");
-        }
-
-        template <int NB, int NQ, bool STIFF>
-        __global__ void __launch_bounds__(256, (NB <= 6 ? 3 : 2))
-        volume_action_pipelined(const __grid_constant__ Tables<NB, NQ, STIFF> tab, const PlanDev plan,
-                                const double * __restrict__ G, const double * __restrict__ x, double * __restrict__ y,
-                                double * __restrict__ partial, const double c, const int accumulate, const int max_pdof,
-                                const int max_nsh, const int n_patches)
-        {
-            constexpr int EPW = 32 / NQ;
-            constexpr int LW = EPW * NQ;
-            constexpr int NB2 = NB * NB;
-            constexpr int NK = STIFF ? 3 * NQ : NQ;
-            constexpr int SCR = scr_layout<NB, NQ, STIFF>().S;
-
-            extern __shared__ __align__(16) unsigned char smem_raw[];
-            const int PE = plan.PE;
-            const int n_pass_patch = (PE + EPW - 1) / EPW;
-            const int nwarps = blockDim.x >> 5;
-            const int nthr = blockDim.x;
-            const int mp2 = (max_pdof + 2) & ~1; // even
-            // layout (8-byte items first)
-            double * xloc = reinterpret_cast<double *>(smem_raw);                  // [2][max_pdof]
-            double * su = xloc + 2 * max_pdof;                                     // [PE*NB2]
-            double * scratch = su + PE * NB2;                                      // [nwarps*EPW*SCR]
-            PatchHdr * hdr_s = reinterpret_cast<PatchHdr *>((reinterpret_cast<size_t>(scratch + nwarps * EPW * SCR) + 15) & ~size_t(15)); // [4], 16-byte aligned
-            int * gid_s = reinterpret_cast<int *>(hdr_s + 4);                      // [3][max_pdof]
-            int * slot_s = gid_s + 3 * max_pdof;                                   // [2][max_nsh]
-            uint16_t * L_s = reinterpret_cast<uint16_t *>(slot_s + 2 * max_nsh);   // [2][PE*NB2]
-            uint16_t * cent_s = L_s + 2 * PE * NB2;                                // [2][PE*NB2]
-            uint16_t * cptr_s = cent_s + 2 * PE * NB2;                             // [2][mp2]
-
-            const int tid = threadIdx.x;
-            const int lane = tid & 31;
-            const int warp = tid >> 5;
-            const size_t g_patch = (size_t)n_pass_patch * NK * LW;
-            const int stride = gridDim.x;
-            auto patch_of = [&](int i) { return (int)blockIdx.x + i * stride; };
-
-            // issue helpers (all threads participate)
-            auto issue_hdr = [&](int i) {
-                const int p = patch_of(i);
-                if (p < n_patches && tid < 2)
-                    cp_async16(reinterpret_cast<char *>(hdr_s + (i & 3)) + 16 * tid, reinterpret_cast<const char *>(plan.hdr + p) + 16 * tid);
-            };
-            auto issue_gid = [&](int i) {
-                const int p = patch_of(i);
-                if (p >= n_patches)
-                    return;
-                const PatchHdr h = hdr_s[i & 3];
-                const int * src = plan.gid + h.pdof_begin;
-                int * dst = gid_s + (i % 3) * max_pdof;
-                for (int d = tid; d < h.n_pdof; d += nthr)
-                    cp_async4(dst + d, src + d);
-            };
-            auto issue_patch_data = [&](int i) {
-                const int p = patch_of(i);
-                if (p >= n_patches)
-                    return;
-                const PatchHdr h = hdr_s[i & 3];
-                const int b = i & 1;
-                const int * gs = gid_s + (i % 3) * max_pdof;
-                double * xl = xloc + b * max_pdof;
-                for (int d = tid; d < h.n_pdof; d += nthr)
-                    cp_async8(xl + d, x + gs[d]);
-                const int n32 = (h.n_elem * NB2 + 1) >> 1;
-                const uint32_t * Lg = reinterpret_cast<const uint32_t *>(plan.L + (size_t)h.elem_begin * NB2);
-                const uint32_t * Cg = reinterpret_cast<const uint32_t *>(plan.cent + (size_t)h.elem_begin * NB2);
-                uint32_t * Ld = reinterpret_cast<uint32_t *>(L_s + b * PE * NB2);
-                uint32_t * Cd = reinterpret_cast<uint32_t *>(cent_s + b * PE * NB2);
-                for (int k = tid; k < n32; k += nthr) {
-                    cp_async4(Ld + k, Lg + k);
-                    cp_async4(Cd + k, Cg + k);
-                }
-                const uint32_t * Pg = reinterpret_cast<const uint32_t *>(plan.cptr + h.cptr_begin); // cptr_begin is even (plan)
-                uint32_t * Pd = reinterpret_cast<uint32_t *>(cptr_s + b * mp2);
-                for (int k = tid; k < (h.n_pdof + 2) >> 1; k += nthr)
-                    cp_async4(Pd + k, Pg + k);
-                const int nsh = h.n_pdof - h.n_int;
-                const int * sg = plan.slot + h.slot_begin;
-                int * sd = slot_s + b * max_nsh;
-                for (int k = tid; k < nsh; k += nthr)
-                    cp_async4(sd + k, sg + k);
-                if (tid == 0)
-                    bulk_prefetch_l2(G + (size_t)p * g_patch, g_patch * sizeof(double));
-            };
-
-            // ---- prologue: headers of p_0..p_2, DOF lists of p_0, p_1, data of p_0 ----
-            issue_hdr(0);
-            issue_hdr(1);
-            issue_hdr(2);
-            cp_async_wait_all();
-            __syncthreads();
-            issue_gid(0);
-            issue_gid(1);
-            cp_async_wait_all();
-            __syncthreads();
-            issue_patch_data(0);
-            cp_async_wait_all();
-            __syncthreads();
-
-            for (int i = 0; patch_of(i) < n_patches; ++i) {
-                // ---- prefetch: header i+3, DOF list i+2, data i+1 ----
-                issue_hdr(i + 3);
-                issue_gid(i + 2);
-                issue_patch_data(i + 1);
-                asm volatile("cp.async.commit_group;" ::: "memory");
-
-                const PatchHdr hdr = hdr_s[i & 3];
-                const int b = i & 1;
-                const double * xl = xloc + b * max_pdof;
-                const uint16_t * Ls = L_s + b * PE * NB2;
-
-                // ---- B. element contractions ----
-                contract_patch<NB, NQ, STIFF>(tab, G, patch_of(i), n_pass_patch, hdr.n_elem, lane, warp, nwarps, xl, Ls, scratch, su);
-                __syncthreads();
-
-                // ---- C. deterministic assembly + write-back (CSR order) ----
-                {
-                    const uint16_t * cp = cptr_s + b * mp2;
-                    const uint16_t * ce = cent_s + b * PE * NB2;
-                    const int * gs = gid_s + (i % 3) * max_pdof;
-                    const int * sl = slot_s + b * max_nsh - hdr.n_int;
-                    for (int d = tid; d < hdr.n_pdof; d += nthr) {
-                        const int k0 = cp[d], k1 = cp[d + 1];
-                        double sum = 0.0;
-                        for (int k = k0; k < k1; ++k)
-                            sum += su[ce[k]];
-                        if (d < hdr.n_int) {
-                            const int gi = gs[d];
-                            const double v = c * sum;
-                            y[gi] = accumulate ? (y[gi] + v) : v;
-                        }
-                        else
-                            partial[sl[d]] = sum;
-                    }
-                }
-                // ---- everything prefetched in this iteration has landed; buffers of patch i may be reused ----
-                asm volatile("cp.async.wait_all;" ::: "memory");
-                __syncthreads();
-            }
         }
 
         // metric layout of the thread-per-element kernel below: [pair of values][element], rows padded to an even count
@@ -1438,35 +1279,6 @@ namespace cb200
                         tab.Dcol[k][q] = op.D[q + NQ * k];
                     }
                 }
-            // opt-in (CUDDH_B200_PIPELINED=1): measured slower than the one-CTA-per-patch kernel at every size tried
-            // (0.48 vs 0.46 ms stiffness, 0.67 vs 0.54 ms weighted mass at 1024^2, n_basis 5): it removes the staging
-            // stalls but its extra buffers cost one resident CTA per SM; see profiles/r01_notes.md
-            static const int use_pipelined = env_int("CUDDH_B200_PIPELINED", 0);
-            if (use_pipelined) {
-                const size_t pe2 = (size_t)plan.PE * NB * NB;
-                size_t sm = sizeof(double) * ((size_t)2 * plan.max_pdof + pe2 + (size_t)nwarps * EPW * SCR) + 4 * sizeof(PatchHdr) +
-                            sizeof(int) * ((size_t)3 * plan.max_pdof + (size_t)2 * plan.max_nsh) +
-                            sizeof(uint16_t) * (4 * pe2 + 2 * (size_t)((plan.max_pdof + 2) & ~1));
-                sm = ((sm + 15) & ~size_t(15)) + 16; // + alignment slack of the header ring
-                auto pk = volume_action_pipelined<NB, NQ, STIFF>;
-                static int grid = 0;
-                static size_t set_sm = 0;
-                if (!grid || sm > set_sm) {
-                    CB_CUDA(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(sm, (size_t)49152)));
-                    CB_CUDA(cudaFuncSetAttribute(pk, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-                    int dev = 0, sms = 148, occ = 1;
-                    cudaGetDevice(&dev);
-                    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-                    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pk, nwarps * 32, sm));
-                    grid = std::max(1, occ) * sms;
-                    set_sm = sm;
-                }
-                const int g = (int)std::min<int64_t>(grid, plan.n_patches);
-                pk<<<g, nwarps * 32, sm, s>>>(tab, pd, op.d_G.p, x, y, op.d_partial.p, c, accumulate, plan.max_pdof, plan.max_nsh,
-                                             (int)plan.n_patches);
-                CB_LAUNCHED();
-                return;
-            }
             auto kern = volume_action_kernel<NB, NQ, STIFF>;
             static bool attr_set = false;
             static size_t attr_smem = 0;
