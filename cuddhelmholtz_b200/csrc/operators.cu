@@ -598,6 +598,159 @@ namespace cb200
             }
         }
 
+        // ---- shared-memory metric ring (TMA bulk copies + mbarriers), used by the heavy fused instances -------------------
+        // The register double buffer above keeps ~one quadrature row of metric data in flight per thread (ptxas sinks the
+        // reloads to the end of a row) and costs 72 registers at n_basis 5. Here the compute warpgroup feeds itself through a
+        // ring of RING chunks in shared memory: a chunk = up to five 16-byte pairs of one quadrature row for all 128 elements
+        // of the patch, one contiguous block of the [pair][element] layout = ONE cp.async.bulk (TMA) copy completing on an
+        // mbarrier. At the start of a row every thread waits for the row's chunk(s), pulls its pairs into registers (one row:
+        // 36 registers instead of 72), a 128-thread named barrier says the slots are free, and thread 0 immediately issues the
+        // copies of the chunks RING positions further down the stream (across phases, fields and patches). Depth is set by
+        // shared memory, not by registers or by ptxas' scheduling.
+        __device__ __forceinline__ unsigned smem_u32(const void * p)
+        {
+            return (unsigned)__cvta_generic_to_shared(p);
+        }
+        __device__ __forceinline__ void mbar_init(const unsigned bar, const int count)
+        {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+        }
+        __device__ __forceinline__ void mbar_expect_tx(const unsigned bar, const unsigned bytes)
+        {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        }
+        __device__ __forceinline__ void bulk_copy_g2s(const unsigned dst, const void * src, const unsigned bytes, const unsigned bar)
+        {
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                         "r"(bytes), "r"(bar)
+                         : "memory");
+        }
+        __device__ __forceinline__ void mbar_wait(const unsigned bar, const unsigned parity)
+        {
+            asm volatile("{\n"
+                         ".reg .pred p;\n"
+                         "MBAR_WAIT_LOOP:\n"
+                         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                         "@p bra MBAR_WAIT_DONE;\n"
+                         "bra MBAR_WAIT_LOOP;\n"
+                         "MBAR_WAIT_DONE:\n"
+                         "}" ::"r"(bar),
+                         "r"(parity)
+                         : "memory");
+        }
+        // chunks of a quadrature row with NPR pairs: NH chunks of at most CP <= 5 pairs
+        __host__ __device__ constexpr int ring_nh(int npr) { return (npr + 4) / 5; }
+        __host__ __device__ constexpr int ring_cp(int npr) { return (npr + ring_nh(npr) - 1) / ring_nh(npr); }
+
+        struct RingState // consumer position in the ring (uniform across the warpgroup)
+        {
+            const double2 * ring; // [RING][CHUNK_PAIRS][PE]
+            unsigned mbar;        // shared address of the RING mbarriers
+            int slot, parity;
+        };
+
+        // one operator phase fed from the ring; `issue(slot)` (thread 0 only) starts the copy of the next chunk of the stream
+        template <int NB, int NQ, bool STIFF, int PE, int RING, int CHUNK_PAIRS, class IssueFn>
+        __device__ __forceinline__ void contract_phase_ring(const Tables<NB, NQ, STIFF> & tab, const double (&U)[NB * NB], RingState & rs, const int e,
+                                                            double (&out)[NB * NB], const double msc, const int zero, const bool leader,
+                                                            IssueFn issue)
+        {
+            using Cfg = TpeCfg<NB, NQ, STIFF>;
+            constexpr int NKI = Cfg::NKI, KR = Cfg::KR, NPR = KR / 2;
+            constexpr int NH = ring_nh(NPR), CP = ring_cp(NPR);
+            static_assert(CP <= CHUNK_PAIRS && NH <= RING, "ring geometry");
+#pragma unroll 1
+            for (int tx = 0; tx < NQ; ++tx) {
+                const int z = tx * zero; // 0 at run time; keeps the ty-indexed table loads inside the rolled loop
+                double g[KR];
+                int freed[NH];
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    mbar_wait(rs.mbar + 8 * rs.slot, (unsigned)rs.parity);
+                    const double2 * src = rs.ring + (size_t)rs.slot * (CHUNK_PAIRS * PE) + e;
+#pragma unroll
+                    for (int m = 0; m < CP; ++m)
+                        if (h * CP + m < NPR) {
+                            const double2 v = src[m * PE];
+                            g[2 * (h * CP + m)] = v.x;
+                            g[2 * (h * CP + m) + 1] = v.y;
+                        }
+                    freed[h] = rs.slot;
+                    if (++rs.slot == RING) {
+                        rs.slot = 0;
+                        rs.parity ^= 1;
+                    }
+                }
+                named_sync(8, PE); // every thread of the warpgroup holds its pairs in registers: the slots are free
+                if (leader) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+                    for (int h = 0; h < NH; ++h)
+                        issue(freed[h]);
+                }
+                double pu[NB], du[STIFF ? NB : 1];
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int ii = 0; ii < NB; ++ii) {
+                        const double u = U[ii + NB * j];
+                        s0 = fma(tab.Prow[tx][ii], u, s0);
+                        if (STIFF)
+                            s1 = fma(tab.Drow[tx][ii], u, s1);
+                    }
+                    pu[j] = s0;
+                    if (STIFF)
+                        du[j] = s1;
+                }
+                double a0[NB], a1[STIFF ? NB : 1];
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    a0[q] = 0.0;
+                    if (STIFF)
+                        a1[q] = 0.0;
+                }
+#pragma unroll
+                for (int ty = 0; ty < NQ; ++ty) {
+                    if (STIFF) {
+                        double Dx = 0.0, Dy = 0.0;
+#pragma unroll
+                        for (int l = 0; l < NB; ++l) {
+                            Dx = fma(tab.Prow[ty + z][l], du[l], Dx);
+                            Dy = fma(tab.Drow[ty + z][l], pu[l], Dy);
+                        }
+                        const double A = g[NKI * ty], B = g[NKI * ty + (NKI > 1 ? 1 : 0)], C = g[NKI * ty + (NKI > 2 ? 2 : 0)];
+                        const double F0 = A * Dx + B * Dy;
+                        const double F1 = B * Dx + C * Dy;
+#pragma unroll
+                        for (int q = 0; q < NB; ++q) {
+                            a0[q] = fma(tab.Prow[ty + z][q], F0, a0[q]);
+                            a1[q] = fma(tab.Drow[ty + z][q], F1, a1[q]);
+                        }
+                    }
+                    else {
+                        double ppu = 0.0;
+#pragma unroll
+                        for (int l = 0; l < NB; ++l)
+                            ppu = fma(tab.Prow[ty + z][l], pu[l], ppu);
+                        const double val = (g[ty] * msc) * ppu;
+#pragma unroll
+                        for (int q = 0; q < NB; ++q)
+                            a0[q] = fma(tab.Prow[ty + z][q], val, a0[q]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < NB; ++q)
+#pragma unroll
+                    for (int ii = 0; ii < NB; ++ii) {
+                        if (STIFF)
+                            out[ii + NB * q] = fma(tab.Drow[tx][ii], a0[q], fma(tab.Prow[tx][ii], a1[q], out[ii + NB * q]));
+                        else
+                            out[ii + NB * q] = fma(tab.Prow[tx][ii], a0[q], out[ii + NB * q]);
+                    }
+            }
+        }
+
         // second-phase placeholder for the single-operator instances
         struct NoTables
         {
@@ -624,7 +777,7 @@ namespace cb200
             int accumulate, n_patches, n_fields, zero;
         };
 
-        template <int NB, int NQ, bool STIFF, int NQ2>
+        template <int NB, int NQ, bool STIFF, int NQ2, int RING>
         __global__ void __launch_bounds__(256, 2)
         volume_action_ws(const __grid_constant__ Tables<NB, NQ, STIFF> tab, const __grid_constant__ typename Phase2<NB, NQ2>::type tab2,
                          const PlanDev plan, const __grid_constant__ WsArgs args)
@@ -634,7 +787,7 @@ namespace cb200
             constexpr int PE = 128;
             constexpr int NB2 = NB * NB;
             constexpr int NPR1 = Cfg::KR / 2, NPR2 = NQ2 > 0 ? Cfg2::KR / 2 : 0;
-            constexpr int GK = 2 * (NPR1 > NPR2 ? NPR1 : NPR2); // metric registers per row buffer
+            constexpr int GK = 2 * (NPR1 > NPR2 ? NPR1 : NPR2); // metric registers per row buffer (RING == 0)
             constexpr int BUF = NB2 * PE; // doubles per patch buffer
             constexpr size_t g_patch1 = (size_t)Cfg::NK2 * PE, g_patch2 = NQ2 > 0 ? (size_t)Cfg2::NK2 * PE : 0; // double2 per patch
             constexpr int FULL = 1, READY = 4, HELPER = 7; // named barrier ids (0 is __syncthreads)
@@ -642,9 +795,18 @@ namespace cb200
             constexpr int NI = (NB > 2 ? NB - 2 : 0) * (NB > 2 ? NB - 2 : 0); // element-interior nodes
             constexpr bool HEAVY = STIFF && NB >= 5 && NQ2 > 0;
 
+            // shared-memory metric ring (RING > 0): chunk = CHUNK_PAIRS x PE 16-byte pairs
+            constexpr int CP1 = ring_cp(NPR1), CP2 = NQ2 > 0 ? ring_cp(NPR2) : 0;
+            constexpr int CHUNK_PAIRS = CP1 > CP2 ? CP1 : CP2;
+            // patch buffers in rotation: 3 (fill i+1 | compute i | assemble i-1 at the same time), or 2 for the deep-ring heavy
+            // instances, where one unit of compute is long enough for the helper to assemble i-1 and THEN refill the same buffer
+            constexpr int NBUF = RING > 2 ? 2 : 3;
+
             extern __shared__ __align__(16) unsigned char smem_raw[];
-            double * bufs = reinterpret_cast<double *>(smem_raw); // [3][NB2][PE]
-            int * gints = reinterpret_cast<int *>(bufs + 3 * BUF);  // [3][NI][PE] global DOFs of the element-interior nodes
+            double * bufs = reinterpret_cast<double *>(smem_raw); // [NBUF][NB2][PE]
+            int * gints = reinterpret_cast<int *>(bufs + NBUF * BUF); // [NBUF][NI][PE] global DOFs of the element-interior nodes
+            double2 * ring = reinterpret_cast<double2 *>(gints + NBUF * NI * PE);                        // [RING][CHUNK_PAIRS][PE]
+            unsigned long long * mbars = reinterpret_cast<unsigned long long *>(ring + RING * CHUNK_PAIRS * PE); // [RING]
 
             const int wg = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 7), 0); // warp-uniform by construction
             const int t = threadIdx.x & 127;
@@ -669,7 +831,7 @@ namespace cb200
                 auto issue_gather = [&](const int i) {
                     const int p = cta + i * stride;
                     const double * x = args.x + f * args.x_stride;
-                    double * b = bufs + (i % 3) * BUF + t;
+                    double * b = bufs + (i % NBUF) * BUF + t;
                     const int4 * ig = reinterpret_cast<const int4 *>(plan.Ig) + (size_t)p * (NG * PE) + t;
                     int4 idx[NG]; // all index loads of the element in flight at once
 #pragma unroll
@@ -678,7 +840,7 @@ namespace cb200
                     // hand the global DOFs of the element-interior nodes (written by the compute thread itself) over in shared memory
                     if (NI > 0) {
                         const int n_el = __ldg(&plan.hdr[p].n_elem);
-                        int * gs = gints + (i % 3) * (NI * PE) + t;
+                        int * gs = gints + (i % NBUF) * (NI * PE) + t;
 #pragma unroll
                         for (int k = 0; k < NB2; ++k) {
                             const int ki = k % NB, kj = k / NB;
@@ -722,7 +884,7 @@ namespace cb200
                     double * partial = args.partial + f * args.partial_stride;
                     const double c = args.c[f];
                     const PatchHdr hdr = plan.hdr[p];
-                    const double * su = bufs + (i % 3) * BUF;
+                    const double * su = bufs + (i % NBUF) * BUF;
                     const uint2 * recp = plan.cent4 + hdr.pdof_begin;
                     const int * tgtp = plan.target + hdr.pdof_begin;
                     constexpr int CU = 4; // DOFs in flight per thread: record and target loads of a batch are independent
@@ -770,18 +932,22 @@ namespace cb200
                 for (int i = 0; i < n_iter; ++i) {
                     if (NF > 1)
                         cluster_sync_all(); // both CTAs of the pair (all 512 threads) start patch i together
-                    if (i + 1 < n_iter)
+                    if (NBUF >= 3 && i + 1 < n_iter)
                         issue_gather(i + 1);
                     if (i >= 1) {
-                        named_sync(READY + (i - 1) % 3, 256);
+                        named_sync(READY + (i - 1) % NBUF, 256);
                         assemble(i - 1);
+                    }
+                    if (NBUF < 3 && i + 1 < n_iter) { // the buffer just assembled is the one to refill
+                        named_sync(HELPER, 128);
+                        issue_gather(i + 1);
                     }
                     cp_async_wait_all();
                     named_sync(HELPER, 128); // every helper thread is done reading buffer i-1 and its copies for i+1 landed
                     if (i + 1 < n_iter)
-                        named_arrive(FULL + (i + 1) % 3, 256);
+                        named_arrive(FULL + (i + 1) % NBUF, 256);
                 }
-                named_sync(READY + (n_iter - 1) % 3, 256);
+                named_sync(READY + (n_iter - 1) % NBUF, 256);
                 assemble(n_iter - 1);
             }
             else {
@@ -791,8 +957,48 @@ namespace cb200
                 else
                     asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
                 const int e = t;
-                double g0[GK], g1[GK];
-                {
+                double g0[RING > 0 ? 1 : GK], g1[RING > 0 ? 1 : GK];
+                // ---- shared-memory metric ring: consumer state (all threads) and producer cursor (thread 0) ----
+                RingState rs{ring, smem_u32(mbars), 0, 0};
+                int cur_i = 0, cur_ph = 0, cur_r = 0, cur_h = 0; // next chunk of the stream to be issued: (patch iteration, phase, row, chunk)
+                auto issue = [&](const int slot) {
+                    if (cur_i >= n_iter)
+                        return;
+                    const int p = cta + cur_i * stride;
+                    const int npr = cur_ph == 0 ? NPR1 : NPR2, cp = cur_ph == 0 ? CP1 : CP2;
+                    const double2 * src = (cur_ph == 0 ? args.G1 + (size_t)p * g_patch1 : args.G2 + (size_t)p * g_patch2) +
+                                          (size_t)(cur_r * npr + cur_h * cp) * PE;
+                    const int pairs = min(cp, npr - cur_h * cp);
+                    const unsigned bytes = (unsigned)(pairs * PE * sizeof(double2));
+                    const unsigned bar = rs.mbar + 8 * slot;
+                    mbar_expect_tx(bar, bytes);
+                    bulk_copy_g2s(smem_u32(ring + (size_t)slot * (CHUNK_PAIRS * PE)), src, bytes, bar);
+                    // advance the cursor: chunk -> row -> phase -> patch
+                    const int nh = cur_ph == 0 ? ring_nh(NPR1) : ring_nh(NPR2 > 0 ? NPR2 : 1);
+                    const int nq = cur_ph == 0 ? NQ : NQ2;
+                    if (++cur_h == nh) {
+                        cur_h = 0;
+                        if (++cur_r == nq) {
+                            cur_r = 0;
+                            if (++cur_ph == (NQ2 > 0 ? 2 : 1)) {
+                                cur_ph = 0;
+                                ++cur_i;
+                            }
+                        }
+                    }
+                };
+                if constexpr (RING > 0) {
+                    if (t == 0) {
+                        for (int k = 0; k < RING; ++k)
+                            mbar_init(rs.mbar + 8 * k, 1);
+                        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                    }
+                    named_sync(8, PE);
+                    if (t == 0)
+                        for (int k = 0; k < RING; ++k)
+                            issue(k);
+                }
+                else {
                     const double2 * gpi = args.G1 + (size_t)cta * g_patch1 + e;
 #pragma unroll
                     for (int m = 0; m < NPR1; ++m) {
@@ -806,19 +1012,29 @@ namespace cb200
                 }
                 for (int i = 0; i < n_iter; ++i) {
                     const int p = cta + i * stride;
-                    double * b = bufs + (i % 3) * BUF + e;
+                    double * b = bufs + (i % NBUF) * BUF + e;
                     // first phase of the next patch of this CTA (at the very end this one again: a harmless reload)
                     const int pn = (i + 1 < n_iter) ? p + stride : p;
                     if (NF > 1)
                         cluster_sync_all();
                     const double2 * gp1 = args.G1 + (size_t)p * g_patch1 + e;
                     const double2 * gp1_next = args.G1 + (size_t)pn * g_patch1 + e;
-                    named_sync(FULL + i % 3, 256);
+                    named_sync(FULL + i % NBUF, 256);
                     double out[NB2];
 #pragma unroll
                     for (int k = 0; k < NB2; ++k)
                         out[k] = 0.0;
-                    if constexpr (NQ2 > 0) {
+                    if constexpr (RING > 0) {
+                        // the ring leaves room in the register file: U stays in registers for all rows of both phases
+                        double U[NB2];
+#pragma unroll
+                        for (int k = 0; k < NB2; ++k)
+                            U[k] = b[k * PE];
+                        contract_phase_ring<NB, NQ, STIFF, PE, RING, CHUNK_PAIRS>(tab, U, rs, e, out, 1.0, args.zero, t == 0, issue);
+                        if constexpr (NQ2 > 0)
+                            contract_phase_ring<NB, NQ2, false, PE, RING, CHUNK_PAIRS>(tab2, U, rs, e, out, args.msc, args.zero, t == 0, issue);
+                    }
+                    else if constexpr (NQ2 > 0) {
                         const double2 * gp2 = args.G2 + (size_t)p * g_patch2 + e;
                         // loads issued while working on field f fetch data of field f (phase 2) or of the next unit (phase 1)
                         const bool shared_read = NF > 1; // another CTA reads the same block at about the same time
@@ -833,7 +1049,7 @@ namespace cb200
                     int gint[NI > 0 ? NI : 1]; // global DOFs of this element's interior nodes (-1: padding slot)
 #pragma unroll
                     for (int m = 0; m < NI; ++m)
-                        gint[m] = gints[(i % 3) * (NI * PE) + m * PE + e];
+                        gint[m] = gints[(i % NBUF) * (NI * PE) + m * PE + e];
 #pragma unroll
                     for (int k = 0; k < NB2; ++k) {
                         const int ki = k % NB, kj = k / NB;
@@ -851,7 +1067,7 @@ namespace cb200
                         else
                             b[k * PE] = out[k];
                     }
-                    named_arrive(READY + i % 3, 256);
+                    named_arrive(READY + i % NBUF, 256);
                 }
             }
         }
@@ -1318,19 +1534,23 @@ namespace cb200
                 }
         }
 
-        template <int NB, int NQ, bool STIFF, int NQ2>
+        template <int NB, int NQ, bool STIFF, int NQ2, int RING = 0>
         void launch_ws(const VolumeOp & op, const VolumeOp * op2, const PlanDev & pd, const Plan & plan, const WsArgs & args, cudaStream_t s)
         {
             CB_REQUIRE(plan.PE == 128, "warp-specialised kernel: patches must hold 128 elements");
             constexpr int NI = (NB > 2 ? NB - 2 : 0) * (NB > 2 ? NB - 2 : 0);
-            const size_t smem = sizeof(double) * 3 * (size_t)NB * NB * 128 + sizeof(int) * 3 * (size_t)NI * 128;
+            constexpr int NPRa = TpeCfg<NB, NQ, STIFF>::KR / 2, NPRb = NQ2 > 0 ? TpeCfg<NB, (NQ2 > 0 ? NQ2 : 1), false>::KR / 2 : 0;
+            constexpr int CHUNK_PAIRS = ring_cp(NPRa) > (NQ2 > 0 ? ring_cp(NPRb) : 0) ? ring_cp(NPRa) : ring_cp(NPRb);
+            constexpr int NBUF = RING > 2 ? 2 : 3; // as in the kernel
+            const size_t smem = sizeof(double) * NBUF * (size_t)NB * NB * 128 + sizeof(int) * NBUF * (size_t)NI * 128 +
+                                (size_t)RING * CHUNK_PAIRS * 128 * sizeof(double2) + (size_t)RING * 8 + 16;
             Tables<NB, NQ, STIFF> tab;
             fill_tables(tab, op);
             typename Phase2<NB, NQ2>::type tab2;
             std::memset(&tab2, 0, sizeof(tab2));
             if constexpr (NQ2 > 0)
                 fill_tables(tab2, *op2);
-            auto kern = volume_action_ws<NB, NQ, STIFF, NQ2>;
+            auto kern = volume_action_ws<NB, NQ, STIFF, NQ2, RING>;
             static int grid = 0;
             if (!grid) {
                 CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)49152)));
@@ -1436,9 +1656,15 @@ namespace cb200
         using FusedFn = void (*)(const VolumeOp &, const VolumeOp *, const PlanDev &, const Plan &, const WsArgs &, cudaStream_t);
         FusedFn find_fused_instance(int nb, int nqs, int nqm)
         {
+            static const int ring = env_int("CUDDH_B200_RING", 5);
 #define CB_CASE(NB_, NQS_, NQM_)                                                                                       \
     if (nb == NB_ && nqs == NQS_ && nqm == NQM_)                                                                       \
         return &launch_ws<NB_, NQS_, true, NQM_>;
+            // shared-memory metric ring for the register-bound n_basis 5 instance
+            if (nb == 5 && nqs == 6 && nqm == 9 && ring == 2)
+                return &launch_ws<5, 6, true, 9, 2>;
+            if (nb == 5 && nqs == 6 && nqm == 9 && ring == 5)
+                return &launch_ws<5, 6, true, 9, 5>;
             // default stiffness rule nq = nb + 1 with the weighted-mass rule nq = 1 + 3nb/2 + 1 (examples/Helmholtz.hpp)
             CB_CASE(2, 3, 5) CB_CASE(3, 4, 6) CB_CASE(4, 5, 8) CB_CASE(5, 6, 9)
 #undef CB_CASE
