@@ -1601,7 +1601,7 @@ namespace cb200
             CB_LAUNCHED();
         }
 
-        template <int NB, int NQ, bool STIFF>
+        template <int NB, int NQ, bool STIFF, int RING = 0>
         void launch_volume_ws(VolumeOp & op, const PlanDev & pd, const Plan & plan, double c, int accumulate, const double * x,
                               double * y, cudaStream_t s)
         {
@@ -1616,7 +1616,7 @@ namespace cb200
             a.accumulate = accumulate;
             a.n_patches = (int)plan.n_patches;
             a.n_fields = 1;
-            launch_ws<NB, NQ, STIFF, 0>(op, nullptr, pd, plan, a, s);
+            launch_ws<NB, NQ, STIFF, 0, RING>(op, nullptr, pd, plan, a, s);
         }
 
         using LaunchFn = void (*)(VolumeOp &, const PlanDev &, const Plan &, double, int, const double *, double *, cudaStream_t);
@@ -1628,6 +1628,16 @@ namespace cb200
 #define CB_CASE(NB_, NQ_)                                                                                              \
     if (nb == NB_ && nq == NQ_)                                                                                        \
         return &launch_volume_ws<NB_, NQ_, STIFF>;
+            // n_basis 5: metric data through the shared-memory ring (see contract_phase_ring)
+            static const int ring = env_int("CUDDH_B200_RING1", 2);
+            if constexpr (STIFF) {
+                if (ring == 2 && nb == 5 && nq == 6)
+                    return &launch_volume_ws<5, 6, true, 2>;
+            }
+            else {
+                if (ring == 2 && nb == 5 && nq == 9)
+                    return &launch_volume_ws<5, 9, false, 2>;
+            }
             CB_CASE(2, 3) CB_CASE(3, 4) CB_CASE(4, 5) CB_CASE(5, 6)
             CB_CASE(3, 5) CB_CASE(4, 6) CB_CASE(5, 7)
             if constexpr (!STIFF) {
