@@ -1629,14 +1629,18 @@ namespace cb200
     if (nb == NB_ && nq == NQ_)                                                                                        \
         return &launch_volume_ws<NB_, NQ_, STIFF>;
             // n_basis 5: metric data through the shared-memory ring (see contract_phase_ring)
-            static const int ring = env_int("CUDDH_B200_RING1", 2);
+            static const int ring = env_int("CUDDH_B200_RING1", 5);
             if constexpr (STIFF) {
                 if (ring == 2 && nb == 5 && nq == 6)
                     return &launch_volume_ws<5, 6, true, 2>;
+                if (ring == 5 && nb == 5 && nq == 6)
+                    return &launch_volume_ws<5, 6, true, 5>;
             }
             else {
                 if (ring == 2 && nb == 5 && nq == 9)
                     return &launch_volume_ws<5, 9, false, 2>;
+                if (ring == 5 && nb == 5 && nq == 9)
+                    return &launch_volume_ws<5, 9, false, 5>;
             }
             CB_CASE(2, 3) CB_CASE(3, 4) CB_CASE(4, 5) CB_CASE(5, 6)
             CB_CASE(3, 5) CB_CASE(4, 6) CB_CASE(5, 7)
