@@ -1635,12 +1635,22 @@ namespace cb200
                     return &launch_volume_ws<5, 6, true, 2>;
                 if (ring == 5 && nb == 5 && nq == 6)
                     return &launch_volume_ws<5, 6, true, 5>;
+                static const int ring4 = env_int("CUDDH_B200_RING4", 5);
+                if (ring4 == 2 && nb == 4 && nq == 5)
+                    return &launch_volume_ws<4, 5, true, 2>;
+                if (ring4 == 5 && nb == 4 && nq == 5)
+                    return &launch_volume_ws<4, 5, true, 5>;
             }
             else {
                 if (ring == 2 && nb == 5 && nq == 9)
                     return &launch_volume_ws<5, 9, false, 2>;
                 if (ring == 5 && nb == 5 && nq == 9)
                     return &launch_volume_ws<5, 9, false, 5>;
+                static const int ring4 = env_int("CUDDH_B200_RING4", 5);
+                if (ring4 == 2 && nb == 4 && nq == 8)
+                    return &launch_volume_ws<4, 8, false, 2>;
+                if (ring4 == 5 && nb == 4 && nq == 8)
+                    return &launch_volume_ws<4, 8, false, 5>;
             }
             CB_CASE(2, 3) CB_CASE(3, 4) CB_CASE(4, 5) CB_CASE(5, 6)
             CB_CASE(3, 5) CB_CASE(4, 6) CB_CASE(5, 7)
@@ -1679,6 +1689,11 @@ namespace cb200
                 return &launch_ws<5, 6, true, 9, 2>;
             if (nb == 5 && nqs == 6 && nqm == 9 && ring == 5)
                 return &launch_ws<5, 6, true, 9, 5>;
+            static const int ring4 = env_int("CUDDH_B200_RING4", 5);
+            if (nb == 4 && nqs == 5 && nqm == 8 && ring4 == 2)
+                return &launch_ws<4, 5, true, 8, 2>;
+            if (nb == 4 && nqs == 5 && nqm == 8 && ring4 == 5)
+                return &launch_ws<4, 5, true, 8, 5>;
             // default stiffness rule nq = nb + 1 with the weighted-mass rule nq = 1 + 3nb/2 + 1 (examples/Helmholtz.hpp)
             CB_CASE(2, 3, 5) CB_CASE(3, 4, 6) CB_CASE(4, 5, 8) CB_CASE(5, 6, 9)
 #undef CB_CASE
