@@ -659,35 +659,10 @@ namespace cb200
             constexpr int NKI = Cfg::NKI, KR = Cfg::KR, NPR = KR / 2;
             constexpr int NH = ring_nh(NPR), CP = ring_cp(NPR);
             static_assert(CP <= CHUNK_PAIRS && NH <= RING, "ring geometry");
-#pragma unroll 1
-            for (int tx = 0; tx < NQ; ++tx) {
+            // rows per barrier group: a row with a single chunk (the short mass rows) shares its barrier with the next row
+            constexpr int RG = NH == 1 && 2 <= RING ? 2 : 1;
+            auto row = [&](const int tx, const double (&g)[KR]) {
                 const int z = tx * zero; // 0 at run time; keeps the ty-indexed table loads inside the rolled loop
-                double g[KR];
-                int freed[NH];
-#pragma unroll
-                for (int h = 0; h < NH; ++h) {
-                    mbar_wait(rs.mbar + 8 * rs.slot, (unsigned)rs.parity);
-                    const double2 * src = rs.ring + (size_t)rs.slot * (CHUNK_PAIRS * PE) + e;
-#pragma unroll
-                    for (int m = 0; m < CP; ++m)
-                        if (h * CP + m < NPR) {
-                            const double2 v = src[m * PE];
-                            g[2 * (h * CP + m)] = v.x;
-                            g[2 * (h * CP + m) + 1] = v.y;
-                        }
-                    freed[h] = rs.slot;
-                    if (++rs.slot == RING) {
-                        rs.slot = 0;
-                        rs.parity ^= 1;
-                    }
-                }
-                named_sync(8, PE); // every thread of the warpgroup holds its pairs in registers: the slots are free
-                if (leader) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#pragma unroll
-                    for (int h = 0; h < NH; ++h)
-                        issue(freed[h]);
-                }
                 double pu[NB], du[STIFF ? NB : 1];
 #pragma unroll
                 for (int j = 0; j < NB; ++j) {
@@ -748,6 +723,46 @@ namespace cb200
                         else
                             out[ii + NB * q] = fma(tab.Prow[tx][ii], a0[q], out[ii + NB * q]);
                     }
+            };
+#pragma unroll 1
+            for (int tx0 = 0; tx0 < NQ; tx0 += RG) {
+                double g[RG][KR];
+                int freed[RG * NH];
+#pragma unroll
+                for (int rr = 0; rr < RG; ++rr)
+                    if (rr == 0 || tx0 + rr < NQ) {
+#pragma unroll
+                        for (int h = 0; h < NH; ++h) {
+                            mbar_wait(rs.mbar + 8 * rs.slot, (unsigned)rs.parity);
+                            const double2 * src = rs.ring + (size_t)rs.slot * (CHUNK_PAIRS * PE) + e;
+#pragma unroll
+                            for (int m = 0; m < CP; ++m)
+                                if (h * CP + m < NPR) {
+                                    const double2 v = src[m * PE];
+                                    g[rr][2 * (h * CP + m)] = v.x;
+                                    g[rr][2 * (h * CP + m) + 1] = v.y;
+                                }
+                            freed[rr * NH + h] = rs.slot;
+                            if (++rs.slot == RING) {
+                                rs.slot = 0;
+                                rs.parity ^= 1;
+                            }
+                        }
+                    }
+                named_sync(8, PE); // every thread of the warpgroup holds its pairs in registers: the slots are free
+                if (leader) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+                    for (int rr = 0; rr < RG; ++rr)
+                        if (rr == 0 || tx0 + rr < NQ) {
+#pragma unroll
+                            for (int h = 0; h < NH; ++h)
+                                issue(freed[rr * NH + h]);
+                        }
+                }
+                row(tx0, g[0]);
+                if (RG > 1 && tx0 + 1 < NQ)
+                    row(tx0 + 1, g[RG - 1]);
             }
         }
 

@@ -62,7 +62,7 @@ with open(os.path.join(out, "%s_volume_kernel_ncu.txt" % tag), "w") as f:
         def gb(k):
             v, un = float(r[idx[k]].replace(",", "")), u[idx[k]]
             return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[un]
-        m = re.search(r"volume_action_(?:kernel|ws)<(?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(bool\))?(\d)(?:, (?:\(int\))?(\d+))?>", r[idx["Kernel Name"]])
+        m = re.search(r"volume_action_(?:kernel|ws)<(?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(bool\))?(\d)(?:, (?:\(int\))?(\d+))?(?:, (?:\(int\))?\d+)?>", r[idx["Kernel Name"]])
         if m:
             if m.group(4) and m.group(4) != "0":
                 key = "helmholtz_%s_%s_%s_nx1024" % (m.group(1), m.group(2), m.group(4))
