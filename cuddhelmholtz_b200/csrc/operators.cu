@@ -659,8 +659,9 @@ namespace cb200
             constexpr int NKI = Cfg::NKI, KR = Cfg::KR, NPR = KR / 2;
             constexpr int NH = ring_nh(NPR), CP = ring_cp(NPR);
             static_assert(CP <= CHUNK_PAIRS && NH <= RING, "ring geometry");
-            // rows per barrier group: a row with a single chunk (the short mass rows) shares its barrier with the next row
-            constexpr int RG = NH == 1 && 2 <= RING ? 2 : 1;
+            // rows per barrier group. Letting two single-chunk rows (the short mass rows) share one barrier was measured: fused
+            // n_basis 5 0.734 -> 0.786 ms (20 more live registers), n_basis 4 0.435 -> 0.427 ms; not worth it, so 1.
+            constexpr int RG = 1;
             auto row = [&](const int tx, const double (&g)[KR]) {
                 const int z = tx * zero; // 0 at run time; keeps the ty-indexed table loads inside the rolled loop
                 double pu[NB], du[STIFF ? NB : 1];
@@ -808,7 +809,7 @@ namespace cb200
             constexpr int FULL = 1, READY = 4, HELPER = 7; // named barrier ids (0 is __syncthreads)
             constexpr int NG = (NB2 + 3) / 4;                // groups of four nodes in the global index map
             constexpr int NI = (NB > 2 ? NB - 2 : 0) * (NB > 2 ? NB - 2 : 0); // element-interior nodes
-            constexpr bool HEAVY = STIFF && NB >= 5 && NQ2 > 0;
+            constexpr bool HEAVY = STIFF && NB >= 5 && NQ2 > 0 && RING == 0; // register-path fused instance only
 
             // shared-memory metric ring (RING > 0): chunk = CHUNK_PAIRS x PE 16-byte pairs
             constexpr int CP1 = ring_cp(NPR1), CP2 = NQ2 > 0 ? ring_cp(NPR2) : 0;
@@ -893,50 +894,89 @@ namespace cb200
                         }
                     }
                 };
+                // Assembly lists of the patch to be assembled NEXT, loaded one step ahead (two-buffer instances): the loads are in
+                // flight while the helper waits for its gather copies, so the assembly itself starts from registers.
+                constexpr int PF = NBUF < 3 ? 8 : 0; // list entries per thread held ahead (covers 1024 listed DOFs per patch)
+                uint2 prec[PF > 0 ? PF : 1];
+                int ptgt[PF > 0 ? PF : 1];
+                int p_npdof = 0, p_nint = 0;
+                auto prefetch_lists = [&](const int i) {
+                    if constexpr (PF > 0) {
+                        const int p = cta + i * stride;
+                        const int pdof_begin = __ldg(&plan.hdr[p].pdof_begin);
+                        p_npdof = __ldg(&plan.hdr[p].n_pdof);
+                        p_nint = __ldg(&plan.hdr[p].n_int);
+                        const uint2 * recp = plan.cent4 + pdof_begin;
+                        const int * tgtp = plan.target + pdof_begin;
+#pragma unroll
+                        for (int a = 0; a < PF; ++a) {
+                            const int d = t + a * PE;
+                            prec[a] = (d < p_npdof) ? __ldg(recp + d) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+                            ptgt[a] = (d < p_npdof) ? __ldg(tgtp + d) : 0;
+                        }
+                    }
+                };
                 auto assemble = [&](const int i) {
                     const int p = cta + i * stride;
                     double * y = args.y + f * args.y_stride;
                     double * partial = args.partial + f * args.partial_stride;
                     const double c = args.c[f];
-                    const PatchHdr hdr = plan.hdr[p];
                     const double * su = bufs + (i % NBUF) * BUF;
-                    const uint2 * recp = plan.cent4 + hdr.pdof_begin;
-                    const int * tgtp = plan.target + hdr.pdof_begin;
+                    // one listed DOF: entries added left to right = the plan's CSR order (adding to 0.0 first is exact)
+                    auto one = [&](const int d, const uint2 rec, const int tgt, const int n_int, const int n_pdof) {
+                        const unsigned c0 = rec.x & 0xFFFFu, c1 = rec.x >> 16, c2 = rec.y & 0xFFFFu, c3 = rec.y >> 16;
+                        double sum = c0 != 0xFFFFu ? su[c0] : 0.0;
+                        if (c1 != 0xFFFFu)
+                            sum += su[c1];
+                        if (c2 != 0xFFFFu)
+                            sum += su[c2];
+                        if (c3 < 0xFFFEu)
+                            sum += su[c3];
+                        else if (c3 == 0xFFFEu) { // more than four contributions (high-valence vertex): rest of the CSR row
+                            const PatchHdr hdr = plan.hdr[p];
+                            const uint16_t * cp = plan.cptr + hdr.cptr_begin;
+                            const uint16_t * ce = plan.cent + (size_t)hdr.elem_begin * NB2;
+                            for (int k = __ldg(cp + d) + 3, e = __ldg(cp + d + 1); k < e; ++k)
+                                sum += su[__ldg(ce + k)];
+                        }
+                        if (d < n_int) {
+                            const double v = c * sum;
+                            y[tgt] = accumulate ? (y[tgt] + v) : v;
+                        }
+                        else if (d < n_pdof)
+                            partial[tgt] = sum;
+                    };
+                    int n_pdof, n_int, first = t;
+                    if constexpr (PF > 0) {
+                        n_pdof = p_npdof;
+                        n_int = p_nint;
+#pragma unroll
+                        for (int a = 0; a < PF; ++a)
+                            one(t + a * PE, prec[a], ptgt[a], n_int, n_pdof);
+                        first = t + PF * PE;
+                        if (first >= n_pdof)
+                            return;
+                    }
+                    else {
+                        n_pdof = __ldg(&plan.hdr[p].n_pdof);
+                        n_int = __ldg(&plan.hdr[p].n_int);
+                    }
+                    const int pdof_begin = __ldg(&plan.hdr[p].pdof_begin);
+                    const uint2 * recp = plan.cent4 + pdof_begin;
+                    const int * tgtp = plan.target + pdof_begin;
                     constexpr int CU = 4; // DOFs in flight per thread: record and target loads of a batch are independent
-                    for (int base = t; base < hdr.n_pdof; base += CU * PE) {
+                    for (int base = first; base < n_pdof; base += CU * PE) {
                         uint2 rec[CU];
                         int tgt[CU];
 #pragma unroll
                         for (int a = 0; a < CU; ++a) {
                             const int d = base + a * PE;
-                            rec[a] = (d < hdr.n_pdof) ? __ldg(recp + d) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-                            tgt[a] = (d < hdr.n_pdof) ? __ldg(tgtp + d) : 0;
+                            rec[a] = (d < n_pdof) ? __ldg(recp + d) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+                            tgt[a] = (d < n_pdof) ? __ldg(tgtp + d) : 0;
                         }
 #pragma unroll
-                        for (int a = 0; a < CU; ++a) {
-                            const int d = base + a * PE;
-                            const unsigned c0 = rec[a].x & 0xFFFFu, c1 = rec[a].x >> 16, c2 = rec[a].y & 0xFFFFu, c3 = rec[a].y >> 16;
-                            // entries added left to right = the plan's CSR order (adding to 0.0 first is exact)
-                            double sum = c0 != 0xFFFFu ? su[c0] : 0.0;
-                            if (c1 != 0xFFFFu)
-                                sum += su[c1];
-                            if (c2 != 0xFFFFu)
-                                sum += su[c2];
-                            if (c3 < 0xFFFEu)
-                                sum += su[c3];
-                            else if (c3 == 0xFFFEu) { // more than four contributions (high-valence vertex): rest of the CSR row
-                                const uint16_t * cp = plan.cptr + hdr.cptr_begin;
-                                const uint16_t * ce = plan.cent + (size_t)hdr.elem_begin * NB2;
-                                for (int k = __ldg(cp + d) + 3, e = __ldg(cp + d + 1); k < e; ++k)
-                                    sum += su[__ldg(ce + k)];
-                            }
-                            if (d < hdr.n_int) {
-                                const double v = c * sum;
-                                y[tgt[a]] = accumulate ? (y[tgt[a]] + v) : v;
-                            }
-                            else if (d < hdr.n_pdof)
-                                partial[tgt[a]] = sum;
-                        }
+                        for (int a = 0; a < CU; ++a)
+                            one(base + a * PE, rec[a], tgt[a], n_int, n_pdof);
                     }
                 };
 
@@ -957,6 +997,7 @@ namespace cb200
                         named_sync(HELPER, 128);
                         issue_gather(i + 1);
                     }
+                    prefetch_lists(i); // for assemble(i) in the next iteration; overlaps the wait for the gather copies
                     cp_async_wait_all();
                     named_sync(HELPER, 128); // every helper thread is done reading buffer i-1 and its copies for i+1 landed
                     if (i + 1 < n_iter)
