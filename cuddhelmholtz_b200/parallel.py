@@ -107,10 +107,26 @@ class GpuSlabHelmholtz:
     def prolong(self, which, buf, y, off):
         self.fs[which].prolong(buf, y[off:off + self.ndof])
 
+    def interface_rows(self, which):
+        """slab-local DOF indices of the bottom / top interface node row"""
+        return self.fs[which].global_indices()
+
     def apply(self, x, y):
         """y = A x on [u; v] with x consistent on the interface rows; y comes out consistent as well."""
         self.op.action(x, y)
         self.exchange(y)
+
+    def solve(self, b, x, m=20, maxit=1000, tol=1e-6, group=None):
+        """distributed GMRES(m) on this slab partition (one allreduce per Arnoldi step), see slab_gmres"""
+        mask = owned_mask(self, self.rank, self.world, (0, self.ndof), 2 * self.ndof, device="cuda")
+        y = torch.empty_like(b)
+
+        def A(v):
+            v = v.contiguous()
+            self.apply(v, y)
+            return y.clone()
+
+        return slab_gmres(A, x, b, mask, m, maxit, tol, group=group, world=self.world)
 
 
 def subdomain_range(n_domains, rank, world):
@@ -171,3 +187,99 @@ class _RawVec:
 
 def _as_tensor(ptr, n, dtype):
     return torch.as_tensor(_RawVec(ptr, n, "<f4" if dtype == torch.float32 else "<f8"), device="cuda")
+
+
+# ---- distributed FP64 GMRES for the slab-partitioned operator (path A) ----------------------------------
+def owned_mask(local, rank, world, offsets, n, device="cpu"):
+    """1.0 on the DOFs this rank owns, 0.0 on the copies it only mirrors: a slab-interface node row is held by both
+    neighbours, the lower rank owns it, so rank > 0 drops its bottom row from every inner product.
+    `local.interface_rows(which)` gives the slab-local DOF indices of that row."""
+    w = torch.ones(n, dtype=torch.float64, device=device)
+    if world > 1 and rank > 0:
+        idx = torch.as_tensor(np.asarray(local.interface_rows("bottom")), dtype=torch.long, device=device)
+        for off in offsets:
+            w[off + idx] = 0.0
+    return w
+
+
+def slab_gmres(apply, x, b, mask, m, maxit, tol=1e-6, group=None, world=1):
+    """Restarted GMRES(m) with the reference's control flow (source/gmres.cpp:91-235: restart counter from 1, inner break
+    on |eta_{k+1}| < tol*||b||, true residual after every restart) on vectors that are partitioned into slabs with
+    mirrored interface rows. `apply(v) -> A v` must return a vector that is consistent on the mirrored rows (operator +
+    SlabExchange). Inner products count every DOF once (`mask`) and cost ONE allreduce per Arnoldi step: classical
+    Gram-Schmidt, [V_k^T w ; w.w] reduced together, ||w - V_k h||^2 = w.w - h.h (recomputed explicitly, one more
+    allreduce, only when that difference cancels badly). Every rank runs the same small Hessenberg / Givens update.
+    Returns dict(success, num_iter, num_matvec, res_norm, allreduces); x is updated in place."""
+    n = x.numel()
+    out = dict(success=False, num_iter=0, num_matvec=0, res_norm=[], allreduces=0)
+
+    def reduce_(t):
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            out["allreduces"] += 1
+        return t
+
+    def dot(a, c):
+        return float(reduce_(torch.dot(mask * a, c).reshape(1))[0])
+
+    bnrm = np.sqrt(dot(b, b))
+    V = torch.zeros(m + 1, n, dtype=x.dtype, device=x.device)
+    H = np.zeros((m + 1, m))
+    cs, sn = np.zeros(m), np.zeros(m)
+    r = b - apply(x)
+    out["num_matvec"] += 1
+    r_nrm = np.sqrt(dot(r, r))
+    out["res_norm"].append(r_nrm)
+    if r_nrm < tol * bnrm:
+        out["success"] = True
+        return out
+    it = 1
+    while it < maxit:
+        V[0] = r / r_nrm
+        eta = np.zeros(m + 1)
+        eta[0] = r_nrm
+        k1 = 0
+        for k in range(m):
+            k1 = k + 1
+            w = apply(V[k])
+            out["num_matvec"] += 1
+            mw = mask * w
+            red = torch.empty(k1 + 1, dtype=x.dtype, device=x.device)
+            red[:k1] = V[:k1] @ mw
+            red[k1] = torch.dot(mw, w)
+            red = reduce_(red).cpu().numpy()
+            h, ww = red[:k1], red[k1]
+            w = w - torch.as_tensor(h, dtype=x.dtype, device=x.device) @ V[:k1]
+            nrm2 = ww - float(np.dot(h, h))
+            if nrm2 < 1e-3 * ww:  # cancellation: take the norm of the orthogonalised vector itself
+                nrm2 = dot(w, w)
+            hk1 = np.sqrt(max(nrm2, 0.0))
+            H[:k1, k] = h
+            H[k1, k] = hk1
+            if hk1 == 0.0:
+                break
+            V[k1] = w / hk1
+            for j in range(k):  # Givens rotations, source/gmres.cpp:7-23
+                t = cs[j] * H[j, k] + sn[j] * H[j + 1, k]
+                H[j + 1, k] = -sn[j] * H[j, k] + cs[j] * H[j + 1, k]
+                H[j, k] = t
+            d = np.hypot(H[k, k], H[k1, k])
+            cs[k], sn[k] = H[k, k] / d, H[k1, k] / d
+            H[k, k] = cs[k] * H[k, k] + sn[k] * H[k1, k]
+            H[k1, k] = 0.0
+            eta[k1] = -sn[k] * eta[k]
+            eta[k] = cs[k] * eta[k]
+            if abs(eta[k1]) < tol * bnrm:
+                break
+        yk = np.linalg.solve(np.triu(H[:k1, :k1]), eta[:k1]) if k1 > 0 else np.zeros(0)
+        x += torch.as_tensor(yk, dtype=x.dtype, device=x.device) @ V[:k1]
+        r = b - apply(x)
+        out["num_matvec"] += 1
+        r_nrm = np.sqrt(dot(r, r))
+        out["res_norm"].append(r_nrm)
+        if r_nrm < tol * bnrm:
+            out["success"] = True
+            break
+        it += 1
+    out["num_iter"] = it
+    return out

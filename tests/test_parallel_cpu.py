@@ -38,6 +38,9 @@ class OracleSlab:
     def prolong(self, which, buf, y, off):
         y[off:off + self.ndof][torch.as_tensor(self.fs[which].proj, dtype=torch.long)] += buf
 
+    def interface_rows(self, which):
+        return self.fs[which].proj
+
     def apply(self, x):
         y = torch.from_numpy(self.op.action(x.numpy()))
         self.exchange(y)
@@ -99,3 +102,64 @@ def test_slab_exchange_two_ranks_gloo(nb):
         assert err < 1e-12, (rank, err)
         assert same
         assert nbytes == 8 * 2 * (nx * (nb - 1) + 1)
+
+
+def _gmres_worker(rank, world, port, nx, ny_local, nb, omega, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cuddhelmholtz_b200.parallel import owned_mask, slab_gmres
+        from oracle import ops as O
+        from oracle import setup_np as S
+        slab = OracleSlab(nx, ny_local, nb, omega, coef, rank, world)
+        om = S.uniform_rect(nx, -1.0, 1.0, ny_local * world, -1.0, -1.0 + 2.0 * world)
+        gfem = O.H1(om, nb)
+        gfs = O.FaceSpace(gfem, om.boundary_edges)
+        c = coef(gfem.xy[:, 0], gfem.xy[:, 1])
+        G = O.Helmholtz(omega, c * c, c[gfs.proj], gfem, gfs)
+        key = lambda xy: [(int(round(a * 1e8)), int(round(b * 1e8))) for a, b in xy]
+        gmap = {k: i for i, k in enumerate(key(gfem.xy))}
+        loc2glob = np.array([gmap[k] for k in key(slab.fem.xy)])
+        ng, nl = gfem.ndof, slab.ndof
+        bg = np.random.default_rng(11).uniform(-1, 1, 2 * ng)
+        # single-process solve of the undivided problem with the restatement of the reference's GMRES (MGS)
+        xg = np.zeros(2 * ng)
+        ref = O.gmres(2 * ng, xg, G.action, bg, 60, 100, 1e-9)
+        # the same problem on two slabs
+        bl = torch.from_numpy(np.concatenate([bg[loc2glob], bg[ng + loc2glob]]))
+        xl = torch.zeros(2 * nl, dtype=torch.float64)
+        mask = owned_mask(slab, rank, world, (0, nl), 2 * nl)
+        n_owned = torch.tensor([float(mask.sum())])
+        dist.all_reduce(n_owned)
+        res = slab_gmres(lambda v: slab.apply(v.contiguous()), xl, bl, mask, 60, 100, 1e-9, world=world)
+        want = np.concatenate([xg[loc2glob], xg[ng + loc2glob]])
+        err = float(np.linalg.norm(xl.numpy() - want) / np.linalg.norm(want))
+        q.put((rank, err, ref["success"], ref["num_iter"], res["success"], res["num_iter"], res["num_matvec"], res["allreduces"],
+               int(n_owned.item()), 2 * ng))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_gmres_two_ranks_gloo():
+    """distributed GMRES on two slabs (gloo) against the single-process restatement of the reference's GMRES on the
+    undivided mesh: every DOF counted once, same restart count (+-1), same solution."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29850 + (os.getpid() % 100)
+    nx, ny_local, world, nb = 3, 2, 2, 3
+    procs = [ctx.Process(target=_gmres_worker, args=(r, world, port, nx, ny_local, nb, 3.0, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=400) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, ref_ok, ref_it, ok, it, matvec, nred, n_owned, n_glob in res:
+        assert n_owned == n_glob, (n_owned, n_glob)
+        assert ref_ok and ok, (ref_ok, ok, ref_it, it)
+        assert abs(it - ref_it) <= 1, (it, ref_it)
+        assert err < 1e-6, err
+        # one allreduce per Arnoldi step (+ the norms of b, r0 and one residual per restart; a few cancellation re-norms allowed)
+        assert nred <= matvec + it + 8, (nred, matvec, it)
