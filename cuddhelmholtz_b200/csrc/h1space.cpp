@@ -523,7 +523,8 @@ namespace cb200
         d_hdr.upload(hdr);
         d_gid.upload(gid);
         d_slot.upload(slot);
-        d_L.upload(L);
+        if (!node_major) // the thread-per-element kernels gather through Ig; L only serves the host-side plan build there
+            d_L.upload(L);
         cptr.resize(cptr.size() + 8, 0); // slack: the last patch's offsets are copied in 32-bit words
         d_cptr.upload(cptr);
         d_cent.upload(cent);

@@ -200,6 +200,30 @@ def test_helmholtz_composite(kind, nb):
         A.action(1.0, dev(x), y)
 
 
+def test_slab_gmres_single_rank_matches_library_gmres():
+    """parallel.slab_gmres (the distributed GMRES of the slab partition, here on one rank) against the library's gmres on the
+    same operator: same restart / matvec counts, same solution (classical vs modified Gram-Schmidt: round-off only)."""
+    from cuddhelmholtz_b200.parallel import slab_gmres
+    om, pm, ofem, pfem = make("rect", 3)
+    n = ofem.ndof
+    a2 = dev(1.0 + 0.25 * np.cos(ofem.xy[:, 0]))
+    M = cb.MassMatrix(a2, pfem)  # SPD, converges in a few restarts
+    b = dev(vec(n, 21))
+    x_lib = torch.zeros(n, dtype=torch.float64, device="cuda")
+    out = cb.gmres(n, x_lib, M, b, 10, 200, 1e-10)
+    assert out.success
+    x = torch.zeros_like(x_lib)
+    y = torch.empty_like(x)
+
+    def A(v):
+        M.action(v.contiguous(), y)
+        return y.clone()
+
+    res = slab_gmres(A, x, b, torch.ones_like(x), 10, 200, 1e-10)
+    assert res["success"] and abs(res["num_iter"] - out.num_iter) <= 1 and abs(res["num_matvec"] - out.num_matvec) <= 11
+    assert rel(host(x), host(x_lib)) < 1e-8
+
+
 def test_linalg():
     # tests/linalg.cpp:7-259
     n = 1024 * 37 + 5
