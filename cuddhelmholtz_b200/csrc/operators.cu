@@ -659,12 +659,10 @@ namespace cb200
             constexpr int NKI = Cfg::NKI, KR = Cfg::KR, NPR = KR / 2;
             constexpr int NH = ring_nh(NPR), CP = ring_cp(NPR);
             static_assert(CP <= CHUNK_PAIRS && NH <= RING, "ring geometry");
-            // rows per barrier group. Letting two single-chunk rows (the short mass rows) share one barrier was measured: fused
-            // n_basis 5 0.734 -> 0.786 ms (20 more live registers), n_basis 4 0.435 -> 0.427 ms; not worth it, so 1.
+            // one barrier per row (two single-chunk mass rows sharing a barrier was measured: n_basis 5 fused 0.734 -> 0.786 ms)
             constexpr int RG = 1;
-            auto row = [&](const int tx, const double (&g)[KR]) {
-                const int z = tx * zero; // 0 at run time; keeps the ty-indexed table loads inside the rolled loop
-                double pu[NB], du[STIFF ? NB : 1];
+            // first-index contraction of a row: needs no metric data
+            auto row_first = [&](const int tx, double (&pu)[NB], double (&du)[STIFF ? NB : 1]) {
 #pragma unroll
                 for (int j = 0; j < NB; ++j) {
                     double s0 = 0.0, s1 = 0.0;
@@ -679,6 +677,9 @@ namespace cb200
                     if (STIFF)
                         du[j] = s1;
                 }
+            };
+            auto row_rest = [&](const int tx, const double (&g)[KR], const double (&pu)[NB], const double (&du)[STIFF ? NB : 1]) {
+                const int z = tx * zero; // 0 at run time; keeps the ty-indexed table loads inside the rolled loop
                 double a0[NB], a1[STIFF ? NB : 1];
 #pragma unroll
                 for (int q = 0; q < NB; ++q) {
@@ -750,6 +751,9 @@ namespace cb200
                             }
                         }
                     }
+                // the first-index contraction runs while the ring reads above are still in flight
+                double pu[NB], du[STIFF ? NB : 1];
+                row_first(tx0, pu, du);
                 named_sync(8, PE); // every thread of the warpgroup holds its pairs in registers: the slots are free
                 if (leader) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -761,9 +765,7 @@ namespace cb200
                                 issue(freed[rr * NH + h]);
                         }
                 }
-                row(tx0, g[0]);
-                if (RG > 1 && tx0 + 1 < NQ)
-                    row(tx0 + 1, g[RG - 1]);
+                row_rest(tx0, g[0], pu, du);
             }
         }
 
