@@ -514,3 +514,40 @@ def test_full_size_properties():
     # bitwise reproducibility at full size
     Sm.action(x, y2)
     assert torch.equal(y, y2)
+    del Sm, M, comb, acc
+
+    # the fused Helmholtz kernel (clusters of two CTAs, shared-memory metric ring) at the headline size: equal to the
+    # operator-by-operator composition through the stand-alone kernels, symmetric (examples/Helmholtz.hpp:55 flips the sign of
+    # the second block row for exactly that), bitwise reproducible
+    omega = 100.0
+    xy = fem.physical_coordinates()
+    c = 1.0 + 0.5 * np.sin(np.pi * xy[:, 0]) * np.cos(np.pi * xy[:, 1])
+    fs = cb.FaceSpace(fem, mesh.boundary_edges())
+    a2, af = dev(c * c), dev(c[fs.global_indices()])
+    A = cb.Helmholtz(omega, a2, af, fem, fs)
+    assert A.kernel_kind() == 2
+    X = torch.rand(2 * n, generator=g, dtype=torch.float64, device="cuda") - 0.5
+    Z = torch.rand(2 * n, generator=g, dtype=torch.float64, device="cuda") - 0.5
+    AX, AZ = torch.empty_like(X), torch.empty_like(X)
+    A.action(X, AX)
+    A.action(Z, AZ)
+    p, q = float(torch.dot(Z, AX)), float(torch.dot(X, AZ))
+    assert abs(p - q) < 1e-10 * max(abs(p), 1.0)
+    AX2 = torch.empty_like(X)
+    A.action(X, AX2)
+    assert torch.equal(AX, AX2)
+    S1, M1 = cb.StiffnessMatrix(fem), cb.MassMatrix(a2, fem)
+    W = torch.empty_like(X)
+    S1.action(X[:n], W[:n]); M1.action(-omega * omega, X[:n], W[:n])
+    S1.action(X[n:], W[n:]); M1.action(-omega * omega, X[n:], W[n:])
+    H1 = cb.FaceMassMatrix(af, fs)
+    fu, fv = torch.empty(fs.size(), dtype=torch.float64, device="cuda"), torch.empty(fs.size(), dtype=torch.float64, device="cuda")
+    fs.restrict(X[:n], fu); fs.restrict(X[n:], fv)
+    hu, hv = torch.zeros_like(fu), torch.zeros_like(fv)
+    H1.action(fu, hu); H1.action(fv, hv)
+    pu, pv = torch.zeros(n, dtype=torch.float64, device="cuda"), torch.zeros(n, dtype=torch.float64, device="cuda")
+    fs.prolong(hu, pu); fs.prolong(hv, pv)
+    W[:n] -= omega * pv
+    W[n:] += omega * pu
+    W[n:] *= -1.0
+    assert float((AX - W).norm() / W.norm()) < 1e-12
