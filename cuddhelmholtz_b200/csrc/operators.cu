@@ -1266,6 +1266,24 @@ namespace cb200
             y[gi] = accumulate ? (y[gi] + v) : v;
         }
 
+        // both block rows of the fused Helmholtz apply in one launch: blockIdx.y = field
+        __global__ void assemble_shared_fields_kernel(const int64_t n_shared, const int * __restrict__ sh_gid,
+                                                      const int * __restrict__ sh_ptr, const double * __restrict__ partial,
+                                                      const int64_t partial_stride, double * __restrict__ y, const int64_t y_stride,
+                                                      const double c0, const double c1)
+        {
+            const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+            if (s >= n_shared)
+                return;
+            const int f = blockIdx.y;
+            const double * pf = partial + f * partial_stride;
+            const int b = sh_ptr[s], e = sh_ptr[s + 1];
+            double sum = 0.0;
+            for (int k = b; k < e; ++k)
+                sum += pf[k];
+            y[f * y_stride + sh_gid[s]] = (f == 0 ? c0 : c1) * sum;
+        }
+
         // ------------------------------------------------------------------------------------------
         // setup kernels: metric data in plan ("lane-major") order.
         //   index(slot e of patch p, q = first quad index, k) =
@@ -1444,6 +1462,36 @@ namespace cb200
             }
             const int64_t yi = proj ? proj[d] : d;
             y[yi] = accumulate ? (y[yi] + sum) : sum;
+        }
+
+        // the two boundary terms of the Helmholtz composite in one launch: blockIdx.y = 0: y[0:n] += c H x[n:2n]; 1: y[n:2n] += c H x[0:n]
+        __global__ void facemass_pair_kernel(const int64_t fdof, const int NB, const int NQ, const double * __restrict__ P,
+                                             const double * __restrict__ a, const int * __restrict__ If,
+                                             const int * __restrict__ inc_ptr, const int * __restrict__ inc,
+                                             const int * __restrict__ proj, const double c, const int64_t n,
+                                             const double * __restrict__ x, double * __restrict__ y)
+        {
+            const int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+            if (d >= fdof)
+                return;
+            const double * xs = blockIdx.y == 0 ? x + n : x;
+            double * yd = blockIdx.y == 0 ? y : y + n;
+            double sum = 0.0;
+            for (int t = inc_ptr[d]; t < inc_ptr[d + 1]; ++t) {
+                const int fk = inc[t];
+                const int f = fk / NB, k = fk - f * NB;
+                const int * Ifa = If + (size_t)NB * f;
+                double Mu = 0.0;
+                for (int i = 0; i < NQ; ++i) {
+                    double pu = 0.0;
+                    for (int l = 0; l < NB; ++l)
+                        pu += P[i + NQ * l] * xs[proj[Ifa[l]]];
+                    pu *= a[i + (size_t)NQ * f];
+                    Mu += P[i + NQ * k] * pu;
+                }
+                sum += c * Mu;
+            }
+            yd[proj[d]] += sum;
         }
 
         __global__ void setup_facemass_kernel(const int64_t nf, const int NB, const int NQ, const double * __restrict__ wq,
@@ -1969,6 +2017,15 @@ namespace cb200
         CB_LAUNCHED();
     }
 
+    void FaceMassOp::apply_h1_pair(double c, const double * x, double * y, int64_t n, cudaStream_t s)
+    {
+        if (fs->fdof == 0)
+            return;
+        facemass_pair_kernel<<<dim3(blocks_for(fs->fdof, 128), 2), 128, 0, s>>>(fs->fdof, nb, nq, d_P.p, d_a.p, fs->d_I.p, fs->d_inc_ptr.p,
+                                                                                fs->d_inc.p, fs->d_proj.p, c, n, x, y);
+        CB_LAUNCHED();
+    }
+
     std::unique_ptr<DiagOp> make_diag_inv_facemass(FaceSpace * fs, const double * d_coef)
     {
         // reference source/FaceMassMatrix.cpp:226-270
@@ -2038,7 +2095,7 @@ namespace cb200
         double * Av = y + n;
         if (fused) {
             // one warp-specialised kernel walks (patch, field) units: S and M share the gather, the index lists and the
-            // assembly, the sign of the second block row is applied on write: 1 + 2 + 2 launches instead of 11 + 4 memsets
+            // assembly, the sign of the second block row is applied on write: 3 launches instead of 11 + 4 memsets
             Plan & plan = *S->plan;
             PlanDev pd{plan.d_hdr.p, plan.d_gid.p, plan.d_slot.p, plan.d_L.p, plan.d_cptr.p, plan.d_cent.p, plan.PE, plan.d_Ig.p,
                        reinterpret_cast<const uint2 *>(plan.d_cent4.p), plan.d_target.p};
@@ -2061,15 +2118,11 @@ namespace cb200
             if (!(phases & 2))
                 return;
             if (plan.n_shared > 0) {
-                assemble_shared_kernel<<<blocks_for(plan.n_shared, 256), 256, 0, s>>>(plan.n_shared, plan.d_sh_gid.p, plan.d_sh_ptr.p,
-                                                                                      d_partial2.p, Au, 1.0, 0);
-                CB_LAUNCHED();
-                assemble_shared_kernel<<<blocks_for(plan.n_shared, 256), 256, 0, s>>>(plan.n_shared, plan.d_sh_gid.p, plan.d_sh_ptr.p,
-                                                                                      d_partial2.p + a.partial_stride, Av, -1.0, 0);
+                assemble_shared_fields_kernel<<<dim3(blocks_for(plan.n_shared, 256), 2), 256, 0, s>>>(
+                    plan.n_shared, plan.d_sh_gid.p, plan.d_sh_ptr.p, d_partial2.p, a.partial_stride, y, n, 1.0, -1.0);
                 CB_LAUNCHED();
             }
-            H->apply_h1(-omega, v, Au, s);
-            H->apply_h1(-omega, u, Av, s);
+            H->apply_h1_pair(-omega, x, y, n, s); // Au -= w H v ; Av -= w H u in one launch
             return;
         }
         // 7 launches + 4 tiny assembly passes instead of the reference's 11 kernels + 4 memsets.

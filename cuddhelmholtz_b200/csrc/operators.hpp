@@ -45,6 +45,8 @@ namespace cb200
         void apply(double c, int accumulate, const double * x, double * y, cudaStream_t s);
         // fused restrict + action + prolong on H1 vectors: y[proj] += c * H * x[proj]
         void apply_h1(double c, const double * x, double * y, cudaStream_t s);
+        // both boundary terms of the Helmholtz composite on [u; v] (n DOFs each): y_u += c H x_v ; y_v += c H x_u
+        void apply_h1_pair(double c, const double * x, double * y, int64_t n, cudaStream_t s);
     };
     std::unique_ptr<FaceMassOp> make_facemass(FaceSpace * fs, const double * d_coef /* device face-space coefficient or null */, int nq);
     std::unique_ptr<DiagOp> make_diag_inv_facemass(FaceSpace * fs, const double * d_coef);
