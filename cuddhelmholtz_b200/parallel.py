@@ -180,6 +180,102 @@ class ShardedDDH:
         self._sum(u)
 
 
+class NeighbourDDH:
+    """Path B with DISTRIBUTED Krylov vectors and a neighbour-only trace exchange (north_star): subdomains
+    are dealt to the ranks in contiguous row slabs as in ShardedDDH, but a lambda slot now lives on ONE rank - the rank of
+    the subdomain that reads it (slots nobody reads: the writer's rank) - and after the local WaveHoltz solves only the
+    traces written across a slab boundary travel: one NCCL send/recv pair per neighbour (~n_dx * 13 * 4 floats per
+    neighbour for n_basis 4) instead of an allreduce of the whole vector. Inner products are masked to the owned slots and
+    summed with one small allreduce per Arnoldi step (`solve` = slab_gmres in FP32 with FP64 reductions).
+
+    The reader / writer of every slot come straight from the library's B table (source/DDH.cpp:425-440, including its
+    cross-point overwrites): slot B(j,0,dom) is read and slot B(j,1,dom) written by subdomain dom."""
+
+    def __init__(self, ddh, rank, world, group=None, device="cuda"):
+        self.ddh, self.rank, self.world, self.group = ddh, rank, world, group
+        info = ddh.info()
+        nd, self.n = info["n_domains"], ddh.size()
+        nl = self.n // 2
+        self.range = subdomain_range(nd, rank, world)
+        B = ddh.array("B").reshape(nd, 2, -1)
+        dom_rank = np.empty(nd, np.int32)
+        for r in range(world):
+            a, b = subdomain_range(nd, r, world)
+            dom_rank[a:b] = r
+        who = np.broadcast_to(dom_rank[:, None], B[:, 0, :].shape)
+        reader, writer = np.full(nl, -1, np.int32), np.full(nl, -1, np.int32)
+        for c, arr in ((0, reader), (1, writer)):
+            idx = B[:, c, :]
+            ok = idx >= 0
+            arr[idx[ok]] = who[ok]
+        self.owner = np.where(reader >= 0, reader, np.where(writer >= 0, writer, 0)).astype(np.int32)
+        both = lambda k: torch.as_tensor(np.concatenate([k, k + nl]), dtype=torch.long, device=device)  # lambda and mu halves
+        mine = self.owner == rank
+        self.mask = torch.zeros(self.n, dtype=torch.float32, device=device)
+        self.mask[both(np.nonzero(mine)[0])] = 1.0
+        self.send_idx, self.recv_idx = {}, {}
+        for q in range(world):
+            if q == rank:
+                continue
+            snd = np.nonzero((writer == rank) & (self.owner == q))[0]
+            rcv = np.nonzero(mine & (writer == q))[0]
+            if len(snd):
+                self.send_idx[q] = both(snd)
+            if len(rcv):
+                self.recv_idx[q] = both(rcv)
+        self.bytes_per_action = 4 * sum(int(v.numel()) for v in self.send_idx.values())
+
+    def size(self):
+        return self.n
+
+    def exchange(self, t):
+        """t holds what this rank's subdomains wrote: ship the slots owned elsewhere, take delivery of the owned ones"""
+        if self.world == 1:
+            return
+        ops, bufs = [], {}
+        for q, idx in self.send_idx.items():
+            sb = t[idx].contiguous()
+            bufs[("s", q)] = sb
+            ops.append(dist.P2POp(dist.isend, sb, q, group=self.group))
+        for q, idx in self.recv_idx.items():
+            rb = torch.empty(idx.numel(), dtype=t.dtype, device=t.device)
+            bufs[("r", q)] = rb
+            ops.append(dist.P2POp(dist.irecv, rb, q, group=self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        for q, idx in self.recv_idx.items():
+            t[idx] = bufs[("r", q)]
+
+    def apply_T(self, x, t):
+        self.ddh.apply_T_range(x, t, *self.range)
+        self.exchange(t)
+
+    def action_tensors(self, x, y):
+        self.apply_T(x, y)
+        y.neg_().add_(x).mul_(self.mask)  # y = x - T(x) on the owned slots, 0 elsewhere
+
+    def rhs(self, f, b):
+        self.ddh.rhs_range(f, b, *self.range)
+        self.exchange(b)
+        b.mul_(self.mask)
+
+    def postprocess(self, lam, f, u):
+        """u from (f, lambda): every rank adds its subdomains' partition-of-unity contributions (one allreduce, once)"""
+        self.ddh.postprocess_range(lam, f, u, *self.range)
+        if self.world > 1:
+            dist.all_reduce(u, op=dist.ReduceOp.SUM, group=self.group)
+
+    def solve(self, b, x, m=20, maxit=100, tol=1e-4):
+        y = torch.empty_like(b)
+
+        def A(v):
+            self.action_tensors(v.contiguous(), y)
+            return y.clone()
+
+        return slab_gmres(A, x, b, self.mask, m, maxit, tol, group=self.group, world=self.world)
+
+
 class _RawVec:
     def __init__(self, ptr, n, typestr):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
@@ -220,7 +316,7 @@ def slab_gmres(apply, x, b, mask, m, maxit, tol=1e-6, group=None, world=1):
         return t
 
     def dot(a, c):
-        return float(reduce_(torch.dot(mask * a, c).reshape(1))[0])
+        return float(reduce_(torch.dot(mask * a, c).reshape(1).double())[0])
 
     bnrm = np.sqrt(dot(b, b))
     V = torch.zeros(m + 1, n, dtype=x.dtype, device=x.device)
@@ -244,9 +340,9 @@ def slab_gmres(apply, x, b, mask, m, maxit, tol=1e-6, group=None, world=1):
             w = apply(V[k])
             out["num_matvec"] += 1
             mw = mask * w
-            red = torch.empty(k1 + 1, dtype=x.dtype, device=x.device)
-            red[:k1] = V[:k1] @ mw
-            red[k1] = torch.dot(mw, w)
+            red = torch.empty(k1 + 1, dtype=torch.float64, device=x.device)  # partial sums travel in FP64 (FP32 path too)
+            red[:k1] = (V[:k1] @ mw).double()
+            red[k1] = torch.dot(mw, w).double()
             red = reduce_(red).cpu().numpy()
             h, ww = red[:k1], red[k1]
             w = w - torch.as_tensor(h, dtype=x.dtype, device=x.device) @ V[:k1]

@@ -6,12 +6,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch, torch.distributed as dist
 import cuddhelmholtz_b200 as cb
-from cuddhelmholtz_b200.parallel import ShardedDDH
+from cuddhelmholtz_b200.parallel import NeighbourDDH, ShardedDDH
 
 nx = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 nb = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 omega_arg = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0     # 0: the examples' 2 pi nx / 10
 only_actions = int(sys.argv[4]) if len(sys.argv) > 4 else 0        # > 0: time this many actions instead of a full solve
+neighbour = int(sys.argv[5]) if len(sys.argv) > 5 else 0           # 1: NeighbourDDH (distributed vectors, send/recv of the slab-boundary traces)
 world, rank, lr = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lr)
 if world > 1:
@@ -28,7 +29,7 @@ n = fem.size()
 f = torch.zeros(2 * n, dtype=torch.float64, device="cuda")
 cb.MassMatrix(fem).action(torch.as_tensor(src, device="cuda"), f[:n])
 D = cb.DDH(omega, ha, fem, nx, nx, 16)
-A = ShardedDDH(D, rank, world)
+A = NeighbourDDH(D, rank, world) if neighbour else ShardedDDH(D, rank, world)
 m = D.size()
 b = torch.empty(m, dtype=torch.float32, device="cuda")
 A.rhs(f, b)
@@ -51,6 +52,12 @@ if only_actions > 0:
     for _ in range(only_actions):
         A.action_tensors(b, tmp)
     L.copy_(tmp)
+elif neighbour:
+    res = A.solve(b, L, m=20, maxit=100, tol=1e-4)
+
+    class _R:
+        num_iter, num_matvec, success = res["num_iter"], res["num_matvec"], res["success"]
+    out = _R()
 else:
     out = cb.gmres(m, L, A, b, 20, 100, 1e-4)
 e2.record()
@@ -65,6 +72,6 @@ if rank == 0:
     info = D.info()
     print(json.dumps({"n_gpus": world, "nx": nx, "n_basis": nb, "n_domains": info["n_domains"], "nt": info["nt"], "n_lambda": m,
                       "omega": omega, "action_ms": float(t[0]), "gmres_seconds": float(t[1]) / 1e3, "restarts": out.num_iter, "matvec": out.num_matvec,
-                      "success": out.success, "u_norm": float(chk[0]), "action_fp32_tflops": D.flops() / (float(t[0]) * 1e-3) / 1e12}))
+                      "success": out.success, "exchange": ("send/recv %d B per action" % A.bytes_per_action) if neighbour else "allreduce %d B" % (4 * m), "u_norm": float(chk[0]), "action_fp32_tflops": D.flops() / (float(t[0]) * 1e-3) / 1e12}))
 if world > 1:
     dist.destroy_process_group()

@@ -479,6 +479,56 @@ def test_ddh_subdomain_ranges_reproduce_the_full_operator():
     assert out.num_iter == out2.num_iter and torch.equal(L, L2)
 
 
+def test_ddh_neighbour_exchange_emulated():
+    """NeighbourDDH (distributed Krylov vectors, neighbour-only trace exchange), ranks emulated on one GPU: every lambda slot
+    has exactly one owner, a rank's kernel only reads slots it owns, and after shipping the slab-boundary traces the owned
+    pieces of x - T(x) (and of the right-hand side) tile the single-GPU vectors exactly."""
+    from cuddhelmholtz_b200.parallel import NeighbourDDH
+    omega = 10.0
+    ofem, pfem, oD, pD, f = _ddh_pair(16, 4, omega)
+    n = pD.size()
+    df = dev(f)
+    lam = dev(np.random.default_rng(6).uniform(-1, 1, n).astype(np.float32), torch.float32)
+    y_ref = torch.empty(n, dtype=torch.float32, device="cuda")
+    pD.action(lam, y_ref)
+    b_ref = torch.empty_like(y_ref)
+    pD.rhs(df, b_ref)
+    for world in (2, 4):
+        R = [NeighbourDDH(pD, r, world) for r in range(world)]
+        cover = sum(r.mask for r in R)
+        assert torch.equal(cover, torch.ones_like(cover))          # one owner per slot
+        for r in R:                                                # only neighbouring slabs talk, symmetric lists
+            assert all(abs(q - r.rank) == 1 for q in list(r.send_idx) + list(r.recv_idx))
+            for q, idx in r.send_idx.items():
+                assert torch.equal(idx, R[q].recv_idx[r.rank])
+            assert 0 < r.bytes_per_action < 4 * n // 4
+        for which in ("action", "rhs"):
+            parts = []
+            for r in R:
+                t = torch.empty(n, dtype=torch.float32, device="cuda")
+                if which == "action":
+                    x_owned = lam * r.mask + 123.0 * (1 - r.mask)  # garbage outside the owned slots must not matter
+                    pD.apply_T_range(x_owned, t, *r.range)
+                else:
+                    pD.rhs_range(df, t, *r.range)
+                parts.append(t)
+            for r in R:                                            # the send / recv pairs, emulated by copies
+                for q, idx in r.recv_idx.items():
+                    parts[r.rank][idx] = parts[q][R[q].send_idx[r.rank]]
+            acc = torch.zeros(n, dtype=torch.float32, device="cuda")
+            for r in R:
+                acc += ((lam - parts[r.rank]) if which == "action" else parts[r.rank]) * r.mask
+            assert torch.equal(acc, y_ref if which == "action" else b_ref), (world, which)
+    # one rank: the class is the plain operator, and its FP32 solve with FP64 reductions agrees with the library's gmres
+    A1 = NeighbourDDH(pD, 0, 1)
+    L = torch.zeros(n, dtype=torch.float32, device="cuda")
+    res = A1.solve(b_ref.clone(), L, m=20, maxit=100, tol=1e-4)
+    L2 = torch.zeros_like(L)
+    out2 = cb.gmres(n, L2, pD, b_ref, 20, 100, 1e-4)
+    assert res["success"] and out2.success and abs(res["num_iter"] - out2.num_iter) <= 1
+    assert float((L - L2).norm() / L2.norm()) < 5e-3
+
+
 def test_full_size_properties():
     # BASELINE config 2 size (uniform_rect(1024), n_basis 5): size-independent properties of the operators
     nx, nb = 1024, 5
