@@ -223,3 +223,36 @@ def test_assembly_plan_self_check(tag, nb, node_major):
             assert st["listed_dofs"] - st["shared_dofs"] < fem.size()
     if tag == "unstr":
         assert st["dofs_over_four"] >= 0  # the unstructured mesh has valence-5 vertices: the overflow path is exercised when > 0
+
+
+@pytest.mark.parametrize("nx,nb,world", [(16, 4, 2), (32, 4, 4), (32, 4, 3), (8, 8, 2)])
+def test_neighbour_ddh_slot_partition(nx, nb, world):
+    """host logic of parallel.NeighbourDDH (no GPU): from the library's B table every lambda slot gets one owning rank, a
+    rank's subdomains read owned slots only, write owned or adjacent-slab slots only, and the send / recv lists of
+    neighbouring ranks mirror each other."""
+    import torch
+    from cuddhelmholtz_b200.parallel import NeighbourDDH, subdomain_range
+    mesh = cb.Mesh2D.uniform_rect(nx, -1.0, 1.0, nx, -1.0, 1.0)
+    fem = cb.H1Space(mesh, cb.Basis(nb))
+    ha = np.ones(fem.size())
+    d = cb.DDH(10.0, ha, fem, nx, nx, 16)
+    nd, n = d.info()["n_domains"], d.size()
+    nl = n // 2
+    B = d.array("B").reshape(nd, 2, -1)
+    R = [NeighbourDDH(d, r, world, device="cpu") for r in range(world)]
+    assert torch.equal(sum(r.mask for r in R), torch.ones(n))
+    total_sent = 0
+    for r in R:
+        a, b = subdomain_range(nd, r.rank, world)
+        reads = B[a:b, 0, :]
+        writes = B[a:b, 1, :]
+        assert np.all(r.owner[reads[reads >= 0]] == r.rank)
+        assert np.all(np.abs(r.owner[writes[writes >= 0]] - r.rank) <= 1)
+        for q, idx in r.send_idx.items():
+            assert abs(q - r.rank) == 1 and torch.equal(idx, R[q].recv_idx[r.rank])
+            assert np.all(r.owner[idx.numpy()[: idx.numel() // 2]] == q)  # first half: lambda block, second: + n_lambda
+            assert torch.equal(idx[idx.numel() // 2:], idx[: idx.numel() // 2] + nl)
+            total_sent += idx.numel()
+        assert set(r.recv_idx) <= {r.rank - 1, r.rank + 1}
+    # only slab-boundary traces travel: a small fraction of the vector
+    assert 0 < total_sent < n // 2
