@@ -163,3 +163,60 @@ def test_slab_gmres_two_ranks_gloo():
         assert err < 1e-6, err
         # one allreduce per Arnoldi step (+ the norms of b, r0 and one residual per restart; a few cancellation re-norms allowed)
         assert nred <= matvec + it + 8, (nred, matvec, it)
+
+
+def _nbr_worker(rank, world, port, nx, nb, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import cuddhelmholtz_b200 as cb
+        from cuddhelmholtz_b200.parallel import NeighbourDDH, subdomain_range
+        mesh = cb.Mesh2D.uniform_rect(nx, -1.0, 1.0, nx, -1.0, 1.0)
+        fem = cb.H1Space(mesh, cb.Basis(nb))
+        d = cb.DDH(10.0, np.ones(fem.size()), fem, nx, nx, 16)   # host tables only: no GPU needed
+        A = NeighbourDDH(d, rank, world, device="cpu")
+        n, nd = d.size(), d.info()["n_domains"]
+        nl = n // 2
+        B = d.array("B").reshape(nd, 2, -1)
+        # what this rank's subdomains "write": slot s gets the value s + 0.25 (lambda half) / s + 0.75 (mu half), zeros elsewhere
+        a, b = subdomain_range(nd, rank, world)
+        w = B[a:b, 1, :]
+        w = np.unique(w[w >= 0])
+        t = torch.zeros(n, dtype=torch.float32)
+        t[torch.as_tensor(w)] = torch.as_tensor(w + 0.25, dtype=torch.float32)
+        t[torch.as_tensor(w + nl)] = torch.as_tensor(w + 0.75, dtype=torch.float32)
+        A.exchange(t)                                             # the real send / recv pairs over gloo
+        # every owned slot that ANY subdomain writes must now hold its value
+        allw = B[:, 1, :]
+        allw = np.unique(allw[allw >= 0])
+        mine = allw[A.owner[allw] == rank]
+        ok = bool(np.array_equal(t[torch.as_tensor(mine)].numpy(), (mine + 0.25).astype(np.float32)) and
+                  np.array_equal(t[torch.as_tensor(mine + nl)].numpy(), (mine + 0.75).astype(np.float32)))
+        # masked inner products sum to the global ones: one owner per slot
+        v = torch.arange(n, dtype=torch.float64)
+        part = torch.tensor([float(torch.dot(A.mask.double() * v, v))], dtype=torch.float64)
+        dist.all_reduce(part)
+        q.put((rank, ok, float(part[0]), float(torch.dot(v, v)), A.bytes_per_action))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_neighbour_ddh_exchange_two_ranks_gloo():
+    """the send / recv trace exchange of NeighbourDDH between two real processes (gloo, CPU tensors, host DDH tables)"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29950 + (os.getpid() % 40)
+    world = 2
+    procs = [ctx.Process(target=_nbr_worker, args=(r, world, port, 32, 4, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, part, full, nbytes in res:
+        assert ok, rank
+        assert part == full
+        assert nbytes > 0
