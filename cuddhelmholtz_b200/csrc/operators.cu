@@ -308,12 +308,7 @@ namespace cb200
             constexpr int LW = EPW * NQ;          // active lanes
             constexpr int NB2 = NB * NB;
             constexpr int NK = STIFF ? 3 * NQ : NQ; // metric values per lane
-            constexpr int NKI = STIFF ? 3 : 1;      // metric values per lane per quadrature column
-            constexpr int PD = STIFF ? 2 : 4;       // metric prefetch depth (quadrature columns) in stage 2
-            constexpr ScrLayout LY = scr_layout<NB, NQ, STIFF>();
-            constexpr int SCR = LY.S;    // scratch doubles per element (padded)
-            constexpr int RS = LY.RS;    // row stride
-            constexpr int HALF = LY.HALF; // offset of the derivative plane
+            constexpr int SCR = scr_layout<NB, NQ, STIFF>().S; // scratch doubles per element (padded; layout: contract_patch)
 
             extern __shared__ __align__(16) unsigned char smem_raw[];
             const int PE = plan.PE;
