@@ -194,8 +194,8 @@ class H1Space:
         """host-only self check of the assembly plan (include/cuddh_b200.h): dict of plan sizes and 'mismatches' (0 = ok)."""
         st = (C.c_int64 * 8)()
         check(load().cuddh_b200_h1space_check_plan(self._h, int(node_major), st))
-        keys = ("n_patches", "patch_elems", "listed_dofs", "shared_dofs", "max_pdof", "dofs_over_four", "mismatches")
-        return dict(zip(keys, [int(v) for v in st[:7]]))
+        keys = ("n_patches", "patch_elems", "listed_dofs", "shared_dofs", "max_pdof", "dofs_over_four", "mismatches", "hash")
+        return dict(zip(keys, [int(v) for v in st[:8]]))
 
     def mesh(self):
         return self._mesh

@@ -433,7 +433,7 @@ namespace cb200
 
     // Host-only self check of an assembly plan (no GPU): plays the kernels' gather / assembly with integer-valued element
     // contributions v(el, a) and compares with the direct sum over I. Exercises both layouts; used by the CPU test-suite.
-    // stats: n_patches, PE, listed patch DOFs, shared DOFs, max_pdof, entries beyond four per DOF, mismatches, reserved
+    // stats: n_patches, PE, listed patch DOFs, shared DOFs, max_pdof, entries beyond four per DOF, mismatches, FNV-1a of all arrays
     void plan_self_check(H1Space & fem, bool tpe, int64_t stats[8])
     {
         Plan plan;
@@ -513,7 +513,24 @@ namespace cb200
         stats[4] = plan.max_pdof;
         stats[5] = over4;
         stats[6] = bad;
-        stats[7] = 0;
+        // FNV-1a over every array of the plan: lets a test pin the plan builder bit for bit
+        uint64_t hsh = 0xcbf29ce484222325ull;
+        auto mix = [&hsh](const void * ptr, size_t bytes) {
+            const unsigned char * b = static_cast<const unsigned char *>(ptr);
+            for (size_t i = 0; i < bytes; ++i) {
+                hsh ^= b[i];
+                hsh *= 0x100000001b3ull;
+            }
+        };
+        auto mixv = [&mix](const auto & v) {
+            if (!v.empty())
+                mix(v.data(), v.size() * sizeof(v[0]));
+        };
+        mixv(plan.hdr); mixv(plan.gid); mixv(plan.slot); mixv(plan.L); mixv(plan.cptr); mixv(plan.cent); mixv(plan.slot_elem);
+        mixv(plan.Ig); mixv(plan.cent4); mixv(plan.target); mixv(plan.sh_gid); mixv(plan.sh_ptr);
+        const int64_t scal[4] = {plan.n_slots_total, plan.n_shared, plan.max_pdof, plan.max_nsh};
+        mix(scal, sizeof(scal));
+        stats[7] = (int64_t)hsh;
     }
 
     void Plan::ensure_device()

@@ -71,7 +71,7 @@ int64_t cuddh_b200_h1space_size(cuddh_h1space_t s);                       /* H1S
  * source/StiffnessMatrix.cpp:174-182): plays gather + assembly with integer-valued element contributions and compares with the
  * direct sum over global_indices. node_major: 1 = thread-per-element plan (n_basis <= 5 kernels), 0 = element-major plan.
  * stats[8] = n_patches, elements per patch, listed patch DOFs, shared DOFs, max DOFs per patch, DOFs with more than four
- * contributions, MISMATCHES (0 = ok), reserved. Needs no GPU. */
+ * contributions, MISMATCHES (0 = ok), FNV-1a hash of all plan arrays. Needs no GPU. */
 int cuddh_b200_h1space_check_plan(cuddh_h1space_t s, int node_major, int64_t * stats);
 int cuddh_b200_h1space_global_indices(cuddh_h1space_t s, int * h_I);      /* (nb,nb,n_elem) host copy */
 int cuddh_b200_h1space_physical_coordinates(cuddh_h1space_t s, double * h_xy); /* (2,ndof) host copy */

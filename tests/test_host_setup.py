@@ -256,3 +256,23 @@ def test_neighbour_ddh_slot_partition(nx, nb, world):
         assert set(r.recv_idx) <= {r.rank - 1, r.rank + 1}
     # only slab-boundary traces travel: a small fraction of the vector
     assert 0 < total_sent < n // 2
+
+
+def test_assembly_plan_hashes_pinned():
+    """every array of both assembly plans, bit for bit, against tests/golden/plan_hashes.json (scripts/make_plan_hashes.py):
+    the kernels consume these arrays verbatim, so an unintended change of the plan builder shows up here without a GPU"""
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "plan_hashes.json")))
+    xy, el = load_mesh_file()
+    mk = {"unstr": lambda: cb.Mesh2D.from_vertices(xy, el), "r37": lambda: cb.Mesh2D.uniform_rect(37, -1.0, 1.0, 29, 0.0, 2.0),
+          "r10": lambda: cb.Mesh2D.uniform_rect(10, -1.0, 1.0, 10, -1.0, 1.0), "r3": lambda: cb.Mesh2D.uniform_rect(3, -1.0, 1.0, 2, -1.0, 1.0)}
+    checked = 0
+    for key, h in gold.items():
+        tag, nb, k = key.split("_")
+        if tag not in mk:
+            continue  # the 256^2 cases are generator-only (seconds each)
+        fem = cb.H1Space(mk[tag](), cb.Basis(int(nb)))
+        assert fem.check_plan(int(k))["hash"] == h, key
+        checked += 1
+    assert checked >= 40
