@@ -365,53 +365,111 @@ class Helmholtz(Operator):
 
 
 class SolverOut:
-    """include/gmres.hpp:14-21 solver_out."""
+    """include/gmres.hpp:14-21 solver_out (+ the orthogonalisation statistics of this library)."""
 
-    def __init__(self, so, res, time):
+    def __init__(self, so, res, time, stats=None):
         self.success = bool(so.success)
         self.num_iter = so.num_iter
         self.num_matvec = so.num_matvec
         self.res_norm = list(res[:so.n_res])
         self.time = list(time[:so.n_res])
+        self.orth_bytes = stats.orth_bytes if stats is not None else 0.0
+        self.orth_ms = stats.orth_ms if stats is not None else 0.0
+        self.reorth = stats.reorth if stats is not None else 0
+        self.allreduces = stats.allreduces if stats is not None else 0
+
+
+_callback_error = []
 
 
 def _callback(A, kind):
     """(function pointer, ctx, keepalive) for an operator: library objects use the in-library trampoline, any
-    object with .action(x, y) taking raw device addresses is wrapped in a ctypes callback."""
+    object with .action(x, y) taking raw device addresses is wrapped in a ctypes callback. The callback runs under the
+    stream gmres works on (it is handed over as the 4th argument; for torch-backed operators that is torch's current
+    stream, because gmres() below passes exactly that one). An exception in the Python operator aborts the solve."""
     if hasattr(A, "_as_apply"):
         fn, ctx = A._as_apply()
         return fn, ctx, None
     proto = capi.APPLY_D if kind == "d" else capi.APPLY_F
 
-    def tramp(_ctx, x, y):
-        A.action(int(x), int(y))
+    def tramp(_ctx, x, y, _stream):
+        try:
+            A.action(int(x), int(y))
+            return 0
+        except BaseException as e:  # ctypes would swallow it: hand a status back instead and re-raise after the solve
+            _callback_error.append(e)
+            return -7
 
     cb = proto(tramp)
     return C.cast(cb, C.c_void_p), None, cb
 
 
-def gmres(n, x, A, b, m, maxit, tol=None, P=None, verbose=0, max_seconds=6 * 60 * 60):
+MGS, CGS2 = 0, 1
+
+
+def gmres(n, x, A, b, m, maxit, tol=None, P=None, verbose=0, max_seconds=6 * 60 * 60, orth=-1, comm=None, mask=None, time_orth=False):
     """include/gmres.hpp:33-36. x, b: device vectors (torch float64 -> FP64 solver, float32 -> FP32 solver).
-    A (and P): operators of this module, or any object with .action(x_ptr, y_ptr) on raw device addresses."""
+    A (and P): operators of this module, or any object with .action(x_ptr, y_ptr) on raw device addresses.
+    orth: MGS (the reference's arithmetic) / CGS2 / -1 = library default; comm + mask: distributed vectors (Comm, uint8 tensor)."""
     import torch
     single = isinstance(x, torch.Tensor) and x.dtype == torch.float32
     cap = maxit + 2
     res = np.zeros(cap)
     tim = np.zeros(cap)
     so = capi.SolverOut()
+    st = capi.GmresStats()
+    opts = capi.GmresOptions(int(orth), comm._h if comm is not None else None, _ptr(mask), int(bool(time_orth)))
     fa, ca, keep_a = _callback(A, "f" if single else "d")
+    del _callback_error[:]
     if single:
         if P is not None:
             raise capi.CuddhError("the FP32 gmres overload has no preconditioner argument (include/gmres.hpp:36)")
         tol = 1e-4 if tol is None else tol
-        check(load().cuddh_b200_gmres_f(n, _ptr(x), fa, ca, _ptr(b), m, maxit, tol, verbose, float(max_seconds), C.byref(so),
-                                        _vp(res), _vp(tim), cap, _stream()))
+        rc = load().cuddh_b200_gmres_f_ex(n, _ptr(x), fa, ca, _ptr(b), m, maxit, tol, verbose, float(max_seconds), C.byref(opts),
+                                          C.byref(so), _vp(res), _vp(tim), cap, C.byref(st), _stream())
     else:
         tol = 1e-6 if tol is None else tol
         fp, cp, keep_p = (None, None, None) if P is None else _callback(P, "d")
-        check(load().cuddh_b200_gmres_d(n, _ptr(x), fa, ca, _ptr(b), fp, cp, m, maxit, tol, verbose, float(max_seconds),
-                                        C.byref(so), _vp(res), _vp(tim), cap, _stream()))
-    return SolverOut(so, res, tim)
+        rc = load().cuddh_b200_gmres_d_ex(n, _ptr(x), fa, ca, _ptr(b), fp, cp, m, maxit, tol, verbose, float(max_seconds),
+                                          C.byref(opts), C.byref(so), _vp(res), _vp(tim), cap, C.byref(st), _stream())
+    if _callback_error:
+        raise _callback_error.pop()
+    check(rc)
+    return SolverOut(so, res, tim, st)
+
+
+def set_option(name, value):
+    check(load().cuddh_b200_set_option(name.encode(), int(value)))
+
+
+def get_option(name):
+    return int(load().cuddh_b200_get_option(name.encode()))
+
+
+class Comm:
+    """Library-owned NCCL communicator (include/cuddh_b200.h: cuddh_b200_comm_*), one per process / GPU. The 128-byte unique id
+    is made by rank 0 and travels through the caller's bootstrap - here torch.distributed (any backend)."""
+
+    def __init__(self, rank, world, group=None):
+        import torch.distributed as dist
+        self.rank, self.world = rank, world
+        ident = [None]
+        if rank == 0:
+            buf = (C.c_ubyte * 128)()
+            check(load().cuddh_b200_comm_unique_id(buf))
+            ident[0] = bytes(buf)
+        if world > 1:
+            dist.broadcast_object_list(ident, src=0, group=group)
+        buf = (C.c_ubyte * 128).from_buffer_copy(ident[0])
+        self._h = C.c_void_p()
+        check(load().cuddh_b200_comm_create(buf, rank, world, C.byref(self._h)))
+
+    def __del__(self):
+        _destroy("cuddh_b200_comm_destroy", self)
+
+    def allreduce(self, t):
+        """in-place sum of a float64 CUDA tensor over the ranks (stream-ordered on torch's current stream)"""
+        check(load().cuddh_b200_comm_allreduce_d(self._h, _ptr(t), t.numel(), _stream()))
 
 
 class DDH:
@@ -470,8 +528,81 @@ class DDH:
     def flops(self):
         return float(load().cuddh_b200_ddh_flops(self._h))
 
+    def kernel_kind(self):
+        """1 = register-tiled thread-per-element kernel (n_basis 4, block 16, uniform metric), 0 = generic kernel"""
+        return int(load().cuddh_b200_ddh_kernel_kind(self._h))
+
     def _as_apply(self):
         return C.cast(load().cuddh_b200_ddh_as_apply, C.c_void_p), self._h
+
+
+class DDHDist:
+    """DDH across GPUs in the library (cuddh_b200_ddh_dist_*): subdomain row slabs, owner = reading subdomain's rank, traces that
+    cross a slab boundary packed in the kernel epilogue and moved with ncclSend/ncclRecv. comm=None: partition tables only /
+    single rank. Vectors keep the global length ddh.size(); use .mask() as the ownership mask of gmres(..., comm=, mask=)."""
+
+    def __init__(self, ddh, comm, rank, world):
+        self.ddh, self.comm, self.rank, self.world = ddh, comm, rank, world
+        self._h = C.c_void_p()
+        check(load().cuddh_b200_ddh_dist_create(ddh._h, comm._h if comm is not None else None, rank, world, C.byref(self._h)))
+        self.n = ddh.size()
+
+    def __del__(self):
+        _destroy("cuddh_b200_ddh_dist_destroy", self)
+
+    def size(self):
+        return self.n
+
+    def info(self):
+        v = np.zeros(8, np.int64)
+        check(load().cuddh_b200_ddh_dist_info(self._h, _vp(v)))
+        keys = ["dom_begin", "dom_end", "n_owned", "n_send", "n_recv", "n_peers", "bytes_per_action", "size"]
+        return {k: int(x) for k, x in zip(keys, v)}
+
+    def array(self, name):
+        cnt = C.c_int64()
+        check(load().cuddh_b200_ddh_dist_get_array(self._h, name.encode(), None, 0, C.byref(cnt)))
+        out = np.zeros(cnt.value, np.int32)
+        check(load().cuddh_b200_ddh_dist_get_array(self._h, name.encode(), _vp(out), out.size, C.byref(cnt)))
+        return out
+
+    def mask(self):
+        """uint8 CUDA tensor view (length size()) of the library's ownership mask"""
+        import torch
+        p = load().cuddh_b200_ddh_dist_mask(self._h)
+        if not p:
+            check(-1)
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (self.n,), "typestr": "|u1", "data": (int(p), False), "version": 2}
+        t = torch.as_tensor(_Raw(), device="cuda")
+        t._keepalive = self
+        return t
+
+    def buffers(self):
+        """(send, recv) raw device addresses of the packed (lambda, mu) pair buffers (tests)"""
+        a, b = C.c_void_p(), C.c_void_p()
+        check(load().cuddh_b200_ddh_dist_buffers(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def rhs(self, f, b):
+        check(load().cuddh_b200_ddh_dist_rhs(self._h, _ptr(f), _ptr(b), _stream()))
+
+    def action(self, x, y):
+        check(load().cuddh_b200_ddh_dist_action(self._h, _ptr(x), _ptr(y), _stream()))
+
+    def apply_T(self, x, t):
+        check(load().cuddh_b200_ddh_dist_apply_T(self._h, _ptr(x), _ptr(t), _stream()))
+
+    def postprocess(self, lam, f, u):
+        check(load().cuddh_b200_ddh_dist_postprocess(self._h, _ptr(lam), _ptr(f), _ptr(u), _stream()))
+
+    def _as_apply(self):
+        return C.cast(load().cuddh_b200_ddh_dist_as_apply, C.c_void_p), self._h
+
+    def solve(self, b, x, m=20, maxit=100, tol=1e-4, orth=-1, time_orth=False):
+        """distributed FP32 GMRES in the library: masked inner products, one NCCL allreduce per pass"""
+        return gmres(self.n, x, self, b, m, maxit, tol, orth=orth, comm=self.comm, mask=self.mask(), time_orth=time_orth)
 
 
 # include/linalg.hpp

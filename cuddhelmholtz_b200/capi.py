@@ -11,12 +11,21 @@ c_i64 = C.c_int64
 c_vp = C.c_void_p
 c_dp = C.c_void_p  # device or host pointers are passed as raw addresses
 
-APPLY_D = C.CFUNCTYPE(None, c_vp, c_vp, c_vp)
-APPLY_F = C.CFUNCTYPE(None, c_vp, c_vp, c_vp)
+# cuddh_apply_{d,f}_fn: int (*)(void* ctx, const T* x, T* y, void* stream); non-zero aborts the solve
+APPLY_D = C.CFUNCTYPE(C.c_int, c_vp, c_vp, c_vp, c_vp)
+APPLY_F = C.CFUNCTYPE(C.c_int, c_vp, c_vp, c_vp, c_vp)
 
 
 class SolverOut(C.Structure):
     _fields_ = [("success", C.c_int), ("num_iter", C.c_int), ("num_matvec", C.c_int), ("n_res", C.c_int)]
+
+
+class GmresOptions(C.Structure):
+    _fields_ = [("orth", C.c_int), ("comm", C.c_void_p), ("d_mask", C.c_void_p), ("time_orth", C.c_int)]
+
+
+class GmresStats(C.Structure):
+    _fields_ = [("orth_bytes", C.c_double), ("orth_ms", C.c_double), ("reorth", C.c_int), ("allreduces", C.c_int)]
 
 
 class CuddhError(RuntimeError):
@@ -105,8 +114,31 @@ def _proto(lib):
                                          C.c_double, P(SolverOut), c_vp, c_vp, C.c_int, c_vp]),
         "cuddh_b200_gmres_f": (C.c_int, [c_i64, c_dp, c_vp, c_vp, c_dp, C.c_int, C.c_int, C.c_float, C.c_int, C.c_double,
                                          P(SolverOut), c_vp, c_vp, C.c_int, c_vp]),
-        "cuddh_b200_operator_as_apply": (None, [c_vp, c_dp, c_dp]),
-        "cuddh_b200_ddh_as_apply": (None, [c_vp, c_dp, c_dp]),
+        "cuddh_b200_gmres_d_ex": (C.c_int, [c_i64, c_dp, c_vp, c_vp, c_dp, c_vp, c_vp, C.c_int, C.c_int, C.c_double, C.c_int,
+                                            C.c_double, P(GmresOptions), P(SolverOut), c_vp, c_vp, C.c_int, P(GmresStats), c_vp]),
+        "cuddh_b200_gmres_f_ex": (C.c_int, [c_i64, c_dp, c_vp, c_vp, c_dp, C.c_int, C.c_int, C.c_float, C.c_int, C.c_double,
+                                            P(GmresOptions), P(SolverOut), c_vp, c_vp, C.c_int, P(GmresStats), c_vp]),
+        "cuddh_b200_operator_as_apply": (C.c_int, [c_vp, c_dp, c_dp, c_vp]),
+        "cuddh_b200_ddh_as_apply": (C.c_int, [c_vp, c_dp, c_dp, c_vp]),
+        "cuddh_b200_set_option": (C.c_int, [C.c_char_p, c_i64]),
+        "cuddh_b200_get_option": (c_i64, [C.c_char_p]),
+        "cuddh_b200_comm_unique_id": (C.c_int, [c_vp]),
+        "cuddh_b200_comm_create": (C.c_int, [c_vp, C.c_int, C.c_int, P(c_vp)]),
+        "cuddh_b200_comm_wrap": (C.c_int, [c_vp, C.c_int, C.c_int, P(c_vp)]),
+        "cuddh_b200_comm_destroy": (C.c_int, [c_vp]),
+        "cuddh_b200_comm_allreduce_d": (C.c_int, [c_vp, c_dp, c_i64, c_vp]),
+        "cuddh_b200_ddh_kernel_kind": (C.c_int, [c_vp]),
+        "cuddh_b200_ddh_dist_create": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, P(c_vp)]),
+        "cuddh_b200_ddh_dist_destroy": (C.c_int, [c_vp]),
+        "cuddh_b200_ddh_dist_info": (C.c_int, [c_vp, c_vp]),
+        "cuddh_b200_ddh_dist_get_array": (C.c_int, [c_vp, C.c_char_p, c_vp, c_i64, P(c_i64)]),
+        "cuddh_b200_ddh_dist_mask": (c_vp, [c_vp]),
+        "cuddh_b200_ddh_dist_buffers": (C.c_int, [c_vp, P(c_vp), P(c_vp)]),
+        "cuddh_b200_ddh_dist_rhs": (C.c_int, [c_vp, c_dp, c_dp, c_vp]),
+        "cuddh_b200_ddh_dist_action": (C.c_int, [c_vp, c_dp, c_dp, c_vp]),
+        "cuddh_b200_ddh_dist_apply_T": (C.c_int, [c_vp, c_dp, c_dp, c_vp]),
+        "cuddh_b200_ddh_dist_postprocess": (C.c_int, [c_vp, c_dp, c_dp, c_dp, c_vp]),
+        "cuddh_b200_ddh_dist_as_apply": (C.c_int, [c_vp, c_dp, c_dp, c_vp]),
         "cuddh_b200_ddh_create": (C.c_int, [C.c_double, c_vp, c_vp, C.c_int, C.c_int, C.c_int, P(c_vp)]),
         "cuddh_b200_ddh_destroy": (C.c_int, [c_vp]),
         "cuddh_b200_ddh_size": (c_i64, [c_vp]),

@@ -47,6 +47,8 @@ struct cuddh_operator_s
 };
 struct cuddh_ddh_s { std::unique_ptr<DDH> d; };
 struct cuddh_ensemble_s { std::unique_ptr<Ensemble> e; };
+struct cuddh_comm_s { std::unique_ptr<Comm> c; };
+struct cuddh_ddh_dist_s { std::unique_ptr<DdhDist> d; };
 
 static inline cudaStream_t S(void * s) { return (cudaStream_t)s; }
 
@@ -484,6 +486,7 @@ int cuddh_b200_fill_i(int64_t n, int a, int * x, void * stream)
 }
 
 // ---- gmres ----
+} // extern "C"
 namespace
 {
     struct PrecondSystem // source/gmres.cpp:68-89 PreconditionedSystem: y = P (A x)
@@ -491,11 +494,22 @@ namespace
         cuddh_apply_d_fn A, P;
         void *Actx, *Pctx;
         double * q;
-        static void apply(void * self, const double * x, double * y)
+        static int apply(void * self, const double * x, double * y, cudaStream_t st)
         {
             auto * s = (PrecondSystem *)self;
-            s->A(s->Actx, x, s->q);
-            s->P(s->Pctx, s->q, y);
+            const int rc = s->A(s->Actx, x, s->q, (void *)st);
+            return rc ? rc : s->P(s->Pctx, s->q, y, (void *)st);
+        }
+    };
+    // the C ABI callback type (void* stream) behind the internal one (cudaStream_t)
+    template <typename T> struct UserApply
+    {
+        int (*fn)(void *, const T *, T *, void *);
+        void * ctx;
+        static int apply(void * self, const T * x, T * y, cudaStream_t st)
+        {
+            auto * u = (UserApply *)self;
+            return u->fn(u->ctx, x, y, (void *)st);
         }
     };
 
@@ -515,43 +529,149 @@ namespace
                 time[i] = r.time[i];
         }
     }
+
+    GmresOptions make_options(const cuddh_gmres_options * o)
+    {
+        GmresOptions g;
+        g.orth = default_gmres_orth();
+        if (o) {
+            if (o->orth >= 0)
+                g.orth = o->orth;
+            g.comm = o->comm ? o->comm->c.get() : nullptr;
+            g.d_mask = o->d_mask;
+            g.time_orth = o->time_orth != 0;
+        }
+        CB_REQUIRE(g.orth == ORTH_MGS || g.orth == ORTH_CGS2, "gmres: unknown orthogonalisation mode");
+        return g;
+    }
+    void fill_stats(const GmresResult & r, cuddh_gmres_stats * st)
+    {
+        if (!st)
+            return;
+        st->orth_bytes = r.orth_bytes;
+        st->orth_ms = r.orth_ms;
+        st->reorth = r.reorth;
+        st->allreduces = r.allreduces;
+    }
 } // namespace
+extern "C" {
+
+int cuddh_b200_gmres_d_ex(int64_t n, double * x, cuddh_apply_d_fn A, void * A_ctx, const double * b, cuddh_apply_d_fn P, void * P_ctx,
+                          int m, int maxit, double tol, int verbose, double max_seconds, const cuddh_gmres_options * opts,
+                          cuddh_solver_out * out, double * res, double * time, int cap, cuddh_gmres_stats * stats, void * stream)
+{
+    CB_TRY
+    CB_REQUIRE(A != nullptr, "gmres: null operator callback");
+    const GmresOptions go = make_options(opts);
+    GmresResult r;
+    if (P) { // gmres.cpp:242-251: solve P A x = P b
+        DevBuf<double> q((size_t)n), r0((size_t)n);
+        PrecondSystem sys{A, P, A_ctx, P_ctx, q.p};
+        const int rc = P(P_ctx, b, r0.p, stream);
+        if (rc != 0)
+            throw Error(rc, "gmres: the preconditioner callback failed");
+        r = gmres<double>(n, x, &PrecondSystem::apply, &sys, r0.p, m, maxit, tol, verbose, max_seconds, S(stream), go);
+        CB_CUDA(cudaStreamSynchronize(S(stream)));
+    }
+    else {
+        UserApply<double> ua{A, A_ctx};
+        r = gmres<double>(n, x, &UserApply<double>::apply, &ua, b, m, maxit, tol, verbose, max_seconds, S(stream), go);
+    }
+    fill_out(r, out, res, time, cap);
+    fill_stats(r, stats);
+    CB_CATCH
+}
+
+int cuddh_b200_gmres_f_ex(int64_t n, float * x, cuddh_apply_f_fn A, void * A_ctx, const float * b, int m, int maxit, float tol,
+                          int verbose, double max_seconds, const cuddh_gmres_options * opts, cuddh_solver_out * out, double * res,
+                          double * time, int cap, cuddh_gmres_stats * stats, void * stream)
+{
+    CB_TRY
+    CB_REQUIRE(A != nullptr, "gmres: null operator callback");
+    const GmresOptions go = make_options(opts);
+    UserApply<float> ua{A, A_ctx};
+    GmresResult r = gmres<float>(n, x, &UserApply<float>::apply, &ua, b, m, maxit, tol, verbose, max_seconds, S(stream), go);
+    fill_out(r, out, res, time, cap);
+    fill_stats(r, stats);
+    CB_CATCH
+}
 
 int cuddh_b200_gmres_d(int64_t n, double * x, cuddh_apply_d_fn A, void * A_ctx, const double * b, cuddh_apply_d_fn P, void * P_ctx,
                        int m, int maxit, double tol, int verbose, double max_seconds, cuddh_solver_out * out, double * res,
                        double * time, int cap, void * stream)
 {
-    CB_TRY
-    GmresResult r;
-    if (P) { // gmres.cpp:242-251: solve P A x = P b
-        DevBuf<double> q((size_t)n), r0((size_t)n);
-        PrecondSystem sys{A, P, A_ctx, P_ctx, q.p};
-        P(P_ctx, b, r0.p);
-        r = gmres<double>(n, x, &PrecondSystem::apply, &sys, r0.p, m, maxit, tol, verbose, max_seconds, S(stream));
-        CB_CUDA(cudaStreamSynchronize(S(stream)));
-    }
-    else
-        r = gmres<double>(n, x, A, A_ctx, b, m, maxit, tol, verbose, max_seconds, S(stream));
-    fill_out(r, out, res, time, cap);
-    CB_CATCH
+    return cuddh_b200_gmres_d_ex(n, x, A, A_ctx, b, P, P_ctx, m, maxit, tol, verbose, max_seconds, nullptr, out, res, time, cap, nullptr, stream);
 }
 
 int cuddh_b200_gmres_f(int64_t n, float * x, cuddh_apply_f_fn A, void * A_ctx, const float * b, int m, int maxit, float tol,
                        int verbose, double max_seconds, cuddh_solver_out * out, double * res, double * time, int cap, void * stream)
 {
-    CB_TRY
-    GmresResult r = gmres<float>(n, x, A, A_ctx, b, m, maxit, tol, verbose, max_seconds, S(stream));
-    fill_out(r, out, res, time, cap);
-    CB_CATCH
+    return cuddh_b200_gmres_f_ex(n, x, A, A_ctx, b, m, maxit, tol, verbose, max_seconds, nullptr, out, res, time, cap, nullptr, stream);
 }
 
-void cuddh_b200_operator_as_apply(void * h, const double * x, double * y)
+int cuddh_b200_operator_as_apply(void * h, const double * x, double * y, void * stream)
 {
-    cuddh_b200_operator_apply((cuddh_operator_t)h, 1.0, 0, x, y, nullptr);
+    return cuddh_b200_operator_apply((cuddh_operator_t)h, 1.0, 0, x, y, stream);
 }
-void cuddh_b200_ddh_as_apply(void * h, const float * x, float * y)
+int cuddh_b200_ddh_as_apply(void * h, const float * x, float * y, void * stream)
 {
-    cuddh_b200_ddh_action((cuddh_ddh_t)h, x, y, nullptr);
+    return cuddh_b200_ddh_action((cuddh_ddh_t)h, x, y, stream);
+}
+
+// ---- options ----
+int cuddh_b200_set_option(const char * name, int64_t value)
+{
+    CB_TRY
+    const std::string n(name ? name : "");
+    if (n == "gmres_orth")
+        set_default_gmres_orth((int)value);
+    else if (n == "max_ctas")
+        set_max_persistent_ctas((int)value);
+    else
+        throw Error(-1, "set_option: unknown option " + n);
+    CB_CATCH
+}
+int64_t cuddh_b200_get_option(const char * name)
+{
+    const std::string n(name ? name : "");
+    if (n == "gmres_orth")
+        return default_gmres_orth();
+    if (n == "max_ctas")
+        return max_persistent_ctas();
+    if (n == "nccl_available")
+        return nccl_available() ? 1 : 0;
+    return -1;
+}
+
+// ---- communicator (multi-GPU runs: one process per GPU) ----
+int cuddh_b200_comm_unique_id(unsigned char * id128)
+{
+    CB_TRY
+    comm_unique_id(id128);
+    CB_CATCH
+}
+int cuddh_b200_comm_create(const unsigned char * id128, int rank, int world, cuddh_comm_t * out)
+{
+    CB_TRY
+    *out = new cuddh_comm_s{comm_create(id128, rank, world)};
+    CB_CATCH
+}
+int cuddh_b200_comm_wrap(void * nccl_comm, int rank, int world, cuddh_comm_t * out)
+{
+    CB_TRY
+    *out = new cuddh_comm_s{comm_wrap(nccl_comm, rank, world)};
+    CB_CATCH
+}
+int cuddh_b200_comm_destroy(cuddh_comm_t c)
+{
+    delete c;
+    return 0;
+}
+int cuddh_b200_comm_allreduce_d(cuddh_comm_t c, double * d_buf, int64_t count, void * stream)
+{
+    CB_TRY
+    comm_allreduce_sum(c ? c->c.get() : nullptr, d_buf, count, S(stream));
+    CB_CATCH
 }
 
 // ---- EnsembleSpace ----
@@ -675,5 +795,110 @@ int cuddh_b200_ddh_get_array(cuddh_ddh_t d, const char * name, void * h_out, int
     CB_CATCH
 }
 double cuddh_b200_ddh_flops(cuddh_ddh_t d) { return d->d->flops(); }
+int cuddh_b200_ddh_kernel_kind(cuddh_ddh_t d) { return d->d->kernel_kind(); }
+
+// ---- DDH across GPUs ----
+int cuddh_b200_ddh_dist_create(cuddh_ddh_t d, cuddh_comm_t comm, int rank, int world, cuddh_ddh_dist_t * out)
+{
+    CB_TRY
+    *out = new cuddh_ddh_dist_s{std::unique_ptr<DdhDist>(new DdhDist(d->d.get(), comm ? comm->c.get() : nullptr, rank, world))};
+    CB_CATCH
+}
+int cuddh_b200_ddh_dist_destroy(cuddh_ddh_dist_t h)
+{
+    delete h;
+    return 0;
+}
+int cuddh_b200_ddh_dist_info(cuddh_ddh_dist_t h, int64_t * info)
+{
+    CB_TRY
+    const DdhDist & D = *h->d;
+    info[0] = D.dom_begin;
+    info[1] = D.dom_end;
+    info[2] = D.n_owned;
+    info[3] = (int64_t)D.send_idx.size();
+    info[4] = (int64_t)D.recv_idx.size();
+    info[5] = (int64_t)D.segs.size();
+    info[6] = D.bytes_per_action();
+    info[7] = 2 * D.n_lambda;
+    CB_CATCH
+}
+int cuddh_b200_ddh_dist_get_array(cuddh_ddh_dist_t h, const char * name, int * h_out, int64_t cap, int64_t * count)
+{
+    CB_TRY
+    const DdhDist & D = *h->d;
+    const std::string n(name ? name : "");
+    std::vector<int> tmp;
+    const std::vector<int> * v = nullptr;
+    if (n == "owner") v = &D.owner;
+    else if (n == "send_idx") v = &D.send_idx;
+    else if (n == "recv_idx") v = &D.recv_idx;
+    else if (n == "segments") { // (5, n_peers): peer, send_off, send_count, recv_off, recv_count
+        for (const PeerSeg & g : D.segs) {
+            tmp.push_back(g.peer);
+            tmp.push_back((int)g.send_off);
+            tmp.push_back((int)g.send_count);
+            tmp.push_back((int)g.recv_off);
+            tmp.push_back((int)g.recv_count);
+        }
+        v = &tmp;
+    }
+    else
+        throw Error(-1, "ddh_dist_get_array: unknown array name " + n);
+    if (count)
+        *count = (int64_t)v->size();
+    if (h_out) {
+        CB_REQUIRE((int64_t)v->size() <= cap, "ddh_dist_get_array: output buffer too small");
+        std::memcpy(h_out, v->data(), v->size() * sizeof(int));
+    }
+    CB_CATCH
+}
+const unsigned char * cuddh_b200_ddh_dist_mask(cuddh_ddh_dist_t h)
+{
+    try {
+        h->d->ensure_device();
+        return h->d->d_mask.p;
+    }
+    catch (const std::exception & e) {
+        set_last_error(e.what());
+        return nullptr;
+    }
+}
+int cuddh_b200_ddh_dist_buffers(cuddh_ddh_dist_t h, void ** d_send, void ** d_recv)
+{
+    CB_TRY
+    h->d->ensure_device();
+    *d_send = h->d->d_send.p;
+    *d_recv = h->d->d_recv.p;
+    CB_CATCH
+}
+int cuddh_b200_ddh_dist_rhs(cuddh_ddh_dist_t h, const double * f, float * b, void * stream)
+{
+    CB_TRY
+    h->d->rhs(f, b, S(stream));
+    CB_CATCH
+}
+int cuddh_b200_ddh_dist_action(cuddh_ddh_dist_t h, const float * x, float * y, void * stream)
+{
+    CB_TRY
+    h->d->action(x, y, S(stream));
+    CB_CATCH
+}
+int cuddh_b200_ddh_dist_apply_T(cuddh_ddh_dist_t h, const float * x, float * t, void * stream)
+{
+    CB_TRY
+    h->d->apply_T(x, t, S(stream));
+    CB_CATCH
+}
+int cuddh_b200_ddh_dist_postprocess(cuddh_ddh_dist_t h, const float * lambda, const double * f, double * u, void * stream)
+{
+    CB_TRY
+    h->d->postprocess(lambda, f, u, S(stream));
+    CB_CATCH
+}
+int cuddh_b200_ddh_dist_as_apply(void * h, const float * x, float * y, void * stream)
+{
+    return cuddh_b200_ddh_dist_action((cuddh_ddh_dist_t)h, x, y, stream);
+}
 
 } // extern "C"

@@ -45,7 +45,20 @@ namespace cb200
             int nt;
             float omega, dt;
             int dom0;          // first subdomain of this launch (subdomain-range sharding across GPUs)
+            int64_t bout_off;  // bout is a table of the local subdomain range only: index of its first entry in the full table
+            float2 * send;     // packed (lambda, mu) pairs for the slots another rank owns: bout entry <= -2 -> pair -2 - entry
         };
+
+        // outgoing trace of one interface node: into the update vector, or (distributed runs) straight into the send buffer
+        __device__ __forceinline__ void write_trace(const DDHArgs & A, const int idx, const float lam_out, const float mu_out)
+        {
+            if (idx >= 0) {
+                A.update[idx] = lam_out;
+                A.update[A.n_lambda + idx] = mu_out;
+            }
+            else if (idx <= -2)
+                A.send[-2 - idx] = make_float2(lam_out, mu_out);
+        }
 
         template <int NB, int NEL>
         __global__ void __launch_bounds__(NB * NB * NEL * NEL)
@@ -189,12 +202,9 @@ namespace cb200
                     A.contrib[2 * o + 1] = (double)(M * v);
                 }
                 if (A.update) {
-                    const int idx = __ldg(A.bout + o);
-                    if (idx >= 0) {
-                        const float S = 2.0f * ai * A.omega;
-                        A.update[idx] = -lambda - S * v;
-                        A.update[A.n_lambda + idx] = -mu + S * u;
-                    }
+                    const int idx = __ldg(A.bout + (o - A.bout_off));
+                    const float S = 2.0f * ai * A.omega;
+                    write_trace(A, idx, -lambda - S * v, -mu + S * u);
                 }
             }
         }
@@ -392,12 +402,9 @@ namespace cb200
                         A.contrib[2 * o + 1] = (double)(M * vv);
                     }
                     if (A.update) {
-                        const int idx = __ldg(A.bout + o);
-                        if (idx >= 0) {
-                            const float S = 2.0f * ai[l][k] * A.omega;
-                            A.update[idx] = -lam[l][k] - S * vv;
-                            A.update[A.n_lambda + idx] = -mu[l][k] + S * u[l][k];
-                        }
+                        const int idx = __ldg(A.bout + (o - A.bout_off));
+                        const float S = 2.0f * ai[l][k] * A.omega;
+                        write_trace(A, idx, -lam[l][k] - S * vv, -mu[l][k] + S * u[l][k]);
                     }
                 }
         }
@@ -419,7 +426,8 @@ namespace cb200
         }
     } // namespace
 
-    void DDH::run(const double * x, double * y, const float * lambda, float * update, cudaStream_t s, int dom_begin, int dom_end)
+    void DDH::run(const double * x, double * y, const float * lambda, float * update, cudaStream_t s, int dom_begin, int dom_end,
+                  const Redirect * redirect)
     {
         if (dom_end < 0)
             dom_end = n_domains;
@@ -448,6 +456,13 @@ namespace cb200
         A.omega = (float)omega;
         A.dt = (float)dt;
         A.dom0 = dom_begin;
+        A.bout_off = 0;
+        A.send = nullptr;
+        if (redirect) {
+            A.bout = redirect->bout;
+            A.bout_off = redirect->bout_off;
+            A.send = redirect->send;
+        }
         const int n_launch = dom_end - dom_begin;
         if (y) {
             if (!d_contrib.p)
@@ -506,6 +521,79 @@ namespace cb200
     void DDH::postprocess(const float * lambda, const double * f, double * u, cudaStream_t s)
     {
         run(f, u, lambda, nullptr, s); // :669-695
+    }
+
+    namespace
+    {
+        // received (lambda, mu) pairs into the owner's vector
+        __global__ void ddh_unpack_kernel(const int64_t n_recv, const int * __restrict__ idx, const float2 * __restrict__ recv,
+                                          const int64_t n_lambda, float * __restrict__ t)
+        {
+            const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+            if (i >= n_recv)
+                return;
+            const float2 v = recv[i];
+            const int k = idx[i];
+            t[k] = v.x;
+            t[n_lambda + k] = v.y;
+        }
+        // mode 0: t <- mask ? t : 0        (rhs: b = T_f(0) on the owned slots)
+        // mode 1: t <- mask ? x - t : 0    (action: lambda - T(lambda), source/DDH.cpp:638)
+        __global__ void ddh_finish_kernel(const int64_t n, const float * __restrict__ x, const unsigned char * __restrict__ mask,
+                                          const int mode, float * __restrict__ t)
+        {
+            const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+            if (i >= n)
+                return;
+            const float tv = t[i];
+            t[i] = mask[i] ? (mode ? x[i] - tv : tv) : 0.0f;
+        }
+    } // namespace
+
+    void DdhDist::exchange_and_finish(const float * x, float * t, int mode, cudaStream_t s)
+    {
+        if (comm && world > 1 && !segs.empty()) {
+            comm_exchange(comm, segs, d_send.p, d_recv.p, sizeof(float2), s);
+            const int64_t nr = (int64_t)recv_idx.size();
+            if (nr > 0) {
+                ddh_unpack_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, s>>>(nr, d_recv_idx.p, d_recv.p, n_lambda, t);
+                CB_LAUNCHED();
+            }
+        }
+        const int64_t n = 2 * n_lambda;
+        ddh_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, x, d_mask.p, mode, t);
+        CB_LAUNCHED();
+    }
+
+    void DdhDist::apply_T(const float * x, float * t, cudaStream_t s)
+    {
+        ensure_device();
+        DDH::Redirect r{d_bout.p, (int64_t)ddh->n1 * ddh->n1 * dom_begin, d_send.p};
+        ddh->run(nullptr, nullptr, x, t, s, dom_begin, dom_end, &r);
+        exchange_and_finish(nullptr, t, 0, s);
+    }
+
+    void DdhDist::action(const float * x, float * y, cudaStream_t s)
+    {
+        ensure_device();
+        DDH::Redirect r{d_bout.p, (int64_t)ddh->n1 * ddh->n1 * dom_begin, d_send.p};
+        ddh->run(nullptr, nullptr, x, y, s, dom_begin, dom_end, &r);
+        exchange_and_finish(x, y, 1, s);
+    }
+
+    void DdhDist::rhs(const double * f, float * b, cudaStream_t s)
+    {
+        ensure_device();
+        DDH::Redirect r{d_bout.p, (int64_t)ddh->n1 * ddh->n1 * dom_begin, d_send.p};
+        ddh->run(f, nullptr, nullptr, b, s, dom_begin, dom_end, &r);
+        exchange_and_finish(nullptr, b, 0, s);
+    }
+
+    void DdhDist::postprocess(const float * lambda, const double * f, double * u, cudaStream_t s)
+    {
+        // every rank adds its subdomains' partition-of-unity contributions; one allreduce, once per solve
+        ddh->run(f, u, lambda, nullptr, s, dom_begin, dom_end);
+        comm_allreduce_sum(comm, u, 2 * ddh->g_ndof, s);
     }
 
     // Subdomain-range variants for sharding across GPUs: rank r runs its contiguous range; `t` / `b` / `u` come out

@@ -2,6 +2,7 @@
 // source/DDH.cpp, source/EnsembleSpace.cpp.
 #pragma once
 #include "common.hpp"
+#include "dist.hpp"
 
 namespace cb200
 {
@@ -62,7 +63,55 @@ namespace cb200
         void get_array(const char * name, void * out, int64_t cap_bytes, int64_t * count) const;
         double flops() const;
 
+        int kernel_kind() const { return (nb == 4 && block == 16 && reg_tiled_ok) ? 1 : 0; } // 1 = register-tiled thread-per-element kernel
+
+        // outgoing-trace redirection of a distributed run (DdhDist): slots owned by another rank go to a packed send buffer
+        struct Redirect
+        {
+            const int * bout = nullptr; // remapped table of the local subdomain range; entry <= -2: pair -2 - entry of `send`
+            int64_t bout_off = 0;       // index of the first local entry in the full (n1*n1, n_domains) table
+            float2 * send = nullptr;
+        };
+        void run(const double * x, double * y, const float * lambda, float * update, cudaStream_t s, int dom_begin = 0, int dom_end = -1,
+                 const Redirect * redirect = nullptr);
+    };
+
+    // contiguous block of subdomains of `rank` (subdomain ids are row-major over the subdomain grid -> row slabs)
+    void subdomain_range(int n_domains, int rank, int world, int & begin, int & end);
+
+    // Path B across GPUs (north_star): subdomains are dealt to the ranks in contiguous row slabs; a lambda slot
+    // lives on ONE rank - the rank of the subdomain that reads it (slots nobody reads: the writer's rank; untouched slots:
+    // rank 0) - and Krylov vectors are distributed accordingly (global length, zero outside the owned slots). The action
+    // kernel writes the traces that cross a slab boundary straight into a packed send buffer (fused pack in the kernel
+    // epilogue); one grouped ncclSend/ncclRecv pair per neighbour moves them; a small unpack kernel drops them into the
+    // owner's vector. Reader / writer of every slot come from the B table (source/DDH.cpp:425-440, cross-point overwrites
+    // included).
+    struct DdhDist
+    {
+        DDH * ddh;
+        const Comm * comm; // may be null (tables only / single rank)
+        int rank, world, dom_begin, dom_end;
+        int64_t n_lambda;
+        std::vector<int> owner;               // (n_lambda) owning rank of slot k (the lambda and mu entries share it)
+        std::vector<int> send_idx, recv_idx;  // slots grouped by peer (ascending peer, ascending slot)
+        std::vector<PeerSeg> segs;            // offsets / counts in (lambda, mu) pairs
+        std::vector<unsigned char> mask;      // (2 n_lambda) 1 = owned
+        int64_t n_owned = 0;
+        // device
+        DevBuf<int> d_bout, d_recv_idx;
+        DevBuf<float2> d_send, d_recv;
+        DevBuf<unsigned char> d_mask;
+        bool on_device = false;
+
+        DdhDist(DDH * ddh, const Comm * comm, int rank, int world);
+        void ensure_device();
+        int64_t bytes_per_action() const { return (int64_t)send_idx.size() * 8; }
+        // t = T(x) on the owned slots (0 elsewhere); x holds valid values on the owned slots
+        void apply_T(const float * x, float * t, cudaStream_t s);
+        void action(const float * x, float * y, cudaStream_t s);      // y = x - T(x) on the owned slots, 0 elsewhere
+        void rhs(const double * f, float * b, cudaStream_t s);        // b = T_f(0) on the owned slots
+        void postprocess(const float * lambda, const double * f, double * u, cudaStream_t s); // u complete on every rank
     private:
-        void run(const double * x, double * y, const float * lambda, float * update, cudaStream_t s, int dom_begin = 0, int dom_end = -1);
+        void exchange_and_finish(const float * x, float * t, int mode, cudaStream_t s);
     };
 } // namespace cb200

@@ -293,7 +293,10 @@ namespace cb200
         reg_tiled_ok = (getenv("CUDDH_B200_DDH_V1") == nullptr);
         for (size_t t = 0; t < g.size() && reg_tiled_ok; ++t) {
             const size_t within = t % ((size_t)3 * nb2);
-            if (within % 3 == 1 ? (g[t] != 0.0f) : (g[t] != g[within]))
+            // a few ulps of slack: uniform_rect vertices are a + i*h, so per-element metrics may differ in the last bit on
+            // domains that are not powers of two; the register-tiled kernel uses element 0's values
+            const float ref = g[within - within % 3] > g[within - within % 3 + 2] ? g[within - within % 3] : g[within - within % 3 + 2];
+            if (within % 3 == 1 ? (std::fabs(g[t]) > 1e-6f * std::fabs(ref)) : (std::fabs(g[t] - g[within]) > 4.0f * 1.1920929e-7f * std::fabs(g[within])))
                 reg_tiled_ok = false;
         }
 
@@ -455,6 +458,96 @@ namespace cb200
             CB_REQUIRE((int64_t)bytes <= cap_bytes, "ddh_get_array: output buffer too small");
             std::memcpy(out, src, bytes);
         }
+    }
+
+    void subdomain_range(int n_domains, int rank, int world, int & begin, int & end)
+    {
+        const int base = n_domains / world, rem = n_domains % world;
+        begin = rank * base + std::min(rank, rem);
+        end = begin + base + (rank < rem ? 1 : 0);
+    }
+
+    DdhDist::DdhDist(DDH * ddh_, const Comm * comm_, int rank_, int world_) : ddh(ddh_), comm(comm_), rank(rank_), world(world_)
+    {
+        CB_REQUIRE(world >= 1 && rank >= 0 && rank < world, "DdhDist: rank out of range");
+        CB_REQUIRE(!comm || (comm->rank == rank && comm->world == world), "DdhDist: communicator rank / size mismatch");
+        const DDH & D = *ddh;
+        n_lambda = D.n_lambda;
+        const int nd = D.n1 * D.n1;
+        subdomain_range(D.n_domains, rank, world, dom_begin, dom_end);
+        std::vector<int> dom_rank((size_t)D.n_domains);
+        for (int r = 0; r < world; ++r) {
+            int a, b;
+            subdomain_range(D.n_domains, r, world, a, b);
+            for (int p = a; p < b; ++p)
+                dom_rank[p] = r;
+        }
+        // reader / writer rank of every slot: slot hg_bin(., p) is read and slot hg_bout(., p) written by subdomain p; later
+        // subdomains overwrite earlier ones, exactly as the lambda map itself is built (source/DDH.cpp:425-440)
+        std::vector<int> reader((size_t)n_lambda, -1), writer((size_t)n_lambda, -1);
+        for (int p = 0; p < D.n_domains; ++p)
+            for (int at = 0; at < nd; ++at) {
+                const size_t o = (size_t)at + (size_t)nd * p;
+                if (D.hg_bin[o] >= 0)
+                    reader[D.hg_bin[o]] = dom_rank[p];
+                if (D.hg_bout[o] >= 0)
+                    writer[D.hg_bout[o]] = dom_rank[p];
+            }
+        owner.resize((size_t)n_lambda);
+        mask.assign(2 * (size_t)n_lambda, 0);
+        for (int64_t k = 0; k < n_lambda; ++k) {
+            owner[k] = reader[k] >= 0 ? reader[k] : (writer[k] >= 0 ? writer[k] : 0);
+            if (owner[k] == rank) {
+                mask[k] = mask[n_lambda + k] = 1;
+                ++n_owned;
+            }
+        }
+        // exchange lists per peer: what I write for q, what q writes for me (both ascending in the slot index, so the two
+        // sides of a pair agree on the packing order without talking to each other)
+        std::vector<std::vector<int>> snd(world), rcv(world);
+        for (int64_t k = 0; k < n_lambda; ++k) {
+            if (writer[k] == rank && owner[k] != rank)
+                snd[owner[k]].push_back((int)k);
+            if (owner[k] == rank && writer[k] >= 0 && writer[k] != rank)
+                rcv[writer[k]].push_back((int)k);
+        }
+        for (int q = 0; q < world; ++q) {
+            if (snd[q].empty() && rcv[q].empty())
+                continue;
+            PeerSeg g;
+            g.peer = q;
+            g.send_off = (int64_t)send_idx.size();
+            g.send_count = (int64_t)snd[q].size();
+            g.recv_off = (int64_t)recv_idx.size();
+            g.recv_count = (int64_t)rcv[q].size();
+            send_idx.insert(send_idx.end(), snd[q].begin(), snd[q].end());
+            recv_idx.insert(recv_idx.end(), rcv[q].begin(), rcv[q].end());
+            segs.push_back(g);
+        }
+    }
+
+    void DdhDist::ensure_device()
+    {
+        if (on_device)
+            return;
+        const DDH & D = *ddh;
+        const int nd = D.n1 * D.n1;
+        // outgoing table of the local subdomains with the foreign slots redirected to their position in the send buffer
+        std::vector<int> pos((size_t)n_lambda, -1);
+        for (size_t i = 0; i < send_idx.size(); ++i)
+            pos[send_idx[i]] = (int)i;
+        std::vector<int> bl((size_t)nd * std::max(dom_end - dom_begin, 0));
+        for (int p = dom_begin; p < dom_end; ++p)
+            for (int at = 0; at < nd; ++at) {
+                const int k = D.hg_bout[(size_t)at + (size_t)nd * p];
+                bl[(size_t)at + (size_t)nd * (p - dom_begin)] = (k >= 0 && pos[k] >= 0) ? (-2 - pos[k]) : k;
+            }
+        d_bout.upload(bl);
+        d_recv_idx.upload(recv_idx);
+        d_send.alloc(std::max<size_t>(send_idx.size(), 1));
+        d_recv.alloc(std::max<size_t>(recv_idx.size(), 1));
+        d_mask.upload(mask);
+        on_device = true;
     }
 
     double DDH::flops() const

@@ -1,6 +1,7 @@
 // BLAS-1 + GMRES declarations (see linalg.cu).
 #pragma once
 #include "common.hpp"
+#include "dist.hpp"
 #include <vector>
 
 namespace cb200
@@ -12,18 +13,41 @@ namespace cb200
     template <typename T> T dot(int64_t n, const T * x, const T * y, cudaStream_t s);   // blocks the host (returns the scalar)
     template <typename T> T dist(int64_t n, const T * x, const T * y, cudaStream_t s);
 
-    template <typename T> using ApplyFn = void (*)(void * ctx, const T * x, T * y);
+    // y = A x enqueued on stream s; non-zero return aborts the solve with that status
+    template <typename T> using ApplyFn = int (*)(void * ctx, const T * x, T * y, cudaStream_t s);
 
     struct GmresResult
     {
         bool success;
         int num_iter, num_matvec;
         std::vector<double> res_norm, time;
+        // vector traffic of the orthogonalisation (bytes moved by the Gram-Schmidt kernels) and its device time, for bench.py
+        double orth_bytes = 0, orth_ms = 0;
+        int reorth = 0;     // CGS: second passes taken (cancellation)
+        int allreduces = 0; // distributed runs
+    };
+
+    enum GmresOrth
+    {
+        ORTH_MGS = 0, // modified Gram-Schmidt, the reference's arithmetic (source/gmres.cpp:167-172): k+2 fused passes per step
+        ORTH_CGS2 = 1 // classical Gram-Schmidt, all inner products in one pass + one update pass; second round on cancellation
+    };
+
+    struct GmresOptions
+    {
+        int orth = ORTH_MGS;
+        const Comm * comm = nullptr;             // distributed vectors: inner products are summed over the ranks
+        const unsigned char * d_mask = nullptr;  // 1 = this rank owns the entry (counted in inner products), 0 = mirror copy / foreign slot
+        bool time_orth = false;                  // record CUDA-event time of the orthogonalisation kernels (adds two event records per step)
     };
 
     // Restarted GMRES(m) with the reference's control flow (source/gmres.cpp:91-235). A is a callback that
-    // must enqueue y = A x on stream s (or on a stream ordered with it, e.g. the legacy default stream).
+    // must enqueue y = A x on the stream it is handed.
     template <typename T>
     GmresResult gmres(int64_t n, T * x, ApplyFn<T> A, void * ctx, const T * b, int m, int maxit, T tol, int verbose,
-                      double max_seconds, cudaStream_t s);
+                      double max_seconds, cudaStream_t s, const GmresOptions & opt = GmresOptions());
+
+    // process-wide default of GmresOptions::orth for the entry points without an options argument (set_option "gmres_orth")
+    int default_gmres_orth();
+    void set_default_gmres_orth(int v);
 } // namespace cb200

@@ -31,6 +31,8 @@ namespace cb200
     namespace
     {
         constexpr int MAXQ = 32;
+        constexpr int MAX_DEVICES = 64;
+        std::atomic<int> g_max_ctas{0};
 
         struct PlanDev
         {
@@ -891,24 +893,30 @@ namespace cb200
                     }
                 }
             auto kern = volume_action_kernel<NB, NQ, STIFF>;
-            static bool attr_set = false;
-            static size_t attr_smem = 0;
-            if (!attr_set || smem > attr_smem) {
+            struct PerDevice
+            {
+                size_t attr_smem = 0;
+                int pf_dist = -1;
+            };
+            static PerDevice per_device[MAX_DEVICES];
+            int dev = 0;
+            cudaGetDevice(&dev);
+            CB_REQUIRE(dev >= 0 && dev < MAX_DEVICES, "device ordinal out of range");
+            PerDevice & pdv = per_device[dev];
+            if (smem > pdv.attr_smem) {
                 CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)49152)));
                 // several CTAs per SM are needed to overlap the staging / assembly phases of one patch with the
                 // contractions of another: ask for the largest shared-memory carve-out
                 CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-                attr_set = true;
-                attr_smem = std::max(smem, (size_t)49152);
+                pdv.attr_smem = std::max(smem, (size_t)49152);
             }
-            static int pf_dist = -1;
-            if (pf_dist < 0) { // one scheduling wave = resident CTAs per SM x SM count
-                int dev = 0, sms = 148, occ = 1;
-                cudaGetDevice(&dev);
+            if (pdv.pf_dist < 0) { // one scheduling wave = resident CTAs per SM x SM count
+                int sms = 148, occ = 1;
                 cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nwarps * 32, smem);
-                pf_dist = env_int("CUDDH_B200_PFDIST", std::max(occ, 1) * sms);
+                pdv.pf_dist = env_int("CUDDH_B200_PFDIST", std::max(occ, 1) * sms);
             }
+            const int pf_dist = pdv.pf_dist;
             kern<<<(unsigned)plan.n_patches, nwarps * 32, smem, s>>>(tab, pd, op.d_G.p, x, y, op.d_partial.p, c, accumulate,
                                                                        plan.max_pdof, (int)plan.n_patches, pf_dist);
             CB_LAUNCHED();
@@ -946,18 +954,22 @@ namespace cb200
             if constexpr (NQ2 > 0)
                 fill_tables(tab2, *op2);
             auto kern = volume_action_ws<NB, NQ, STIFF, NQ2, RING>;
-            static int grid = 0;
+            // one wave of resident CTAs, cached per device (function attributes are per device too)
+            static int grid_of_device[MAX_DEVICES] = {};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            CB_REQUIRE(dev >= 0 && dev < MAX_DEVICES, "device ordinal out of range");
+            int & grid = grid_of_device[dev];
             if (!grid) {
                 CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)49152)));
                 CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-                int dev = 0, sms = 148, occ = 1;
-                cudaGetDevice(&dev);
+                int sms = 148, occ = 1;
                 cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
                 CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
-                grid = std::max(1, occ) * sms;
+                int gsz = std::max(1, occ) * sms;
                 if (NQ2 > 0) { // launched as clusters of two CTAs: ask how many of those are co-resident
                     cudaLaunchConfig_t cfg = {};
-                    cfg.gridDim = dim3((unsigned)grid);
+                    cfg.gridDim = dim3((unsigned)gsz);
                     cfg.blockDim = dim3(256);
                     cfg.dynamicSmemBytes = smem;
                     cudaLaunchAttribute at[1];
@@ -969,13 +981,16 @@ namespace cb200
                     cfg.numAttrs = 1;
                     int ncl = 0;
                     if (cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg) == cudaSuccess && ncl > 0)
-                        grid = std::min(grid, 2 * ncl);
+                        gsz = std::min(gsz, 2 * ncl);
                     else
                         cudaGetLastError();
                 }
+                grid = gsz;
             }
             const int nf = std::max(args.n_fields, 1);
-            const int g = (int)std::min<int64_t>(grid / nf, plan.n_patches) * nf;
+            const int cap = max_persistent_ctas(); // test / tuning knob: fewer CTAs = more patches per persistent CTA
+            const int wave = cap > 0 ? std::max(nf, std::min(grid, cap)) : grid;
+            const int g = (int)std::min<int64_t>(wave / nf, plan.n_patches) * nf;
             if (nf > 1) { // one cluster = the CTAs that walk the same patches, one field each
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = dim3((unsigned)g);
@@ -1095,6 +1110,9 @@ namespace cb200
             return nullptr;
         }
     } // namespace
+
+    int max_persistent_ctas() { return g_max_ctas.load(); }
+    void set_max_persistent_ctas(int n) { g_max_ctas.store(n > 0 ? n : 0); }
 
     void VolumeOp::apply(double c, int accumulate, const double * x, double * y, cudaStream_t s, int phases)
     {

@@ -55,6 +55,10 @@ namespace cb200
     void face_prolong(FaceSpace * fs, const double * x, double * y, cudaStream_t s);
     void face_orth(FaceSpace * fs, double * x, cudaStream_t s);
 
+    // upper bound on the CTAs of the persistent kernels (0 = one full wave of resident CTAs); test / tuning knob
+    int max_persistent_ctas();
+    void set_max_persistent_ctas(int n);
+
     // examples/Helmholtz.hpp:28-56 composite on [u;v]
     struct HelmholtzOp
     {

@@ -26,8 +26,10 @@ namespace cuddh
 
     namespace detail
     {
-        inline void apply_double(void * ctx, const double * x, double * y) { static_cast<const Operator *>(ctx)->action(x, y); }
-        inline void apply_float(void * ctx, const float * x, float * y) { static_cast<const SinglePrecisionOperator *>(ctx)->action(x, y); }
+        // Operator::action has no stream argument (include/Operator.hpp:12-16): user operators enqueue on the legacy default
+        // stream, which is also the stream handed to the library below (nullptr), so the ordering is the reference's.
+        inline int apply_double(void * ctx, const double * x, double * y, void *) { static_cast<const Operator *>(ctx)->action(x, y); return 0; }
+        inline int apply_float(void * ctx, const float * x, float * y, void *) { static_cast<const SinglePrecisionOperator *>(ctx)->action(x, y); return 0; }
 
         inline solver_out unpack(const cuddh_solver_out & so, const std::vector<double> & res, const std::vector<double> & tim)
         {

@@ -153,8 +153,10 @@ int cuddh_b200_fill_f(int64_t n, float a, float * x, void * stream);
 int cuddh_b200_fill_i(int64_t n, int a, int * x, void * stream);
 
 /* ---- gmres: include/gmres.hpp:14-36 ------------------------------------------------------------- */
-typedef void (*cuddh_apply_d_fn)(void * ctx, const double * x, double * y); /* must enqueue y = A x (device pointers) */
-typedef void (*cuddh_apply_f_fn)(void * ctx, const float * x, float * y);
+/* Operator callback: must enqueue y = A x (device pointers) on `stream` (the stream gmres itself runs its vector kernels on)
+ * and return 0; a non-zero return aborts the solve, which then returns that status. */
+typedef int (*cuddh_apply_d_fn)(void * ctx, const double * x, double * y, void * stream);
+typedef int (*cuddh_apply_f_fn)(void * ctx, const float * x, float * y, void * stream);
 typedef struct
 {
     int success;      /* solver_out.success */
@@ -171,8 +173,54 @@ int cuddh_b200_gmres_f(int64_t n, float * x, cuddh_apply_f_fn A, void * A_ctx, c
                        int verbose, double max_seconds, cuddh_solver_out * out, double * h_res_norm, double * h_time, int cap,
                        void * stream);
 /* convenience trampolines so that a cuddh_operator_t / cuddh_ddh_t can be handed to gmres without a host callback */
-void cuddh_b200_operator_as_apply(void * op_handle, const double * x, double * y);
-void cuddh_b200_ddh_as_apply(void * ddh_handle, const float * x, float * y);
+int cuddh_b200_operator_as_apply(void * op_handle, const double * x, double * y, void * stream);
+int cuddh_b200_ddh_as_apply(void * ddh_handle, const float * x, float * y, void * stream);
+
+/* ---- communicator: one process per GPU (new: the reference is single-GPU). NCCL is bound at run time (dlopen). ---- */
+typedef struct cuddh_comm_s * cuddh_comm_t;
+/* 128-byte ncclUniqueId: call on one rank, hand the bytes to every rank through the host bootstrap (MPI_Bcast, torch.distributed, ...) */
+int cuddh_b200_comm_unique_id(unsigned char * id128);
+/* ncclCommInitRank on the current device (collective over the `world` ranks) */
+int cuddh_b200_comm_create(const unsigned char * id128, int rank, int world, cuddh_comm_t * out);
+/* adopt a caller-owned ncclComm_t (not destroyed with the handle) */
+int cuddh_b200_comm_wrap(void * nccl_comm, int rank, int world, cuddh_comm_t * out);
+int cuddh_b200_comm_destroy(cuddh_comm_t c);
+int cuddh_b200_comm_allreduce_d(cuddh_comm_t c, double * d_buf, int64_t count, void * stream); /* in-place sum, stream-ordered */
+
+/* gmres with options: orthogonalisation mode, distributed vectors.
+ *   orth   0 = modified Gram-Schmidt: the reference's arithmetic (source/gmres.cpp:167-172), one fused kernel per basis vector;
+ *          1 = classical Gram-Schmidt: all inner products in one pass + one update pass, second round on cancellation;
+ *         -1 = library default (set_option "gmres_orth", initially 0).
+ *   comm / d_mask: vectors are distributed over the ranks of `comm`; inner products count the entries with d_mask[i] != 0
+ *          (device array of n bytes: 1 = this rank owns entry i) and are summed with one ncclAllReduce per pass. */
+typedef struct
+{
+    int orth;
+    cuddh_comm_t comm;
+    const unsigned char * d_mask;
+    int time_orth; /* != 0: record the device time of the orthogonalisation kernels (stats.orth_ms) */
+} cuddh_gmres_options;
+typedef struct
+{
+    double orth_bytes; /* vector bytes moved by the orthogonalisation kernels */
+    double orth_ms;    /* their device time (time_orth) */
+    int reorth;        /* orth 1: second rounds taken */
+    int allreduces;
+} cuddh_gmres_stats;
+int cuddh_b200_gmres_d_ex(int64_t n, double * x, cuddh_apply_d_fn A, void * A_ctx, const double * b, cuddh_apply_d_fn P, void * P_ctx,
+                          int m, int maxit, double tol, int verbose, double max_seconds, const cuddh_gmres_options * opts,
+                          cuddh_solver_out * out, double * h_res_norm, double * h_time, int cap, cuddh_gmres_stats * stats, void * stream);
+int cuddh_b200_gmres_f_ex(int64_t n, float * x, cuddh_apply_f_fn A, void * A_ctx, const float * b, int m, int maxit, float tol,
+                          int verbose, double max_seconds, const cuddh_gmres_options * opts, cuddh_solver_out * out, double * h_res_norm,
+                          double * h_time, int cap, cuddh_gmres_stats * stats, void * stream);
+
+/* ---- tuning / test knobs -------------------------------------------------------------------------
+ * "gmres_orth": default orthogonalisation of gmres (0 MGS, 1 CGS2);
+ * "max_ctas":   upper bound on the CTAs of the persistent operator kernels (0 = one full wave; tests use a small value to
+ *               force many patches per CTA on small meshes);
+ * get_option also answers "nccl_available". Unknown names: set returns non-zero, get returns -1. */
+int cuddh_b200_set_option(const char * name, int64_t value);
+int64_t cuddh_b200_get_option(const char * name);
 
 /* ---- EnsembleSpace: include/EnsembleSpace.hpp:13-140 (host index maps of a labelled decomposition) ------------- */
 typedef struct cuddh_ensemble_s * cuddh_ensemble_t;
@@ -207,6 +255,30 @@ int cuddh_b200_ddh_info(cuddh_ddh_t d, int64_t * info, double * dt);
 int cuddh_b200_ddh_get_array(cuddh_ddh_t d, const char * name, void * h_out, int64_t cap_bytes, int64_t * count);
 /* algorithmic FP32 flops of one action */
 double cuddh_b200_ddh_flops(cuddh_ddh_t d);
+/* which kernel serves this handle: 1 = register-tiled thread-per-element kernel (n_basis 4, block 16, uniform metric), 0 = generic */
+int cuddh_b200_ddh_kernel_kind(cuddh_ddh_t d);
+
+/* ---- DDH across GPUs (new; SURVEY §8e path B): subdomain row slabs, one per rank --------------------------------
+ * Vectors keep the global length DDH::size(); a lambda slot is OWNED by the rank of the subdomain that reads it and is zero
+ * on every other rank (use cuddh_b200_ddh_dist_mask as d_mask of cuddh_b200_gmres_f_ex). rhs / action run this rank's
+ * subdomains; traces written for a slot another rank owns leave the kernel through a packed send buffer (pack fused into
+ * the kernel epilogue) and travel with one grouped ncclSend/ncclRecv per neighbour on `stream`.
+ * comm == NULL: partition tables only (host; for tests) or a single rank. */
+typedef struct cuddh_ddh_dist_s * cuddh_ddh_dist_t;
+int cuddh_b200_ddh_dist_create(cuddh_ddh_t d, cuddh_comm_t comm, int rank, int world, cuddh_ddh_dist_t * out);
+int cuddh_b200_ddh_dist_destroy(cuddh_ddh_dist_t h);
+/* info[0..7] = dom_begin, dom_end, owned slots, slots sent, slots received, neighbours, bytes sent per action, vector length */
+int cuddh_b200_ddh_dist_info(cuddh_ddh_dist_t h, int64_t * info);
+/* host tables: "owner" (n_lambda), "send_idx", "recv_idx" (grouped by peer), "segments" (5, neighbours): peer, send_off,
+ * send_count, recv_off, recv_count in (lambda, mu) pairs */
+int cuddh_b200_ddh_dist_get_array(cuddh_ddh_dist_t h, const char * name, int * h_out, int64_t cap, int64_t * count);
+const unsigned char * cuddh_b200_ddh_dist_mask(cuddh_ddh_dist_t h);            /* DEVICE, DDH::size() bytes */
+int cuddh_b200_ddh_dist_buffers(cuddh_ddh_dist_t h, void ** d_send, void ** d_recv); /* packed (lambda, mu) float pairs; tests */
+int cuddh_b200_ddh_dist_rhs(cuddh_ddh_dist_t h, const double * f, float * b, void * stream);
+int cuddh_b200_ddh_dist_action(cuddh_ddh_dist_t h, const float * x, float * y, void * stream);
+int cuddh_b200_ddh_dist_apply_T(cuddh_ddh_dist_t h, const float * x, float * t, void * stream);
+int cuddh_b200_ddh_dist_postprocess(cuddh_ddh_dist_t h, const float * lambda, const double * f, double * u, void * stream);
+int cuddh_b200_ddh_dist_as_apply(void * dist_handle, const float * x, float * y, void * stream); /* cuddh_apply_f_fn */
 
 #ifdef __cplusplus
 }
