@@ -164,6 +164,18 @@ class Mesh2D:
         check(load().cuddh_b200_mesh_boundary_edges(self._h, _vp(b)))
         return b
 
+    def vertices(self):
+        """(n_nodes, 2) vertex coordinates"""
+        xy = np.zeros((self.n_nodes(), 2))
+        check(load().cuddh_b200_mesh_vertices(self._h, _vp(xy)))
+        return xy
+
+    def elements(self):
+        """(n_elem, 4) CCW corner vertex ids"""
+        el = np.zeros((self.n_elem(), 4), np.int32)
+        check(load().cuddh_b200_mesh_elements(self._h, _vp(el)))
+        return el
+
     def min_h(self):
         a, b = C.c_double(), C.c_double()
         check(load().cuddh_b200_mesh_h(self._h, C.byref(a), C.byref(b)))
@@ -215,6 +227,19 @@ class H1Space:
         check(load().cuddh_b200_h1space_physical_coordinates(self._h, _vp(xy)))
         return xy
 
+    def element_metrics(self, xq, which):
+        """Mesh2D::ElementMetricCollection (include/Mesh2D.hpp:33-41) on the tensor grid of the 1-D points xq, as a CUDA tensor:
+        which = "jacobians" (n_elem, nq, nq, 2, 2) [el, j, i, c, r] = J(r, c, i, j, el); "measures" (n_elem, nq, nq);
+        "physical_coordinates" (n_elem, nq, nq, 2)."""
+        import torch
+        xq = _np(xq, np.float64)
+        nq, nel = len(xq), self._mesh.n_elem()
+        k = {"jacobians": 0, "measures": 1, "physical_coordinates": 2}[which]
+        shape = {0: (nel, nq, nq, 2, 2), 1: (nel, nq, nq), 2: (nel, nq, nq, 2)}[k]
+        out = torch.empty(shape, dtype=torch.float64, device="cuda")
+        check(load().cuddh_b200_element_metrics(self._h, nq, _vp(xq), k, _ptr(out), _stream()))
+        return out
+
 
 class FaceSpace:
     """include/H1Space.hpp:69-147."""
@@ -222,6 +247,7 @@ class FaceSpace:
     def __init__(self, fem, faces):
         self.fem = fem
         faces = _np(faces, np.int32)
+        self._faces = faces
         self._nf = len(faces)
         self._h = C.c_void_p()
         check(load().cuddh_b200_facespace_create(fem._h, len(faces), _vp(faces), C.byref(self._h)))
@@ -234,6 +260,9 @@ class FaceSpace:
 
     def n_faces(self):
         return self._nf
+
+    def faces(self):
+        return self._faces
 
     def h1_space(self):
         return self.fem
@@ -362,6 +391,70 @@ class Helmholtz(Operator):
             raise capi.CuddhError("Helmholtz::action(c, x, y) not implemented")
         x, y = args
         check(load().cuddh_b200_operator_apply(self._h, 1.0, 0, _ptr(x), _ptr(y), _stream()))
+
+
+class LinearFunctional:
+    """include/LinearFunctional.hpp:11-37: F[i] (+)= c (f, phi_i). LinearFunctional(fem): collocated rule on the basis' own
+    Gauss-Lobatto nodes; LinearFunctional(fem, quad): quad.size()-point rule. f is called with CUDA tensors (x, y) of the
+    quadrature-point coordinates and returns a tensor of the same shape (the reference takes a __device__ lambda)."""
+
+    def __init__(self, fem, quad=None):
+        self.fem = fem
+        self.fast = quad is None
+        if quad is None:
+            self.x, self.w = fem.basis().quadrature()
+            self.P = None
+        else:
+            self.x, self.w = np.array(quad.x(), np.float64), np.array(quad.w(), np.float64)
+            self.P = np.ascontiguousarray(fem.basis().eval(self.x).T)  # column-major (nq, nb)
+
+    def action(self, *args):
+        import torch
+        c, f, F = (1.0,) + tuple(args) if len(args) == 2 else args
+        if len(args) == 2:
+            F.zero_()
+        X = self.fem.element_metrics(self.x, "physical_coordinates")
+        detJ = self.fem.element_metrics(self.x, "measures")
+        w = torch.as_tensor(self.w, device="cuda")
+        g = (w[None, :, None] * w[None, None, :] * detJ * f(X[..., 0], X[..., 1])).contiguous()
+        check(load().cuddh_b200_linear_functional_assemble(self.fem._h, len(self.x), None if self.P is None else _vp(self.P), _ptr(g),
+                                                           float(c), _ptr(F), _stream()))
+
+
+class FaceLinearFunctional:
+    """include/FaceLinearFunctional.hpp:13-39: F[i] (+)= c <f, phi_i> over the faces of a FaceSpace (FaceSpace vectors). Face
+    points: the side of edge->elements[0] the face lies on, in increasing reference coordinate (source/H1Space.cpp:151-157),
+    measure = length / 2 (StraightEdge)."""
+
+    def __init__(self, fs, quad=None):
+        self.fs = fs
+        fem = fs.fem
+        if quad is None:
+            self.x, self.w = fem.basis().quadrature()
+            self.P = None
+        else:
+            self.x, self.w = np.array(quad.x(), np.float64), np.array(quad.w(), np.float64)
+            self.P = np.ascontiguousarray(fem.basis().eval(self.x).T)
+        mesh = fem.mesh()
+        E = mesh.edges()[fs.faces()]
+        V, EL = mesh.vertices(), mesh.elements()
+        side_nodes = np.array([[0, 1], [1, 2], [3, 2], [0, 3]])
+        el, sd = E[:, 2], E[:, 4]
+        v0 = V[EL[el, side_nodes[sd, 0]]]
+        v1 = V[EL[el, side_nodes[sd, 1]]]
+        t = 0.5 * (1.0 + self.x)
+        self.X = v0[:, None, :] + t[None, :, None] * (v1 - v0)[:, None, :]  # (n_faces, nq, 2)
+        self.meas = 0.5 * np.linalg.norm(v1 - v0, axis=1)
+
+    def action(self, *args):
+        import torch
+        c, f, F = (1.0,) + tuple(args) if len(args) == 2 else args
+        if len(args) == 2:
+            F.zero_()
+        X = torch.as_tensor(self.X, device="cuda")
+        g = (f(X[..., 0], X[..., 1]) * torch.as_tensor(self.w, device="cuda")[None, :] * torch.as_tensor(self.meas, device="cuda")[:, None]).contiguous()
+        check(load().cuddh_b200_face_linear_functional_assemble(self.fs._h, len(self.x), None if self.P is None else _vp(self.P), _ptr(g),
+                                                                float(c), _ptr(F), _stream()))
 
 
 class SolverOut:
@@ -534,6 +627,52 @@ class DDH:
 
     def _as_apply(self):
         return C.cast(load().cuddh_b200_ddh_as_apply, C.c_void_p), self._h
+
+
+class HelmholtzSlab:
+    """Path A across GPUs in the library (cuddh_b200_slab_*): the Helmholtz composite on this rank's slab + the interface-row
+    exchange with the two neighbours (pack fused into the face-mass launch, one grouped ncclSend/ncclRecv, add)."""
+
+    def __init__(self, op, comm, rank, world, fem, fs_phys, bottom_dofs, top_dofs):
+        self.op, self.comm, self.rank, self.world, self.fem = op, comm, rank, world, fem
+        b, t = _np(bottom_dofs, np.int32), _np(top_dofs, np.int32)
+        self._h = C.c_void_p()
+        check(load().cuddh_b200_slab_create(comm._h if comm is not None else None, rank, world, fem._h, fs_phys._h if fs_phys is not None else None,
+                                            len(b), _vp(b), len(t), _vp(t), C.byref(self._h)))
+        check(load().cuddh_b200_slab_bind(self._h, op._h))
+        self.n = 2 * fem.size()
+
+    def __del__(self):
+        _destroy("cuddh_b200_slab_destroy", self)
+
+    def bytes_per_apply(self):
+        return int(load().cuddh_b200_slab_bytes(self._h))
+
+    def apply(self, x, y):
+        check(load().cuddh_b200_helmholtz_apply_slab(self.op._h, self._h, _ptr(x), _ptr(y), _stream()))
+
+    def exchange(self, y):
+        check(load().cuddh_b200_slab_exchange(self._h, _ptr(y), _stream()))
+
+    def mask(self):
+        import torch
+        p = load().cuddh_b200_slab_mask(self._h)
+        if not p:
+            check(-1)
+        n = self.n
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (int(p), False), "version": 2}
+        t = torch.as_tensor(_Raw(), device="cuda")
+        t._keepalive = self
+        return t
+
+    def _as_apply(self):
+        return C.cast(load().cuddh_b200_slab_as_apply, C.c_void_p), self._h
+
+    def solve(self, b, x, m=20, maxit=1000, tol=1e-6, orth=-1):
+        """distributed FP64 GMRES(m) in the library on the slab partition: masked inner products + one NCCL allreduce per pass"""
+        return gmres(self.n, x, self, b, m, maxit, tol, orth=orth, comm=self.comm, mask=self.mask())
 
 
 class DDHDist:

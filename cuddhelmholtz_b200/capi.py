@@ -127,6 +127,14 @@ def _proto(lib):
         "cuddh_b200_comm_wrap": (C.c_int, [c_vp, C.c_int, C.c_int, P(c_vp)]),
         "cuddh_b200_comm_destroy": (C.c_int, [c_vp]),
         "cuddh_b200_comm_allreduce_d": (C.c_int, [c_vp, c_dp, c_i64, c_vp]),
+        "cuddh_b200_slab_create": (C.c_int, [c_vp, C.c_int, C.c_int, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, P(c_vp)]),
+        "cuddh_b200_slab_destroy": (C.c_int, [c_vp]),
+        "cuddh_b200_slab_bytes": (c_i64, [c_vp]),
+        "cuddh_b200_slab_exchange": (C.c_int, [c_vp, c_dp, c_vp]),
+        "cuddh_b200_slab_mask": (c_vp, [c_vp]),
+        "cuddh_b200_helmholtz_apply_slab": (C.c_int, [c_vp, c_vp, c_dp, c_dp, c_vp]),
+        "cuddh_b200_slab_bind": (C.c_int, [c_vp, c_vp]),
+        "cuddh_b200_slab_as_apply": (C.c_int, [c_vp, c_dp, c_dp, c_vp]),
         "cuddh_b200_ddh_kernel_kind": (C.c_int, [c_vp]),
         "cuddh_b200_ddh_dist_create": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, P(c_vp)]),
         "cuddh_b200_ddh_dist_destroy": (C.c_int, [c_vp]),

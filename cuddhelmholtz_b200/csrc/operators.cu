@@ -755,18 +755,43 @@ namespace cb200
             y[yi] = accumulate ? (y[yi] + sum) : sum;
         }
 
-        // the two boundary terms of the Helmholtz composite in one launch: blockIdx.y = 0: y[0:n] += c H x[n:2n]; 1: y[n:2n] += c H x[0:n]
+        // interface rows of a slab (SlabHalo): position of (field f, row entry e) in the send / recv buffers
+        struct HaloDev
+        {
+            const int * row_dof;    // (n_bottom + n_top)
+            const int * face_entry; // per face DOF: row entry or -1
+            const int * plain;      // row entries packed by plain copy
+            double * send;
+            int64_t n_bottom, n_top, n_plain;
+        };
+        __device__ __forceinline__ int64_t halo_pos(const HaloDev & h, const int f, const int e)
+        {
+            return e < h.n_bottom ? f * h.n_bottom + e : 2 * h.n_bottom + f * h.n_top + (e - h.n_bottom);
+        }
+
+        // the two boundary terms of the Helmholtz composite in one launch: blockIdx.y = 0: y[0:n] += c H x[n:2n]; 1: y[n:2n] += c H x[0:n].
+        // With a halo (slab of a partitioned mesh) the same launch packs the two interface rows of the finished result: the
+        // thread that adds the face term of a corner node writes that node's final value, blocks beyond the face DOFs copy the rest.
         __global__ void facemass_pair_kernel(const int64_t fdof, const int NB, const int NQ, const double * __restrict__ P,
                                              const double * __restrict__ a, const int * __restrict__ If,
                                              const int * __restrict__ inc_ptr, const int * __restrict__ inc,
                                              const int * __restrict__ proj, const double c, const int64_t n,
-                                             const double * __restrict__ x, double * __restrict__ y)
+                                             const double * __restrict__ x, double * __restrict__ y, const HaloDev halo, const int face_blocks)
         {
+            const int fld = blockIdx.y;
+            double * yd = fld == 0 ? y : y + n;
+            if ((int)blockIdx.x >= face_blocks) { // pack-only part
+                const int64_t k = (int64_t)(blockIdx.x - face_blocks) * blockDim.x + threadIdx.x;
+                if (k < halo.n_plain) {
+                    const int e = halo.plain[k];
+                    halo.send[halo_pos(halo, fld, e)] = yd[halo.row_dof[e]];
+                }
+                return;
+            }
             const int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
             if (d >= fdof)
                 return;
-            const double * xs = blockIdx.y == 0 ? x + n : x;
-            double * yd = blockIdx.y == 0 ? y : y + n;
+            const double * xs = fld == 0 ? x + n : x;
             double sum = 0.0;
             for (int t = inc_ptr[d]; t < inc_ptr[d + 1]; ++t) {
                 const int fk = inc[t];
@@ -782,7 +807,27 @@ namespace cb200
                 }
                 sum += c * Mu;
             }
-            yd[proj[d]] += sum;
+            const double v = yd[proj[d]] + sum;
+            yd[proj[d]] = v;
+            if (halo.face_entry) {
+                const int e = halo.face_entry[d];
+                if (e >= 0)
+                    halo.send[halo_pos(halo, fld, e)] = v;
+            }
+        }
+
+        // stand-alone pack of every row entry (SlabHalo::exchange) and the add of the received rows
+        __global__ void halo_pack_kernel(const HaloDev halo, const int64_t n, const double * __restrict__ y)
+        {
+            const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+            if (e < halo.n_bottom + halo.n_top)
+                halo.send[halo_pos(halo, blockIdx.y, (int)e)] = y[blockIdx.y * n + halo.row_dof[e]];
+        }
+        __global__ void halo_add_kernel(const HaloDev halo, const double * __restrict__ recv, const int64_t n, double * __restrict__ y)
+        {
+            const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+            if (e < halo.n_bottom + halo.n_top)
+                y[blockIdx.y * n + halo.row_dof[e]] += recv[halo_pos(halo, blockIdx.y, (int)e)]; // own + received: same sum on both sides
         }
 
         __global__ void setup_facemass_kernel(const int64_t nf, const int NB, const int NQ, const double * __restrict__ wq,
@@ -1324,13 +1369,116 @@ namespace cb200
         CB_LAUNCHED();
     }
 
-    void FaceMassOp::apply_h1_pair(double c, const double * x, double * y, int64_t n, cudaStream_t s)
+    namespace
     {
-        if (fs->fdof == 0)
+        HaloDev halo_dev(SlabHalo & h)
+        {
+            return HaloDev{h.d_row_dof.p, h.d_face_entry.p, h.d_plain.p, h.d_send.p, h.n_bottom, h.n_top, h.n_plain};
+        }
+    } // namespace
+
+    void FaceMassOp::apply_h1_pair(double c, const double * x, double * y, int64_t n, cudaStream_t s, SlabHalo * halo)
+    {
+        const unsigned fb = fs->fdof > 0 ? blocks_for(fs->fdof, 128) : 0;
+        const unsigned pb = halo ? blocks_for(halo->n_plain, 128) : 0;
+        if (fb + pb == 0)
             return;
-        facemass_pair_kernel<<<dim3(blocks_for(fs->fdof, 128), 2), 128, 0, s>>>(fs->fdof, nb, nq, d_P.p, d_a.p, fs->d_I.p, fs->d_inc_ptr.p,
-                                                                                fs->d_inc.p, fs->d_proj.p, c, n, x, y);
+        HaloDev hd{};
+        if (halo)
+            hd = halo_dev(*halo);
+        facemass_pair_kernel<<<dim3(fb + pb, 2), 128, 0, s>>>(fs->fdof, nb, nq, d_P.p, d_a.p, fs->d_I.p, fs->d_inc_ptr.p, fs->d_inc.p,
+                                                              fs->d_proj.p, c, n, x, y, hd, (int)fb);
         CB_LAUNCHED();
+    }
+
+    std::unique_ptr<SlabHalo> make_slab_halo(const Comm * comm, int rank, int world, int64_t ndof, FaceSpace * fs_phys, int64_t n_bottom,
+                                             const int * h_bottom, int64_t n_top, const int * h_top)
+    {
+        CB_REQUIRE(world >= 1 && rank >= 0 && rank < world, "slab halo: rank out of range");
+        CB_REQUIRE((rank > 0) == (n_bottom > 0) || world == 1, "slab halo: rank > 0 needs a bottom interface row, rank 0 must not have one");
+        CB_REQUIRE((rank < world - 1) == (n_top > 0) || world == 1, "slab halo: every rank but the last needs a top interface row");
+        std::unique_ptr<SlabHalo> h(new SlabHalo);
+        h->comm = comm;
+        h->rank = rank;
+        h->world = world;
+        h->ndof = ndof;
+        h->n_bottom = n_bottom;
+        h->n_top = n_top;
+        std::vector<int> row((size_t)(n_bottom + n_top));
+        std::copy(h_bottom, h_bottom + n_bottom, row.begin());
+        std::copy(h_top, h_top + n_top, row.begin() + n_bottom);
+        for (int v : row)
+            CB_REQUIRE(v >= 0 && v < ndof, "slab halo: interface DOF out of range");
+        // entries that are also face DOFs of the physical boundary are packed by the face-mass thread that finishes them
+        std::vector<int> entry_of_dof;
+        std::vector<int> face_entry;
+        std::vector<char> covered(row.size(), 0);
+        if (fs_phys) {
+            fs_phys->ensure_device();
+            entry_of_dof.assign((size_t)ndof, -1);
+            for (size_t e = 0; e < row.size(); ++e)
+                entry_of_dof[row[e]] = (int)e;
+            face_entry.assign((size_t)fs_phys->fdof, -1);
+            for (int64_t d = 0; d < fs_phys->fdof; ++d) {
+                const int e = entry_of_dof[fs_phys->proj[d]];
+                face_entry[d] = e;
+                if (e >= 0)
+                    covered[e] = 1;
+            }
+        }
+        std::vector<int> plain;
+        for (size_t e = 0; e < row.size(); ++e)
+            if (!covered[e])
+                plain.push_back((int)e);
+        h->n_plain = (int64_t)plain.size();
+        h->d_row_dof.upload(row);
+        if (!face_entry.empty())
+            h->d_face_entry.upload(face_entry);
+        if (!plain.empty())
+            h->d_plain.upload(plain);
+        const size_t tot = (size_t)h->n_fields * (size_t)(n_bottom + n_top);
+        h->d_send.alloc(std::max<size_t>(tot, 1));
+        h->d_recv.alloc(std::max<size_t>(tot, 1));
+        if (n_bottom > 0)
+            h->segs.push_back(PeerSeg{rank - 1, 0, 2 * n_bottom, 0, 2 * n_bottom});
+        if (n_top > 0)
+            h->segs.push_back(PeerSeg{rank + 1, 2 * n_bottom, 2 * n_top, 2 * n_bottom, 2 * n_top});
+        return h;
+    }
+
+    const unsigned char * SlabHalo::mask()
+    {
+        if (!d_mask.p) {
+            std::vector<unsigned char> m((size_t)n_fields * (size_t)ndof, 1);
+            if (n_bottom > 0) { // rank > 0 mirrors its bottom row: the rank below owns it (owner = lower rank)
+                const std::vector<int> row = d_row_dof.download();
+                for (int f = 0; f < n_fields; ++f)
+                    for (int64_t e = 0; e < n_bottom; ++e)
+                        m[(size_t)f * ndof + row[e]] = 0;
+            }
+            d_mask.upload(m);
+        }
+        return d_mask.p;
+    }
+
+    void SlabHalo::unpack_add(double * y, cudaStream_t s)
+    {
+        const int64_t ne = n_bottom + n_top;
+        if (ne == 0)
+            return;
+        halo_add_kernel<<<dim3(blocks_for(ne, 256), (unsigned)n_fields), 256, 0, s>>>(halo_dev(*this), d_recv.p, ndof, y);
+        CB_LAUNCHED();
+    }
+
+    void SlabHalo::exchange(double * y, cudaStream_t s)
+    {
+        const int64_t ne = n_bottom + n_top;
+        if (ne == 0 || world == 1)
+            return;
+        halo_pack_kernel<<<dim3(blocks_for(ne, 256), (unsigned)n_fields), 256, 0, s>>>(halo_dev(*this), ndof, y);
+        CB_LAUNCHED();
+        comm_exchange(comm, segs, d_send.p, d_recv.p, sizeof(double), s);
+        unpack_add(y, s);
     }
 
     std::unique_ptr<DiagOp> make_diag_inv_facemass(FaceSpace * fs, const double * d_coef)
@@ -1441,6 +1589,32 @@ namespace cb200
         H->apply_h1(omega, u, Av, s);
         negate_kernel<<<blocks_for(n, 256), 256, 0, s>>>(n, Av);
         CB_LAUNCHED();
+    }
+
+    void HelmholtzOp::apply_slab(const double * x, double * y, SlabHalo & halo, cudaStream_t s)
+    {
+        CB_REQUIRE(halo.ndof == fem->ndof && halo.n_fields == 2, "apply_slab: halo was built for another space");
+        if (halo.world == 1) {
+            apply(x, y, s);
+            return;
+        }
+        if (fused) {
+            // volume kernel + shared-DOF pass, then ONE launch for both face terms and the pack of the interface rows
+            apply(x, y, s, 1);
+            Plan & plan = *S->plan;
+            if (plan.n_shared > 0) {
+                assemble_shared_fields_kernel<<<dim3(blocks_for(plan.n_shared, 256), 2), 256, 0, s>>>(
+                    plan.n_shared, plan.d_sh_gid.p, plan.d_sh_ptr.p, d_partial2.p, std::max<int64_t>(plan.n_slots_total, 1), y, fem->ndof, 1.0, -1.0);
+                CB_LAUNCHED();
+            }
+            H->apply_h1_pair(-omega, x, y, fem->ndof, s, &halo);
+            comm_exchange(halo.comm, halo.segs, halo.d_send.p, halo.d_recv.p, sizeof(double), s);
+            halo.unpack_add(y, s);
+        }
+        else {
+            apply(x, y, s);
+            halo.exchange(y, s);
+        }
     }
 
     size_t HelmholtzOp::algorithmic_bytes() const

@@ -2,9 +2,13 @@
 // diagonal inverses, face restrict/prolong/orth and the fused Helmholtz composite.
 #pragma once
 #include "common.hpp"
+#include "dist.hpp"
 
 namespace cb200
 {
+    struct SlabHalo;
+    struct HelmholtzOp;
+
     // y = (accumulate ? y : 0) + c * A x  for a patch-planned volume operator
     struct VolumeOp
     {
@@ -46,7 +50,7 @@ namespace cb200
         // fused restrict + action + prolong on H1 vectors: y[proj] += c * H * x[proj]
         void apply_h1(double c, const double * x, double * y, cudaStream_t s);
         // both boundary terms of the Helmholtz composite on [u; v] (n DOFs each): y_u += c H x_v ; y_v += c H x_u
-        void apply_h1_pair(double c, const double * x, double * y, int64_t n, cudaStream_t s);
+        void apply_h1_pair(double c, const double * x, double * y, int64_t n, cudaStream_t s, SlabHalo * halo = nullptr);
     };
     std::unique_ptr<FaceMassOp> make_facemass(FaceSpace * fs, const double * d_coef /* device face-space coefficient or null */, int nq);
     std::unique_ptr<DiagOp> make_diag_inv_facemass(FaceSpace * fs, const double * d_coef);
@@ -58,6 +62,34 @@ namespace cb200
     // upper bound on the CTAs of the persistent kernels (0 = one full wave of resident CTAs); test / tuning knob
     int max_persistent_ctas();
     void set_max_persistent_ctas(int n);
+
+    // Path A across GPUs: the mesh is cut into slabs of element rows, one per rank; a rank holds every DOF its
+    // elements touch, so the node row on a slab interface is held by both neighbours and gets partial sums from both. After
+    // the local apply the two interface rows of [u; v] are packed (fused into the face-mass launch), exchanged with the two
+    // neighbours (one grouped ncclSend/ncclRecv) and added: own + received is the same commutative two-term sum on both
+    // sides, so the mirrored rows stay bitwise identical and the result does not depend on the rank count.
+    struct SlabHalo
+    {
+        const Comm * comm = nullptr;
+        int rank = 0, world = 1, n_fields = 2;
+        int64_t n_bottom = 0, n_top = 0, ndof = 0; // entries of the bottom / top interface row (one field); DOFs of one field
+        std::vector<PeerSeg> segs;                 // offsets / counts in doubles
+        DevBuf<int> d_row_dof;                     // (n_bottom + n_top) slab-local DOF of every row entry
+        DevBuf<int> d_face_entry;                  // per face-space DOF of the physical boundary: its row entry or -1
+        DevBuf<int> d_plain;                       // row entries that are not physical-boundary face DOFs (packed by copy)
+        DevBuf<double> d_send, d_recv;             // [bottom: field 0 entries, field 1 entries | top: field 0, field 1]
+        int64_t n_plain = 0;
+        HelmholtzOp * op = nullptr;         // bound operator (gmres callback), not owned
+        DevBuf<unsigned char> d_mask;              // (n_fields * ndof) 1 = owned: the lower rank owns a mirrored row (built lazily)
+        const unsigned char * mask();
+        int64_t bytes_per_apply() const { return (int64_t)sizeof(double) * n_fields * (n_bottom + n_top); }
+        // y <- y + neighbours' copies on the interface rows (stand-alone: makes a vector consistent / sums partial results)
+        void exchange(double * y, cudaStream_t s);
+        void unpack_add(double * y, cudaStream_t s);
+    };
+    struct FaceSpace;
+    std::unique_ptr<SlabHalo> make_slab_halo(const Comm * comm, int rank, int world, int64_t ndof, FaceSpace * fs_phys, int64_t n_bottom,
+                                             const int * h_bottom, int64_t n_top, const int * h_top);
 
     // examples/Helmholtz.hpp:28-56 composite on [u;v]
     struct HelmholtzOp
@@ -71,6 +103,9 @@ namespace cb200
         bool fused = false;           // S - omega^2 M on u and v in one warp-specialised kernel (n_basis <= 5)
         // phases (fused path only): bit 0 = the fused volume kernel, bit 1 = shared-DOF assembly + face terms
         void apply(const double * x, double * y, cudaStream_t s, int phases = 3);
+        // the apply of one slab of a partitioned mesh: local apply, interface rows packed inside the face-mass launch,
+        // neighbour exchange, add. 4 launches + one grouped send/recv (fused path).
+        void apply_slab(const double * x, double * y, SlabHalo & halo, cudaStream_t s);
         size_t algorithmic_bytes() const;
     };
     std::unique_ptr<HelmholtzOp> make_helmholtz(double omega, const double * d_a2, const double * d_a, H1Space * fem, FaceSpace * fs);

@@ -78,7 +78,9 @@ class SlabExchange:
 class GpuSlabHelmholtz:
     """Helmholtz composite (examples/Helmholtz.hpp) on this rank's slab, on the GPU, plus the interface exchange."""
 
-    def __init__(self, nx, ny_local, nb, omega, coef, rank, world, group=None):
+    def __init__(self, nx, ny_local, nb, omega, coef, rank, world, group=None, comm=None):
+        """comm: a cuddhelmholtz_b200.Comm -> the interface exchange runs inside the library (HelmholtzSlab: pack fused into the
+        face-mass launch, ncclSend/ncclRecv, 4 launches per apply); None -> the torch.distributed exchange below (any backend)."""
         import cuddhelmholtz_b200 as cb
         self.cb = cb
         self.rank, self.world = rank, world
@@ -96,7 +98,20 @@ class GpuSlabHelmholtz:
         dev = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda")
         self._a2, self._af = dev(c * c), dev(c[self.fs_phys.global_indices()])
         self.op = cb.Helmholtz(omega, self._a2, self._af, self.fem, self.fs_phys)
-        self.exchange = SlabExchange(self, rank, world, offsets=(0, self.ndof), device="cuda", group=group)
+        self.lib = None
+        if comm is not None and world > 1:
+            none = np.zeros(0, np.int32)
+            self.lib = cb.HelmholtzSlab(self.op, comm, rank, world, self.fem, self.fs_phys,
+                                        self.fs["bottom"].global_indices() if rank > 0 else none,
+                                        self.fs["top"].global_indices() if rank < world - 1 else none)
+            self.exchange = self.lib.exchange
+        else:
+            self.exchange = SlabExchange(self, rank, world, offsets=(0, self.ndof), device="cuda", group=group)
+
+    def exchange_info(self):
+        if self.lib is not None:
+            return {"bytes_per_apply": self.lib.bytes_per_apply(), "path": "library: pack fused into the face-mass launch, grouped ncclSend/ncclRecv, add kernel"}
+        return {"bytes_per_apply": getattr(self.exchange, "bytes_per_apply", 0), "path": "torch.distributed send/recv + restrict / prolong kernels"}
 
     def n_vec_rows(self):
         return self.fs["bottom"].size()
@@ -113,11 +128,16 @@ class GpuSlabHelmholtz:
 
     def apply(self, x, y):
         """y = A x on [u; v] with x consistent on the interface rows; y comes out consistent as well."""
+        if self.lib is not None:
+            self.lib.apply(x, y)
+            return
         self.op.action(x, y)
         self.exchange(y)
 
     def solve(self, b, x, m=20, maxit=1000, tol=1e-6, group=None):
         """distributed GMRES(m) on this slab partition (one allreduce per Arnoldi step), see slab_gmres"""
+        if self.lib is not None:
+            return self.lib.solve(b, x, m=m, maxit=maxit, tol=tol, orth=1)
         mask = owned_mask(self, self.rank, self.world, (0, self.ndof), 2 * self.ndof, device="cuda")
         y = torch.empty_like(b)
 

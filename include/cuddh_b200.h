@@ -124,8 +124,8 @@ int cuddh_b200_helmholtz_create(double omega, const double * d_a2, const double 
 int cuddh_b200_operator_apply(cuddh_operator_t op, double c, int accumulate, const double * x, double * y, void * stream);
 /* fused FaceSpace::restrict + FaceMassMatrix::action + FaceSpace::prolong on H1 vectors: y[proj] += c*H*x[proj] */
 int cuddh_b200_facemass_apply_h1(cuddh_operator_t op, double c, const double * x, double * y, void * stream);
-/* measurement aid (bench.py roofline): average CUDA-event time, over `reps` back-to-back launches on `stream`, of the
- * patch kernel alone and of the rest of the action alone (stiffness / mass handles: the shared-DOF assembly pass; Helmholtz
+/* measurement aid (bench.py roofline): MEDIAN CUDA-event time over `reps` (<= 256) repetitions on `stream`, after three warm
+ * applies, of the patch kernel alone and of the rest of the action alone (stiffness / mass handles: the shared-DOF assembly pass; Helmholtz
  * handles on the fused path: shared-DOF assembly + face terms; computes y = A x) */
 int cuddh_b200_operator_time_phases(cuddh_operator_t op, const double * x, double * y, int reps, float * ms_patch, float * ms_shared,
                                     void * stream);
@@ -213,6 +213,24 @@ int cuddh_b200_gmres_d_ex(int64_t n, double * x, cuddh_apply_d_fn A, void * A_ct
 int cuddh_b200_gmres_f_ex(int64_t n, float * x, cuddh_apply_f_fn A, void * A_ctx, const float * b, int m, int maxit, float tol,
                           int verbose, double max_seconds, const cuddh_gmres_options * opts, cuddh_solver_out * out, double * h_res_norm,
                           double * h_time, int cap, cuddh_gmres_stats * stats, void * stream);
+
+/* ---- path A across GPUs (new): one slab of element rows per rank ----------------------------------------
+ * A rank holds every DOF its elements touch; the node row on a slab interface is mirrored by both neighbours. h_bottom / h_top:
+ * slab-local DOF indices of the interface row shared with rank-1 / rank+1, in the same order on both sides (increasing x);
+ * n_bottom == 0 on rank 0, n_top == 0 on the last rank. fs_phys: the FaceSpace of the PHYSICAL boundary of this slab (the one
+ * the Helmholtz handle was built with) or NULL. apply_slab = local apply + interface rows packed inside the face-mass launch +
+ * one grouped ncclSend/ncclRecv + add (4 launches); own + received is the same commutative sum on both sides -> mirrored rows
+ * stay bitwise identical. slab_mask: 1 = owned (the lower rank owns a mirrored row) for cuddh_b200_gmres_d_ex. */
+typedef struct cuddh_slab_s * cuddh_slab_t;
+int cuddh_b200_slab_create(cuddh_comm_t comm, int rank, int world, cuddh_h1space_t s, cuddh_facespace_t fs_phys, int64_t n_bottom,
+                           const int * h_bottom, int64_t n_top, const int * h_top, cuddh_slab_t * out);
+int cuddh_b200_slab_destroy(cuddh_slab_t h);
+int64_t cuddh_b200_slab_bytes(cuddh_slab_t h);                                   /* bytes sent per apply */
+int cuddh_b200_slab_exchange(cuddh_slab_t h, double * y, void * stream);         /* y[rows] += neighbours' y[rows], y = [u; v] */
+const unsigned char * cuddh_b200_slab_mask(cuddh_slab_t h);                      /* DEVICE, 2*ndof bytes */
+int cuddh_b200_helmholtz_apply_slab(cuddh_operator_t op, cuddh_slab_t h, const double * x, double * y, void * stream);
+int cuddh_b200_slab_bind(cuddh_slab_t h, cuddh_operator_t helmholtz);            /* operator behind slab_as_apply (not owned) */
+int cuddh_b200_slab_as_apply(void * slab_handle, const double * x, double * y, void * stream); /* cuddh_apply_d_fn */
 
 /* ---- tuning / test knobs -------------------------------------------------------------------------
  * "gmres_orth": default orthogonalisation of gmres (0 MGS, 1 CGS2);

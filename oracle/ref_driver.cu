@@ -249,6 +249,127 @@ __device__ static double f_coef(const double X[2])
     return 1.0 + 0.5 * std::sin(M_PI * X[0]) * std::cos(M_PI * X[1]);
 }
 
+// "lite": only what the large steady-state parity cases need (a2, af, the seeded [u; v], S u, S accumulate, weighted M u,
+// M accumulate, Helmholtz composite) - one third of the bytes of the full dump
+static int cmd_ops_lite(const std::string & meshspec, int nb, double omega, uint64_t seed, const std::string & out)
+{
+    Dump d(out);
+    Mesh2D mesh = load_mesh(meshspec);
+    Basis basis(nb);
+    H1Space fem(mesh, basis);
+    const int ndof = fem.size();
+    d.i1("ndof", ndof);
+    d.i1("nb", nb);
+    ivec bf = mesh.boundary_edges();
+    FaceSpace fs(fem, bf.size(), bf.data());
+    const int fdof = fs.size();
+    d.i1("fdof", fdof);
+    host_device_dvec _a2(ndof), _af(fdof), _y(ndof), _u(2 * ndof), _Au(2 * ndof);
+    double * a2 = _a2.device_write();
+    double * af = _af.device_write();
+    double * y = _y.device_write();
+    double * u = _u.device_write();
+    double * Au = _Au.device_write();
+    auto X = fem.physical_coordinates(MemorySpace::DEVICE);
+    forall(ndof, [=] __device__ (int i) -> void
+    {
+        const double xi[] = {X(0, i), X(1, i)};
+        const double c = f_coef(xi);
+        a2[i] = c * c;
+    });
+    {
+        auto proj = fs.global_indices(MemorySpace::DEVICE);
+        forall(fdof, [=] __device__ (int i) -> void
+        {
+            const int g = proj(i);
+            const double xi[] = {X(0, g), X(1, g)};
+            af[i] = f_coef(xi);
+        });
+    }
+    std::vector<double> hu(2 * (size_t)ndof);
+    fill_uniform(hu, seed);
+    cudaMemcpy(u, hu.data(), hu.size() * sizeof(double), cudaMemcpyHostToDevice);
+    d.dbls("a2", ndof, d2h(a2, ndof).data());
+    d.dbls("af", fdof, d2h(af, fdof).data());
+    d.dbls("helm_x", 2 * (int64_t)ndof, hu.data());
+    {
+        StiffnessMatrix S(fem);
+        S.action(u, y);
+        d.dbls("S_u", ndof, d2h(y, ndof).data());
+        S.action(-0.75, u + ndof, y);
+        d.dbls("S_acc", ndof, d2h(y, ndof).data());
+    }
+    {
+        MassMatrix Mw(a2, fem);
+        Mw.action(u, y);
+        d.dbls("Mw_u", ndof, d2h(y, ndof).data());
+        Mw.action(2.5, u + ndof, y);
+        d.dbls("Mw_acc", ndof, d2h(y, ndof).data());
+    }
+    {
+        Helmholtz A(omega, a2, af, fem, fs);
+        A.action(u, Au);
+        d.d1("omega", omega);
+        d.dbls("helm_Ax", 2 * (int64_t)ndof, d2h(Au, 2 * (size_t)ndof).data());
+    }
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) { fprintf(stderr, "CUDA error: %s\n", cudaGetErrorString(err)); return 3; }
+    return 0;
+}
+
+// Mesh2D::ElementMetricCollection (source/Mesh2D.cpp:173-227) on the Gauss-Legendre rule with nq points, LinearFunctional::action
+// (include/LinearFunctional.hpp:145-181; collocated and nq-point rule) and FaceLinearFunctional::action on the boundary face
+// space (include/FaceLinearFunctional.hpp:130-164), for fixed polynomial / smooth integrands
+static int cmd_metrics_lf(const std::string & meshspec, int nb, int nq, const std::string & out)
+{
+    Dump d(out);
+    Mesh2D mesh = load_mesh(meshspec);
+    Basis basis(nb);
+    H1Space fem(mesh, basis);
+    const int ndof = fem.size();
+    const int nel = mesh.n_elem();
+    d.i1("ndof", ndof);
+    d.i1("n_elem", nel);
+    QuadratureRule q(nq, QuadratureRule::GaussLegendre);
+    d.dbls("xq", nq, q.x().data());
+    auto & em = mesh.element_metrics(q);
+    d.dbls("J", 4 * (int64_t)nq * nq * nel, d2h(em.jacobians(MemorySpace::DEVICE), 4 * (size_t)nq * nq * nel).data());
+    d.dbls("detJ", (int64_t)nq * nq * nel, d2h(em.measures(MemorySpace::DEVICE), (size_t)nq * nq * nel).data());
+    d.dbls("xphys", 2 * (int64_t)nq * nq * nel, d2h(em.physical_coordinates(MemorySpace::DEVICE), 2 * (size_t)nq * nq * nel).data());
+
+    host_device_dvec _F(ndof);
+    double * F = _F.device_write();
+    {
+        LinearFunctional l(fem);
+        l.action([] __device__ (const double X[2]) -> double {return f_mass(X);}, F);
+        d.dbls("lf_fast", ndof, d2h(F, ndof).data());
+        LinearFunctional l2(fem, q);
+        l2.action([] __device__ (const double X[2]) -> double {return f_mass(X);}, F);
+        d.dbls("lf_quad", ndof, d2h(F, ndof).data());
+        l2.action(-0.5, [] __device__ (const double X[2]) -> double {return f_coef(X);}, F);
+        d.dbls("lf_quad_acc", ndof, d2h(F, ndof).data());
+    }
+    {
+        ivec bf = mesh.boundary_edges();
+        FaceSpace fs(fem, bf.size(), bf.data());
+        const int fdof = fs.size();
+        d.i1("fdof", fdof);
+        host_device_dvec _G(fdof);
+        double * G = _G.device_write();
+        FaceLinearFunctional fl(fs);
+        fl.action([] __device__ (const double X[2]) -> double {return f_mass(X);}, G);
+        d.dbls("fl_fast", fdof, d2h(G, fdof).data());
+        FaceLinearFunctional fl2(fs, q);
+        fl2.action([] __device__ (const double X[2]) -> double {return f_mass(X);}, G);
+        d.dbls("fl_quad", fdof, d2h(G, fdof).data());
+        fl2.action(1.5, [] __device__ (const double X[2]) -> double {return f_coef(X);}, G);
+        d.dbls("fl_quad_acc", fdof, d2h(G, fdof).data());
+    }
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) { fprintf(stderr, "CUDA error: %s\n", cudaGetErrorString(err)); return 3; }
+    return 0;
+}
+
 static int cmd_ops(const std::string & meshspec, int nb, double omega, uint64_t seed, const std::string & out)
 {
     Dump d(out);
@@ -415,8 +536,13 @@ static int cmd_helm_gmres(const std::string & meshspec, int nb, double omega, in
     l.action([=] __device__ (const double Xq[2]) -> double {return f_src(Xq, omega);}, d_b);
 
     Helmholtz A(omega, d_a2, d_a, fem, fs);
+    cudaDeviceSynchronize();
+    auto t0 = std::chrono::high_resolution_clock::now();
     auto res = gmres(N, d_U, &A, d_b, m, maxit, tol, 0);
+    cudaDeviceSynchronize();
+    auto t1 = std::chrono::high_resolution_clock::now();
 
+    d.d1("gmres_seconds", 1e-9 * std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count());
     d.i1("ndof", ndof);
     d.d1("omega", omega);
     d.i1("success", res.success ? 1 : 0);
@@ -619,6 +745,8 @@ int main(int argc, char ** argv)
             "       ref_driver h1 <mesh> <nb> <out>\n"
             "       ref_driver ensemble <nx> <nb> <block> <out>\n"
             "       ref_driver ops <mesh> <nb> <omega> <seed> <out>            (GPU)\n"
+            "       ref_driver ops_lite <mesh> <nb> <omega> <seed> <out>       (GPU)\n"
+            "       ref_driver metrics_lf <mesh> <nb> <nq> <out>               (GPU)\n"
             "       ref_driver helm_gmres <mesh> <nb> <omega> <m> <maxit> <tol> <out>   (GPU)\n"
             "       ref_driver ddh <nx> <nb> <omega> <m> <maxit> <tol> <seed> <out>     (GPU)\n"
             "       ref_driver time_ops <nx> <nb> <omega> <reps>                (GPU)\n"
@@ -631,6 +759,8 @@ int main(int argc, char ** argv)
     if (cmd == "h1" && argc == 5) return cmd_h1(argv[2], atoi(argv[3]), argv[4]);
     if (cmd == "ensemble" && argc == 6) return cmd_ensemble(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5]);
     if (cmd == "ops" && argc == 7) return cmd_ops(argv[2], atoi(argv[3]), atof(argv[4]), strtoull(argv[5], nullptr, 10), argv[6]);
+    if (cmd == "ops_lite" && argc == 7) return cmd_ops_lite(argv[2], atoi(argv[3]), atof(argv[4]), strtoull(argv[5], nullptr, 10), argv[6]);
+    if (cmd == "metrics_lf" && argc == 6) return cmd_metrics_lf(argv[2], atoi(argv[3]), atoi(argv[4]), argv[5]);
     if (cmd == "helm_gmres" && argc == 9) return cmd_helm_gmres(argv[2], atoi(argv[3]), atof(argv[4]), atoi(argv[5]), atoi(argv[6]), atof(argv[7]), argv[8]);
     if (cmd == "ddh" && argc == 10) return cmd_ddh(atoi(argv[2]), atoi(argv[3]), atof(argv[4]), atoi(argv[5]), atoi(argv[6]), atof(argv[7]), strtoull(argv[8], nullptr, 10), argv[9]);
     if (cmd == "time_ops" && argc == 6) return cmd_time_ops(atoi(argv[2]), atoi(argv[3]), atof(argv[4]), atoi(argv[5]));

@@ -395,6 +395,99 @@ def facespace(mesh, I3, nb, faces):
     return fI, np.array(P, np.int32)
 
 
+def uniform_rect_closed_form(nx, ax, bx, ny, ay, by, basis):
+    """Vectorised numpy restatement of uniform_rect -> from_vertices -> H1Space -> boundary FaceSpace for structured meshes
+    (source/Mesh2D.cpp:138-171, :11-136; source/H1Space.cpp:11-127, :129-187), for sizes where the loops above take minutes
+    (bench.py's reference arm at 1024^2). No hash maps: on uniform_rect the first-touch rule has a closed form -
+      * element (ex, ey) introduces the nodes with (i > 0 or ex == 0) and (j > 0 or ey == 0), numbered in (j, i) scan order after
+        all nodes of the elements before it; every other node copies the element to its left / below;
+      * nodal coordinates are written by every element that touches a node, so the LAST element (largest id) wins;
+      * boundary edges in edge-id order = boundary (element, side) pairs in (element, side) order, sides 0..3 = bottom, right,
+        top, left; face DOFs are numbered first-touch over (face, i).
+    Checked entry by entry against the loop versions in tests/test_oracle_golden.py. Returns a dict of arrays."""
+    nb = basis.n
+    p = nb - 1
+    dx = (bx - ax) / nx
+    dy = (by - ay) / ny
+    vx = ax + dx * np.arange(nx + 1)      # :147-157 (one rounding per product and per sum, as numpy does)
+    vy = ay + dy * np.arange(ny + 1)
+    ex = np.arange(nx)
+    ey = np.arange(ny)
+    ni = np.where(ex == 0, nb, p)          # new nodes per element row / column
+    nj = np.where(ey == 0, nb, p)
+    cnt = (nj[:, None] * ni[None, :]).ravel()             # element id = ex + nx * ey
+    base = np.concatenate([[0], np.cumsum(cnt)[:-1]]).reshape(ny, nx)
+    ndof = int(cnt.sum())
+    # owner (element + local node) of grid node g along one axis: g == 0 -> (0, 0), else ((g-1) // p, g - p * that)
+    def owner(n_el):
+        g = np.arange(n_el * p + 1)
+        e = np.where(g == 0, 0, (g - 1) // p)
+        return e, g - p * e
+    ox, oi = owner(nx)
+    oy, oj = owner(ny)
+    gid = (base[oy[:, None], ox[None, :]] + (oj - (oy > 0))[:, None] * ni[ox][None, :] + (oi - (ox > 0))[None, :])  # (gy, gx)
+    gx = (ex[:, None] * p + np.arange(nb)[None, :])       # (nx, nb)
+    gy = (ey[:, None] * p + np.arange(nb)[None, :])       # (ny, nb)
+    # I[el, j, i] with el = ex + nx * ey
+    I = gid[gy[:, None, :, None], gx[None, :, None, :]].reshape(nx * ny, nb, nb).astype(np.int32)
+    # coordinates: last element touching grid node g: e = min(g // p, n_el - 1), local index g - p e
+    def last(n_el):
+        g = np.arange(n_el * p + 1)
+        e = np.minimum(g // p, n_el - 1)
+        return e, g - p * e
+    lx, li = last(nx)
+    ly, lj = last(ny)
+    xi0 = basis.x[li][None, :]
+    xi1 = basis.x[lj][:, None]
+    b = (0.25 * (1.0 - xi0) * (1.0 - xi1), 0.25 * (1.0 + xi0) * (1.0 - xi1), 0.25 * (1.0 + xi0) * (1.0 + xi1),
+         0.25 * (1.0 - xi0) * (1.0 + xi1))
+    X0, X1 = vx[lx][None, :], vx[lx + 1][None, :]
+    Y0, Y1 = vy[ly][:, None], vy[ly + 1][:, None]
+    zero = np.zeros((ny * p + 1, nx * p + 1))
+    cx = (X0 + zero, X1 + zero, X1 + zero, X0 + zero)      # corner order 0..3 = (i,j), (i+1,j), (i+1,j+1), (i,j+1)
+    cy = (Y0 + zero, Y0 + zero, Y1 + zero, Y1 + zero)
+    px = 0.0
+    py = 0.0
+    for c in range(4):                                      # source/Element.cpp:5-19: x += corner * b, c = 0..3
+        px = px + cx[c] * b[c]
+        py = py + cy[c] * b[c]
+    xy = np.zeros((ndof, 2))
+    xy[gid.ravel(), 0] = px.ravel()
+    xy[gid.ravel(), 1] = py.ravel()
+    corners = np.zeros((ny, nx, 4, 2))
+    corners[:, :, 0, 0] = corners[:, :, 3, 0] = vx[:-1][None, :]
+    corners[:, :, 1, 0] = corners[:, :, 2, 0] = vx[1:][None, :]
+    corners[:, :, 0, 1] = corners[:, :, 1, 1] = vy[:-1][:, None]
+    corners[:, :, 2, 1] = corners[:, :, 3, 1] = vy[1:][:, None]
+    corners = corners.reshape(nx * ny, 4, 2)
+    # boundary faces: (element, side) pairs on the domain boundary, ordered by (element, side)
+    EX, EY = np.meshgrid(ex, ey, indexing="xy")
+    el_id = (EX + nx * EY).ravel()
+    pairs = []
+    for side, on in ((0, EY == 0), (1, EX == nx - 1), (2, EY == ny - 1), (3, EX == 0)):
+        e = el_id[on.ravel()]
+        pairs.append(np.stack([e, np.full_like(e, side)], 1))
+    pairs = np.concatenate(pairs)
+    pairs = pairs[np.lexsort((pairs[:, 1], pairs[:, 0]))]
+    f_el, f_s = pairs[:, 0], pairs[:, 1]
+    k = np.arange(nb)[None, :]
+    m = np.where(np.isin(f_s, (0, 2))[:, None], k, np.where(f_s[:, None] == 1, nb - 1, 0))
+    n = np.where(np.isin(f_s, (1, 3))[:, None], k, np.where(f_s[:, None] == 2, nb - 1, 0))
+    idx = I[f_el[:, None], n, m]                            # (nf, nb) global DOFs in (face, i) order
+    flat = idx.ravel()
+    uniq, first = np.unique(flat, return_index=True)
+    order = np.argsort(first)                               # first-touch order
+    proj = uniq[order].astype(np.int32)
+    rank = np.empty(len(uniq), np.int64)
+    rank[order] = np.arange(len(uniq))
+    fI = rank[np.searchsorted(uniq, flat)].reshape(idx.shape).astype(np.int32)
+    # StraightEdge::meas = length / 2 between the side's two vertices (include/Edge.hpp:95-157)
+    side_nodes = np.array([[0, 1], [1, 2], [3, 2], [0, 3]])
+    d = corners[f_el, side_nodes[f_s, 1]] - corners[f_el, side_nodes[f_s, 0]]
+    meas = np.hypot(d[:, 0], d[:, 1]) / 2
+    return dict(I=I, ndof=ndof, xy=xy, corners=corners, face_el=f_el, face_side=f_s, face_I=fI, face_proj=proj, face_meas=meas)
+
+
 # ------------------------------------------------------------------------------------------------
 # source/EnsembleSpace.cpp:11-287
 # ------------------------------------------------------------------------------------------------

@@ -50,7 +50,8 @@ def main():
 
     # index maps: hashes for larger meshes
     hashes = {}
-    for spec, tag, nb in [("rect:64", "rect64", 5), ("rect:128", "rect128", 4), ("rect:256", "rect256", 5), ("rect:64", "rect64", 9)]:
+    for spec, tag, nb in [("rect:64", "rect64", 5), ("rect:128", "rect128", 4), ("rect:256", "rect256", 5), ("rect:64", "rect64", 9),
+                          ("rect:512", "rect512", 4), ("rect:1024", "rect1024", 5)]:  # 1024^2 = BASELINE config 2 (30 s, 6 GB here)
         h = run("h1", spec, nb)
         hashes["h1_%s_%d" % (tag, nb)] = dict(ndof=int(h["ndof"][0]), n_edges=int(h["n_edges"][0]), I=fnv1a64(h["I"]),
                                               xy=fnv1a64(h["xy"]), edges=fnv1a64(h["edges"]), face_I=fnv1a64(h["face_I"]),

@@ -10,7 +10,7 @@ import torch
 
 import cuddhelmholtz_b200 as cb
 from conftest import load_mesh_file
-from gpu_util import as_tensor, dev, host, rel
+from gpu_util import as_tensor, dev, host, max_ctas, rel, warped_mesh
 from oracle import ops as O
 from oracle import setup_np as S
 
@@ -527,6 +527,211 @@ def test_ddh_neighbour_exchange_emulated():
     out2 = cb.gmres(n, L2, pD, b_ref, 20, 100, 1e-4)
     assert res["success"] and out2.success and abs(res["num_iter"] - out2.num_iter) <= 1
     assert float((L - L2).norm() / L2.norm()) < 5e-3
+
+
+def test_gmres_cgs2_orthogonalisation_matches_mgs():
+    """the single-pass orthogonalisation (multi_dot + multi_update, re-orthogonalised on cancellation) against the MGS parity
+    mode: same restart / matvec counts and residual history on the Toeplitz KAT (FP64 and FP32), on the stagnating
+    Helmholtz(unstructured) history and on the converging GMRES(200) case; orthogonality of the basis is what both deliver"""
+    n = (1 << 10) + 3  # not a multiple of the 16-byte packet: the scalar tail of the vector kernels runs
+    A = Toeplitz(n)
+    xt = torch.rand(n, dtype=torch.float64, device="cuda")
+    b = torch.empty_like(xt)
+    A.action(xt.data_ptr(), b.data_ptr())
+    outs = {}
+    for mode in (cb.MGS, cb.CGS2):
+        x = torch.zeros_like(xt)
+        outs[mode] = cb.gmres(n, x, A, b, 5, 100, 1e-10, orth=mode)
+        assert outs[mode].success and rel(host(x), host(xt)) < 1e-8
+    a, c = outs[cb.MGS], outs[cb.CGS2]
+    assert a.num_iter == c.num_iter and a.num_matvec == c.num_matvec
+    assert np.allclose(a.res_norm, c.res_norm, rtol=1e-6, atol=1e-14)
+    assert c.orth_bytes > 0 and a.orth_bytes > c.orth_bytes  # fewer bytes than the k+2 MGS passes
+    A32, b32 = Toeplitz(n, torch.float32), b.float()
+    for mode in (cb.MGS, cb.CGS2):
+        x32 = torch.zeros(n, dtype=torch.float32, device="cuda")
+        o = cb.gmres(n, x32, A32, b32, 5, 100, 1e-4, orth=mode)
+        assert o.success and rel(host(x32), host(xt)) < 1e-3
+    # Helmholtz, unstructured mesh: stagnating GMRES(20) history and converging GMRES(200)
+    nn, Ah, R, bh = _helmholtz_problem(5, 10.0)
+    hist = {}
+    for mode in (cb.MGS, cb.CGS2):
+        U = torch.zeros(2 * nn, dtype=torch.float64, device="cuda")
+        hist[mode] = (cb.gmres(2 * nn, U, Ah, dev(bh), 20, 30, 1e-6, orth=mode), host(U))
+    assert hist[cb.MGS][0].num_matvec == hist[cb.CGS2][0].num_matvec
+    assert np.allclose(hist[cb.MGS][0].res_norm, hist[cb.CGS2][0].res_norm, rtol=1e-6)
+    assert rel(hist[cb.CGS2][1], hist[cb.MGS][1]) < 1e-6
+    nn, Ah, R, bh = _helmholtz_problem(4, 10.0)
+    its = {}
+    for mode in (cb.MGS, cb.CGS2):
+        U = torch.zeros(2 * nn, dtype=torch.float64, device="cuda")
+        its[mode] = cb.gmres(2 * nn, U, Ah, dev(bh), 200, 60, 1e-4, orth=mode)
+        assert its[mode].success
+        r = R.action(host(U)) - bh
+        assert np.linalg.norm(r) < 1.01e-4 * np.linalg.norm(bh)
+    assert abs(its[cb.MGS].num_iter - its[cb.CGS2].num_iter) <= 1 and abs(its[cb.MGS].num_matvec - its[cb.CGS2].num_matvec) <= 2
+
+
+def test_ddh_gmres_cgs2_iteration_parity():
+    """DDH ladder (examples/DDH.cpp flow, FP32 GMRES(20)): restart counts of the CGS2 mode against the MGS parity mode"""
+    for nx in (8, 16, 32):
+        omega = 2 * np.pi * nx / 10
+        ofem, pfem, oD, pD, f = _ddh_pair(nx, 4, omega)
+        n = pD.size()
+        b = torch.empty(n, dtype=torch.float32, device="cuda")
+        pD.rhs(dev(f), b)
+        got = {}
+        for mode in (cb.MGS, cb.CGS2):
+            L = torch.zeros(n, dtype=torch.float32, device="cuda")
+            got[mode] = (cb.gmres(n, L, pD, b, 20, 100, 1e-4, orth=mode), L)
+        a, c = got[cb.MGS][0], got[cb.CGS2][0]
+        assert a.success == c.success and abs(a.num_iter - c.num_iter) <= 1, (nx, a.num_iter, c.num_iter)
+        if a.success:
+            assert float((got[cb.MGS][1] - got[cb.CGS2][1]).norm() / got[cb.MGS][1].norm()) < 5e-3
+
+
+def test_gmres_callback_failure_and_stream():
+    """(1) a failing operator callback aborts the solve with an error instead of iterating on garbage; (2) the
+    library trampolines run on the stream gmres is given, so a solve inside a non-default torch stream is ordered"""
+    n = 4096
+
+    class Broken:
+        calls = 0
+
+        def action(self, xp, yp):
+            Broken.calls += 1
+            if Broken.calls == 3:
+                raise RuntimeError("operator exploded")
+            as_tensor(yp, n).copy_(2.0 * as_tensor(xp, n))
+
+    b = torch.rand(n, dtype=torch.float64, device="cuda")
+    x = torch.zeros_like(b)
+    with pytest.raises(RuntimeError, match="operator exploded"):
+        cb.gmres(n, x, Broken(), b, 5, 10, 1e-12)
+    assert Broken.calls == 3
+    # library operator on a side stream: results equal the default-stream solve bit for bit
+    om, pm, ofem, pfem = make("rect", 4)
+    M = cb.MassMatrix(pfem)
+    nn = ofem.ndof
+    rhs = dev(vec(nn, 5))
+    x0 = torch.zeros(nn, dtype=torch.float64, device="cuda")
+    o0 = cb.gmres(nn, x0, M, rhs, 10, 20, 1e-10)
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        x1 = torch.zeros(nn, dtype=torch.float64, device="cuda")
+        o1 = cb.gmres(nn, x1, M, rhs, 10, 20, 1e-10)
+    st.synchronize()
+    assert o0.success and o1.success and o0.num_matvec == o1.num_matvec and torch.equal(x0, x1)
+
+
+def test_ddh_dist_pack_emulated_ranks():
+    """Library-side distributed DDH (csrc/ddh.cu: fused pack in the kernel epilogue) with the ranks emulated on one GPU (no
+    communicator): the slots a rank owns and writes itself equal the single-GPU T(x) bit for bit, the packed send buffer holds
+    exactly the (lambda, mu) pairs of the slots it writes for its neighbours, and everything together tiles T(x)."""
+    nx, nb, omega = 32, 4, 2 * np.pi * 3.2
+    ofem, pfem, oD, pD, f = _ddh_pair(nx, nb, omega)
+    n = pD.size()
+    nl = n // 2
+    lam = dev(vec(n, 21).astype(np.float32), torch.float32)
+    y_ref = torch.empty(n, dtype=torch.float32, device="cuda")
+    pD.action(lam, y_ref)
+    T_ref = lam - y_ref
+    b_ref = torch.empty(n, dtype=torch.float32, device="cuda")
+    pD.rhs(dev(f), b_ref)
+    for world in (2, 3, 4):
+        R = [cb.DDHDist(pD, None, r, world) for r in range(world)]
+        covered = torch.zeros(n, dtype=torch.bool, device="cuda")
+        for r in R:
+            info = r.info()
+            mask = r.mask().bool()
+            # input restricted to the owned slots (what a distributed Krylov vector holds)
+            t = torch.empty(n, dtype=torch.float32, device="cuda")
+            r.apply_T(lam * mask, t)
+            torch.cuda.synchronize()
+            recv_idx = torch.as_tensor(r.array("recv_idx").astype(np.int64), device="cuda")
+            expect_local = mask.clone()
+            expect_local[recv_idx] = False
+            expect_local[recv_idx + nl] = False
+            assert torch.equal(t[expect_local], T_ref[expect_local]), world
+            assert float(t[~expect_local].abs().max()) == 0.0
+            covered |= expect_local
+            snd = torch.as_tensor(r.array("send_idx").astype(np.int64), device="cuda")
+            if len(snd):
+                sp, _ = r.buffers()
+                pairs = as_tensor(sp, 2 * len(snd), torch.float32).view(-1, 2)
+                assert torch.equal(pairs[:, 0], T_ref[snd]) and torch.equal(pairs[:, 1], T_ref[snd + nl]), world
+                covered[snd] = True
+                covered[snd + nl] = True
+            assert info["n_send"] == len(snd)
+        # every slot some subdomain writes is produced exactly once across the ranks (locally or in a send buffer)
+        Bout = pD.array("B").reshape(pD.info()["n_domains"], 2, -1)[:, 1, :]
+        written = torch.zeros(n, dtype=torch.bool, device="cuda")
+        w = torch.as_tensor(Bout[Bout >= 0].astype(np.int64), device="cuda")
+        written[w] = True
+        written[w + nl] = True
+        assert torch.equal(covered & written, written)
+    # one rank: the distributed object is the plain operator, and its library solve equals gmres on the DDH handle
+    A1 = cb.DDHDist(pD, None, 0, 1)
+    y1 = torch.empty(n, dtype=torch.float32, device="cuda")
+    A1.action(lam, y1)
+    written_f = written.float()
+    assert torch.equal(y1 * written_f, y_ref * written_f)
+    b1 = torch.empty(n, dtype=torch.float32, device="cuda")
+    A1.rhs(dev(f), b1)
+    assert torch.equal(b1, b_ref)
+    L1, L2 = torch.zeros(n, dtype=torch.float32, device="cuda"), torch.zeros(n, dtype=torch.float32, device="cuda")
+    o1 = A1.solve(b1, L1, m=20, maxit=100, tol=1e-4)
+    o2 = cb.gmres(n, L2, pD, b_ref, 20, 100, 1e-4)
+    assert o1.success and o2.success and abs(o1.num_iter - o2.num_iter) <= 1
+    assert float((L1 - L2).norm() / L2.norm()) < 5e-3
+
+
+@pytest.mark.parametrize("nb,nx,cap", [(4, 200, 16), (5, 200, 16), (5, 200, 3), (5, 256, 0), (3, 128, 8), (2, 128, 8)])
+def test_steady_state_against_oracle(nb, nx, cap):
+    """Persistent multi-patch path of volume_action_ws against the oracle (the same check as
+    test_gpu_reference.py::test_steady_state_matches_reference_kernels, independent of the prebuilt reference driver): warped
+    mesh = a different metric block per element and per patch; the CTA cap gives every persistent CTA >= 10 patches, so buffer
+    rotation, ring-slot wrap across rows / phases / fields / patches and the assembly-list prefetch are all under the 1e-12
+    compare. Index data comes from the library (pinned bit-exact elsewhere) because the oracle's Python setup is too slow here."""
+    xy, el = warped_mesh(nx)
+    mesh = cb.Mesh2D.from_vertices(xy, el)
+    fem = cb.H1Space(mesh, cb.Basis(nb))
+    bnd = mesh.boundary_edges()
+    fs = cb.FaceSpace(fem, bnd)
+    n = fem.size()
+    ofem = O.H1.from_arrays(nb, fem.global_indices(), fem.physical_coordinates(), xy[el])
+    E = mesh.edges()[bnd]
+    meas = 0.5 * np.linalg.norm(xy[E[:, 1]] - xy[E[:, 0]], axis=1)
+    ofs = O.FaceSpace.from_arrays(ofem, fs.subspace_indices(), fs.global_indices(), meas)
+    c = 1.0 + 0.5 * np.sin(np.pi * ofem.xy[:, 0]) * np.cos(np.pi * ofem.xy[:, 1])
+    X = vec(2 * n, 11)
+    omega = 10.0
+    dX, a2, af = dev(X), dev(c * c), dev(c[ofs.proj])
+    y = torch.empty(n, dtype=torch.float64, device="cuda")
+    with max_ctas(cap):
+        n_patch = fem.check_plan(1)["n_patches"]
+        assert n_patch >= 1.7 * (cap if cap else 296)
+        Sp, Mp = cb.StiffnessMatrix(fem), cb.MassMatrix(a2, fem)
+        assert Sp.kernel_kind() == 1 and Mp.kernel_kind() == 1
+        Sp.action(dX[:n], y)
+        assert rel(host(y), O.StiffnessMatrix(ofem).action(X[:n])) < TOL
+        y0 = vec(n, 12)
+        dy = dev(y0)
+        Mp.action(-0.75, dX[n:], dy)
+        assert rel(host(dy), O.MassMatrix(ofem, c * c).action(X[n:], y0.copy(), -0.75)) < TOL
+        Mu = cb.MassMatrix(fem)  # unweighted rule (nq = nb + 1): the small-order register-path instances
+        Mu.action(dX[:n], y)
+        assert rel(host(y), O.MassMatrix(ofem).action(X[:n])) < TOL
+        A = cb.Helmholtz(omega, a2, af, fem, fs)
+        assert A.kernel_kind() == 2
+        AX = torch.empty(2 * n, dtype=torch.float64, device="cuda")
+        A.action(dX, AX)
+        want = O.Helmholtz(omega, c * c, c[ofs.proj], ofem, ofs).action(X)
+        assert rel(host(AX[:n]), want[:n]) < TOL and rel(host(AX[n:]), want[n:]) < TOL
+        AX2 = torch.empty_like(AX)
+        A.action(dX, AX2)
+        assert torch.equal(AX, AX2)
 
 
 def test_full_size_properties():

@@ -11,7 +11,7 @@ import torch
 
 import cuddhelmholtz_b200 as cb
 from conftest import MESH_FILE, REF_DRIVER, load_mesh_file
-from gpu_util import dev, host, rel
+from gpu_util import dev, host, max_ctas, rel, warped_mesh, write_mesh_file
 from oracle.rdmp import read_rdmp
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(REF_DRIVER), reason="oracle/_ref/ref_driver not built")]
@@ -87,6 +87,101 @@ def test_operator_actions_match_reference_kernels(spec, nb):
     Ax = torch.empty(2 * n, dtype=torch.float64, device="cuda")
     A.action(dev(r["helm_x"]), Ax)
     assert rel(host(Ax), r["helm_Ax"]) < tol
+
+
+# Steady state of the persistent kernels (buffer rotation, metric-ring wrap across rows / phases / fields / patches, list
+# prefetch, per-patch cluster barrier) against the reference's own kernels: every case gives each persistent CTA SEVERAL
+# patches - by size (256^2: 512 patches on <= 296 CTAs; 1024^2: 8192) or by capping the CTA count - and the warped mesh gives
+# every element its own metric block, so a stale ring slot or a wrong-patch read cannot hide.
+STEADY = [("rect:64", 4, 8), ("rect:64", 5, 8), ("rect:64", 5, 2), ("warp:200", 4, 16), ("warp:200", 5, 16), ("warp:256", 5, 0),
+          ("rect:256", 4, 0), ("rect:256", 5, 0), ("rect:256", 8, 0), ("warp:96", 8, 0), ("rect:1024", 5, 0)]
+
+
+@pytest.mark.parametrize("spec,nb,cap", STEADY)
+def test_steady_state_matches_reference_kernels(spec, nb, cap, tmp_path):
+    omega = 10.0
+    if spec.startswith("warp:"):
+        xy, el = warped_mesh(int(spec[5:]))
+        path = str(tmp_path / "warped.txt")
+        write_mesh_file(path, xy, el)
+        rspec = "file:" + path
+        mesh = cb.Mesh2D.from_vertices(xy, el)
+    else:
+        rspec = spec
+        mesh = product_mesh(spec)
+    r = ref("ops_lite", rspec, nb, omega, 4242, timeout=1500)
+    fem = cb.H1Space(mesh, cb.Basis(nb))
+    fs = cb.FaceSpace(fem, mesh.boundary_edges())
+    n = fem.size()
+    assert n == r["ndof"][0] and fs.size() == r["fdof"][0]
+    a2, af, X = dev(r["a2"]), dev(r["af"]), dev(r["helm_x"])
+    u, v = X[:n], X[n:]
+    y = torch.empty(n, dtype=torch.float64, device="cuda")
+    tol = 1e-12
+    with max_ctas(cap):
+        S = cb.StiffnessMatrix(fem)
+        n_patch = fem.check_plan(1)["n_patches"] if nb <= 5 else 0
+        if nb <= 5:
+            assert S.kernel_kind() == 1
+            ctas = cap if cap else 296
+            assert n_patch >= 1.7 * ctas, (n_patch, ctas)  # several patches per persistent CTA
+        S.action(u, y)
+        assert rel(host(y), r["S_u"]) < tol
+        S.action(-0.75, v, y)
+        assert rel(host(y), r["S_acc"]) < tol
+        Mw = cb.MassMatrix(a2, fem)
+        Mw.action(u, y)
+        assert rel(host(y), r["Mw_u"]) < tol
+        Mw.action(2.5, v, y)
+        assert rel(host(y), r["Mw_acc"]) < tol
+        A = cb.Helmholtz(omega, a2, af, fem, fs)
+        if nb <= 5:
+            assert A.kernel_kind() == 2
+        Ax = torch.empty(2 * n, dtype=torch.float64, device="cuda")
+        A.action(X, Ax)
+        assert rel(host(Ax), r["helm_Ax"]) < tol
+        # each block row on its own as well (a wrong-field read would otherwise average out in the joint norm)
+        assert rel(host(Ax[:n]), r["helm_Ax"][:n]) < tol and rel(host(Ax[n:]), r["helm_Ax"][n:]) < tol
+
+
+@pytest.mark.parametrize("spec", ["rect:10", "file:" + MESH_FILE])
+@pytest.mark.parametrize("nb,nq", [(4, 6), (5, 9), (8, 10)])
+def test_metrics_and_linear_functionals_match_reference(spec, nb, nq):
+    # Mesh2D::ElementMetricCollection::{jacobians, measures, physical_coordinates} (source/Mesh2D.cpp:173-227),
+    # LinearFunctional::action (include/LinearFunctional.hpp:145-181), FaceLinearFunctional::action
+    # (include/FaceLinearFunctional.hpp:130-164) against the reference's own objects
+    r = ref("metrics_lf", spec, nb, nq)
+    mesh = product_mesh(spec)
+    fem = cb.H1Space(mesh, cb.Basis(nb))
+    n, nel = fem.size(), mesh.n_elem()
+    assert n == r["ndof"][0] and nel == r["n_elem"][0]
+    xq = r["xq"]
+    assert np.array_equal(cb.QuadratureRule(nq, cb.GaussLegendre).x(), xq)
+    tol = 1e-13
+    assert rel(host(fem.element_metrics(xq, "jacobians")).ravel(), r["J"]) < tol
+    assert rel(host(fem.element_metrics(xq, "measures")).ravel(), r["detJ"]) < tol
+    assert rel(host(fem.element_metrics(xq, "physical_coordinates")).ravel(), r["xphys"]) < tol
+    f_mass = lambda x, y: 3.0 * x * x - 2.0 * x * y + y + 1.0
+    f_coef = lambda x, y: 1.0 + 0.5 * torch.sin(np.pi * x) * torch.cos(np.pi * y)
+    quad = cb.QuadratureRule(nq, cb.GaussLegendre)
+    F = torch.full((n,), 3.0, dtype=torch.float64, device="cuda")  # action(f, F) overwrites
+    cb.LinearFunctional(fem).action(f_mass, F)
+    assert rel(host(F), r["lf_fast"]) < 1e-12
+    l2 = cb.LinearFunctional(fem, quad)
+    l2.action(f_mass, F)
+    assert rel(host(F), r["lf_quad"]) < 1e-12
+    l2.action(-0.5, f_coef, F)
+    assert rel(host(F), r["lf_quad_acc"]) < 1e-12
+    fs = cb.FaceSpace(fem, mesh.boundary_edges())
+    assert fs.size() == r["fdof"][0]
+    G = torch.full((fs.size(),), -2.0, dtype=torch.float64, device="cuda")
+    cb.FaceLinearFunctional(fs).action(f_mass, G)
+    assert rel(host(G), r["fl_fast"]) < 1e-12
+    fl2 = cb.FaceLinearFunctional(fs, quad)
+    fl2.action(f_mass, G)
+    assert rel(host(G), r["fl_quad"]) < 1e-12
+    fl2.action(1.5, f_coef, G)
+    assert rel(host(G), r["fl_quad_acc"]) < 1e-12
 
 
 @pytest.mark.parametrize("spec,nb,m,maxit,tol", [("file:" + MESH_FILE, 5, 20, 30, 1e-6), ("file:" + MESH_FILE, 4, 200, 60, 1e-4),

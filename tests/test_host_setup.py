@@ -88,7 +88,7 @@ def test_mesh_h1_facespace_bit_exact(gold, tag, nb):
     assert mesh.min_h() == g("min_h")[0] and mesh.max_h() == g("max_h")[0]
 
 
-@pytest.mark.parametrize("key", ["h1_rect64_5", "h1_rect128_4", "h1_rect256_5", "h1_rect64_9"])
+@pytest.mark.parametrize("key", ["h1_rect64_5", "h1_rect128_4", "h1_rect256_5", "h1_rect64_9", "h1_rect512_4", "h1_rect1024_5"])
 def test_h1_hashes_larger(gold, key):
     _, tag, nb = key.split("_")
     nx, nb = int(tag[4:]), int(nb)
@@ -256,6 +256,53 @@ def test_neighbour_ddh_slot_partition(nx, nb, world):
         assert set(r.recv_idx) <= {r.rank - 1, r.rank + 1}
     # only slab-boundary traces travel: a small fraction of the vector
     assert 0 < total_sent < n // 2
+
+
+@pytest.mark.parametrize("nx,nb,world", [(16, 4, 2), (32, 4, 4), (32, 4, 3), (8, 8, 2), (32, 4, 1)])
+def test_library_ddh_partition_matches_python(nx, nb, world):
+    """host tables of the library's distributed DDH (csrc/ddh_setup.cpp: DdhDist, no GPU, no NCCL) against the numpy construction
+    of parallel.NeighbourDDH: owner of every slot, subdomain ranges, send / recv lists per neighbour (mirrored, ascending)."""
+    from cuddhelmholtz_b200.parallel import NeighbourDDH, subdomain_range
+    mesh = cb.Mesh2D.uniform_rect(nx, -1.0, 1.0, nx, -1.0, 1.0)
+    fem = cb.H1Space(mesh, cb.Basis(nb))
+    d = cb.DDH(10.0, np.ones(fem.size()), fem, nx, nx, 16)
+    nd, n = d.info()["n_domains"], d.size()
+    L = [cb.DDHDist(d, None, r, world) for r in range(world)]
+    R = [NeighbourDDH(d, r, world, device="cpu") for r in range(world)]
+    owned = 0
+    for r in range(world):
+        info = L[r].info()
+        assert (info["dom_begin"], info["dom_end"]) == subdomain_range(nd, r, world) and info["size"] == n
+        assert np.array_equal(L[r].array("owner"), R[r].owner)
+        assert info["n_owned"] == int((R[r].owner == r).sum())
+        owned += info["n_owned"]
+        seg = L[r].array("segments").reshape(-1, 5)
+        snd, rcv = L[r].array("send_idx"), L[r].array("recv_idx")
+        assert info["n_send"] == len(snd) and info["n_recv"] == len(rcv) and info["bytes_per_action"] == 8 * len(snd)
+        peers = sorted(set(R[r].send_idx) | set(R[r].recv_idx))
+        assert list(seg[:, 0]) == peers
+        for q, so, sc, ro, rc in seg:
+            want_s = R[r].send_idx[q].numpy()[: R[r].send_idx[q].numel() // 2] if q in R[r].send_idx else np.zeros(0, np.int64)
+            want_r = R[r].recv_idx[q].numpy()[: R[r].recv_idx[q].numel() // 2] if q in R[r].recv_idx else np.zeros(0, np.int64)
+            assert np.array_equal(snd[so:so + sc], want_s) and np.array_equal(rcv[ro:ro + rc], want_r)
+            # what r packs for q is what q expects from r, in the same order
+            segq = L[q].array("segments").reshape(-1, 5)
+            row = segq[list(segq[:, 0]).index(r)]
+            assert np.array_equal(L[q].array("recv_idx")[row[3]:row[3] + row[4]], snd[so:so + sc])
+    assert owned == n // 2
+
+
+def test_gmres_options_and_knobs():
+    """option plumbing of the C ABI (no GPU): defaults, set / get, unknown names, NCCL discovery answers without a device"""
+    assert cb.get_option("gmres_orth") == cb.MGS and cb.get_option("max_ctas") == 0
+    cb.set_option("gmres_orth", cb.CGS2)
+    cb.set_option("max_ctas", 8)
+    assert cb.get_option("gmres_orth") == cb.CGS2 and cb.get_option("max_ctas") == 8
+    cb.set_option("gmres_orth", cb.MGS)
+    cb.set_option("max_ctas", 0)
+    assert cb.get_option("nccl_available") in (0, 1) and cb.get_option("nope") == -1
+    with pytest.raises(cb.CuddhError):
+        cb.set_option("nope", 1)
 
 
 def test_assembly_plan_hashes_pinned():

@@ -148,3 +148,31 @@ def test_gmres_toeplitz_kat():
     out = O.gmres(n, x, A, A(xt), 5, 100, 1e-10)
     assert out["success"]
     assert np.linalg.norm(x - xt) / np.linalg.norm(xt) < 1e-8
+
+
+@pytest.mark.parametrize("nx,ny,nb,box", [(2, 2, 3, (-1, 1, -1, 1)), (5, 3, 4, (-1, 2, 0, 1)), (10, 10, 5, (-1, 1, -1, 1)), (7, 9, 2, (0, 1, 0, 3)),
+                                          (6, 6, 8, (-1, 1, -1, 1))])
+def test_closed_form_uniform_rect_equals_first_touch(nx, ny, nb, box):
+    """the vectorised closed form used by bench.py's reference arm at 1024^2 (oracle/setup_np.py:uniform_rect_closed_form)
+    against the loop restatement of the reference's constructors, entry by entry and bit for bit"""
+    ax, bx, ay, by = box
+    m = S.uniform_rect(nx, ax, bx, ny, ay, by)
+    B = S.Basis(nb)
+    I3, ndof, xy = S.h1space(m, B)
+    fI, proj = S.facespace(m, I3, nb, m.boundary_edges)
+    c = S.uniform_rect_closed_form(nx, ax, bx, ny, ay, by, B)
+    assert np.array_equal(I3, c["I"]) and ndof == c["ndof"] and np.array_equal(xy, c["xy"])
+    assert np.array_equal(m.corners, c["corners"])
+    assert np.array_equal(m.edges[m.boundary_edges, 2], c["face_el"]) and np.array_equal(m.edges[m.boundary_edges, 4], c["face_side"])
+    assert np.array_equal(fI, c["face_I"]) and np.array_equal(proj, c["face_proj"])
+    assert np.array_equal(m.edge_meas[m.boundary_edges], c["face_meas"])
+
+
+def test_closed_form_matches_reference_at_1024(gold):
+    """BASELINE config 2 mesh: global map, nodal coordinates and boundary face space of the closed form hash to what the
+    UNMODIFIED reference's H1Space / FaceSpace produce at uniform_rect(1024), n_basis 5 (scripts/make_golden.py)"""
+    h = gold.hashes["h1_rect1024_5"]
+    c = S.uniform_rect_closed_form(1024, -1.0, 1.0, 1024, -1.0, 1.0, S.Basis(5))
+    assert c["ndof"] == h["ndof"]
+    assert fnv1a64(c["I"]) == h["I"] and fnv1a64(c["xy"]) == h["xy"]
+    assert fnv1a64(c["face_I"]) == h["face_I"] and fnv1a64(c["face_proj"]) == h["face_proj"]
