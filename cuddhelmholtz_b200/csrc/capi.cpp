@@ -16,6 +16,15 @@ namespace cb200
     void set_last_error(const std::string & msg) { g_last_error = msg; }
     const char * get_last_error() { return g_last_error.c_str(); }
     std::atomic<int64_t> g_launches{0};
+    int setup_threads()
+    {
+        static const int n = [] {
+            const char * v = getenv("CUDDH_B200_SETUP_THREADS");
+            int k = v ? atoi(v) : (int)std::thread::hardware_concurrency();
+            return std::max(1, std::min(k, 64));
+        }();
+        return n;
+    }
 } // namespace cb200
 
 using namespace cb200;

@@ -8,6 +8,8 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
+#include <algorithm>
 #include <vector>
 #include <cuda_runtime.h>
 
@@ -41,6 +43,30 @@ namespace cb200
         if (!(cond))                                                                                          \
             throw cb200::Error(-1, std::string(msg));                                                         \
     } while (0)
+
+    // ---- host-side parallel loop for the embarrassingly parallel setup stages (elements / subdomains are independent);
+    // chunks are contiguous index ranges, so every stage writes the same values wherever it ran: results do not depend on
+    // the thread count. CUDDH_B200_SETUP_THREADS overrides the thread count (1 = serial).
+    int setup_threads();
+    template <class F>
+    void parallel_for(int64_t n, F && body /* (int64_t begin, int64_t end, int thread) */)
+    {
+        const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(setup_threads(), n / 256));
+        if (nt <= 1) {
+            body((int64_t)0, n, 0);
+            return;
+        }
+        std::vector<std::thread> th;
+        const int64_t chunk = (n + nt - 1) / nt;
+        for (int t = 0; t < nt; ++t) {
+            const int64_t b = t * chunk, e = std::min<int64_t>(n, b + chunk);
+            if (b >= e)
+                break;
+            th.emplace_back([&body, b, e, t] { body(b, e, t); });
+        }
+        for (auto & x : th)
+            x.join();
+    }
 
     // ---- device buffer (64-bit sizes; the reference's int byte counts overflow at 2 GiB) ----
     template <typename T>

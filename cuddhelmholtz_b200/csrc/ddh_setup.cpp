@@ -6,6 +6,8 @@
 #include "ddh.hpp"
 #include <algorithm>
 #include <array>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -13,6 +15,25 @@
 
 namespace cb200
 {
+    namespace
+    {
+        // CUDDH_B200_SETUP_TIMING=1: print the wall time of each setup stage (stderr)
+        struct StageTimer
+        {
+            bool on;
+            std::chrono::steady_clock::time_point t0;
+            StageTimer() : on(getenv("CUDDH_B200_SETUP_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+            void lap(const char * what)
+            {
+                if (!on)
+                    return;
+                const auto t1 = std::chrono::steady_clock::now();
+                fprintf(stderr, "[cuddh_b200 setup] %-28s %8.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+                t0 = t1;
+            }
+        };
+    } // namespace
+
     // ---------------------------------------------------------------------------------------------
     // Ensemble: same first-touch numbering rules as the reference, with flat scratch arrays instead of
     // per-subdomain hash maps (O(total size), works at 262 144 subdomains).
@@ -22,6 +43,7 @@ namespace cb200
         const Mesh & mesh = *fem.mesh;
         const int64_t nel = mesh.n_elem;
         const int nb2 = nb * nb;
+        StageTimer tm;
 
         // elements of each subspace in global element order (:28-71)
         s_elems.assign(n_spaces, 0);
@@ -72,6 +94,7 @@ namespace cb200
             }
         }
 
+        tm.lap("ensemble elems+faces");
         // subspace DOF numbering: first touch over (el, j, i) (:142-175)
         sI.assign((size_t)nb2 * mx_elems * n_spaces, -1);
         s_dof.assign(n_spaces, 0);
@@ -101,6 +124,7 @@ namespace cb200
         for (int p = 0; p < n_spaces; ++p)
             std::copy(s2g[p].begin(), s2g[p].end(), gI.begin() + (size_t)mx_ndof * p);
 
+        tm.lap("ensemble dof numbering");
         // face-space numbering: first touch over (face, i), reversed on side 1 of a flipped edge (:193-234)
         fI.assign((size_t)nb * mx_faces * n_spaces, -1);
         s_fdof.assign(n_spaces, 0);
@@ -139,6 +163,7 @@ namespace cb200
         for (int p = 0; p < n_spaces; ++p)
             std::copy(f2s[p].begin(), f2s[p].end(), pI.begin() + (size_t)mx_fdof * p);
 
+        tm.lap("ensemble face numbering");
         // connectivity map: one entry per unique shared face DOF per subspace pair (:254-286); 64-bit keys
         std::unordered_set<uint64_t> seen;
         seen.reserve(shared_faces.size() * (size_t)nb * 2);
@@ -156,6 +181,7 @@ namespace cb200
             }
         }
         n_shared = (int64_t)cmap.size() / 4;
+        tm.lap("ensemble cmap");
     }
 
     // ---------------------------------------------------------------------------------------------
@@ -178,8 +204,10 @@ namespace cb200
         for (int j = 0; j < ny; ++j)
             for (int i = 0; i < nx; ++i)
                 labels[(size_t)i + (size_t)nx * j] = (i / nel1) + ndx * (j / nel1);
+        StageTimer tm;
         en.reset(new Ensemble(*fem, n_domains, labels.data()));
         const Ensemble & E = *en;
+        tm.lap("ddh: ensemble total");
 
         // WaveHoltz time grid and filter (:363-386)
         const double T = (2 * M_PI) / omega;
@@ -217,14 +245,15 @@ namespace cb200
             B[(size_t)j1 + (size_t)mx_fdof * (1 + 2 * (size_t)S1)] = (int)k;
         }
 
+        tm.lap("ddh: time tables + B");
         // permutation: face DOFs first (face-space order), then the rest in subspace order (:443-510)
         const int nb2 = nb * nb;
         gI.assign((size_t)mx_dof * n_domains, 0);
         sI.assign((size_t)nb2 * mx_elem * n_domains, 0);
-        {
+        parallel_for(n_domains, [&](int64_t pb, int64_t pe, int) {
             std::vector<int> perm(mx_dof), inv(mx_dof);
             std::vector<char> isface(mx_dof);
-            for (int p = 0; p < n_domains; ++p) {
+            for (int64_t p = pb; p < pe; ++p) {
                 const int ndof = E.s_dof[p], fdof = E.s_fdof[p];
                 std::fill(isface.begin(), isface.end(), 0);
                 int l = 0;
@@ -246,8 +275,9 @@ namespace cb200
                         sI[at] = inv[E.sI[at]];
                     }
             }
-        }
+        });
 
+        tm.lap("ddh: permutation");
         // 1-D derivative matrix at the GLL nodes, FP32 (:523-528)
         {
             std::vector<double> Dd((size_t)nb2);
@@ -264,7 +294,8 @@ namespace cb200
         std::vector<double> detJ((size_t)nb2 * g_elem);
         g.assign((size_t)3 * nb2 * mx_elem * n_domains, 0.0f);
         std::vector<float> g_elem3((size_t)3 * nb2 * g_elem);
-        for (int64_t el = 0; el < g_elem; ++el) {
+        parallel_for(g_elem, [&](int64_t el_b, int64_t el_e, int) {
+        for (int64_t el = el_b; el < el_e; ++el) {
             double c[8];
             mesh.corners(el, c);
             for (int j = 0; j < nb; ++j)
@@ -283,23 +314,43 @@ namespace cb200
                     g_elem3[3 * at + 2] = (float)(W * (Y_xi * Y_xi + X_xi * X_xi) / det);
                 }
         }
-        for (int p = 0; p < n_domains; ++p)
+        });
+        parallel_for(n_domains, [&](int64_t pb, int64_t pe, int) {
+        for (int64_t p = pb; p < pe; ++p)
             for (int el = 0; el < E.s_elems[p]; ++el) {
                 const int g_el = E.elems[(size_t)el + (size_t)mx_elem * p];
                 std::memcpy(&g[3 * (size_t)nb2 * (el + (size_t)mx_elem * p)], &g_elem3[3 * (size_t)nb2 * g_el], sizeof(float) * 3 * nb2);
             }
+        });
 
+        tm.lap("ddh: metrics g");
         // is the metric diagonal and the same in every element? (true for Mesh2D::uniform_rect; decides the kernel variant)
         reg_tiled_ok = (getenv("CUDDH_B200_DDH_V1") == nullptr);
-        for (size_t t = 0; t < g.size() && reg_tiled_ok; ++t) {
-            const size_t within = t % ((size_t)3 * nb2);
+        if (reg_tiled_ok) {
             // a few ulps of slack: uniform_rect vertices are a + i*h, so per-element metrics may differ in the last bit on
-            // domains that are not powers of two; the register-tiled kernel uses element 0's values
-            const float ref = g[within - within % 3] > g[within - within % 3 + 2] ? g[within - within % 3] : g[within - within % 3 + 2];
-            if (within % 3 == 1 ? (std::fabs(g[t]) > 1e-6f * std::fabs(ref)) : (std::fabs(g[t] - g[within]) > 4.0f * 1.1920929e-7f * std::fabs(g[within])))
-                reg_tiled_ok = false;
+            // domains that are not powers of two; the register-tiled kernel uses the first element's values
+            std::atomic<int> bad{0};
+            const size_t per = (size_t)3 * nb2;
+            const float * g0p = &g[0]; // first element of the first subdomain
+            parallel_for(g_elem, [&](int64_t el_b, int64_t el_e, int) {
+                for (int64_t el = el_b; el < el_e && !bad.load(std::memory_order_relaxed); ++el) {
+                    const float * ge = &g_elem3[per * (size_t)el];
+                    for (size_t w = 0; w < per; ++w) {
+                        const size_t node0 = w - w % 3;
+                        const float ref = std::max(g0p[node0], g0p[node0 + 2]);
+                        const bool ok = (w % 3 == 1) ? (std::fabs(ge[w]) <= 1e-6f * std::fabs(ref))
+                                                     : (std::fabs(ge[w] - g0p[w]) <= 4.0f * 1.1920929e-7f * std::fabs(g0p[w]));
+                        if (!ok) {
+                            bad.store(1, std::memory_order_relaxed);
+                            break;
+                        }
+                    }
+                }
+            });
+            reg_tiled_ok = bad.load() == 0;
         }
 
+        tm.lap("ddh: reg_tiled check");
         // global inverse lumped mass (:556-565)
         std::vector<double> mi((size_t)g_ndof, 0.0);
         for (int64_t el = 0; el < g_elem; ++el)
@@ -317,7 +368,8 @@ namespace cb200
         H.assign((size_t)mx_fdof * n_domains, 0.0f);
         a.assign((size_t)mx_dof * n_domains, 0.0f);
         gmi.assign((size_t)mx_dof * n_domains, 0.0f);
-        for (int p = 0; p < n_domains; ++p) {
+        parallel_for(n_domains, [&](int64_t pb, int64_t pe, int) {
+        for (int64_t p = pb; p < pe; ++p) {
             for (int el = 0; el < E.s_elems[p]; ++el) {
                 const int g_el = E.elems[(size_t)el + (size_t)mx_elem * p];
                 for (int j = 0; j < nb; ++j)
@@ -341,7 +393,9 @@ namespace cb200
                 }
             }
         }
+        });
 
+        tm.lap("ddh: m H a gmi");
         // -----------------------------------------------------------------------------------------
         // grid layout for the kernel: unique DOF (X, Y) of subdomain p at p*n1*n1 + Y*n1 + X, where the
         // element-local node (k, l) of local element (ex, ey) sits at X = ex*(nb-1)+k, Y = ey*(nb-1)+l.
@@ -352,8 +406,9 @@ namespace cb200
         std::vector<int> h_gid((size_t)nd * n_domains, -1), h_bin((size_t)nd * n_domains, -1), h_bout((size_t)nd * n_domains, -1);
         std::vector<float> h_a2((size_t)nd * n_domains, 1.0f), h_m((size_t)nd * n_domains, 1.0f), h_pou((size_t)nd * n_domains, 0.0f),
             h_H((size_t)nd * n_domains, 0.0f);
+        parallel_for(n_domains, [&](int64_t pb, int64_t pe, int) {
         std::vector<int> dof_of_grid(nd);
-        for (int p = 0; p < n_domains; ++p) {
+        for (int64_t p = pb; p < pe; ++p) {
             std::fill(dof_of_grid.begin(), dof_of_grid.end(), -1);
             CB_REQUIRE(E.s_elems[p] == mx_elem && E.s_dof[p] == nd, "DDH error: non-uniform subdomain (Mesh2D::uniform_rect required).");
             for (int el = 0; el < mx_elem; ++el) {
@@ -380,6 +435,7 @@ namespace cb200
                 }
             }
         }
+        });
         hg_gid = std::move(h_gid);
         hg_bin = std::move(h_bin);
         hg_bout = std::move(h_bout);
@@ -388,6 +444,7 @@ namespace cb200
         hg_pou = std::move(h_pou);
         hg_H = std::move(h_H);
 
+        tm.lap("ddh: grid layout");
         // transposed map for the ordered partition-of-unity sum in postprocess(): global DOF -> slots (p*nd+at)
         {
             std::vector<int> ptr((size_t)g_ndof + 1, 0), src(hg_gid.size());
@@ -402,6 +459,7 @@ namespace cb200
             h_asm_ptr = std::move(ptr);
             h_asm_src = std::move(src);
         }
+        tm.lap("ddh: pou transpose");
     }
 
     void DDH::ensure_device()
