@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <vector>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h> // header-only NVTX 3: a no-op unless a profiler (nsys / ncu --nvtx) injects itself
 
 namespace cb200
 {
@@ -43,6 +44,17 @@ namespace cb200
         if (!(cond))                                                                                          \
             throw cb200::Error(-1, std::string(msg));                                                         \
     } while (0)
+
+    // ---- NVTX ranges around the host-visible stages of the solve path (operator applies, DDH action / rhs / postprocess, GMRES
+    // restart cycles, halo exchanges): `nsys profile` / `ncu --nvtx` then show the reference's call structure
+    // (examples/Helmholtz.hpp:28-56, source/gmres.cpp:146-215, source/DDH.cpp:611-695) on the timeline
+    struct NvtxRange
+    {
+        explicit NvtxRange(const char * name) { nvtxRangePushA(name); }
+        ~NvtxRange() { nvtxRangePop(); }
+        NvtxRange(const NvtxRange &) = delete;
+        NvtxRange & operator=(const NvtxRange &) = delete;
+    };
 
     // ---- host-side parallel loop for the embarrassingly parallel setup stages (elements / subdomains are independent);
     // chunks are contiguous index ranges, so every stage writes the same values wherever it ran: results do not depend on

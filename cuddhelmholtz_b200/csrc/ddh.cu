@@ -32,7 +32,8 @@ namespace cb200
             const float * m;
             const float * pou;
             const float * H;
-            const float * g;   // (3, NB, NB, NEL*NEL, dom)
+            const float * g;   // (3, NB, NB, NEL*NEL, dom), or one (3, NB, NB) table when g_uniform
+            int g_uniform;
             const float * D;   // (NB, NB) column-major
             const float * whf;
             const float * cs;
@@ -102,7 +103,7 @@ namespace cb200
                 DTk[i] = __ldg(A.D + i + NB * k);
                 DTl[i] = __ldg(A.D + i + NB * l);
             }
-            const float * gp = A.g + 3 * ((size_t)tid + (size_t)MX * dom);
+            const float * gp = A.g + 3 * (A.g_uniform ? (size_t)(tid % (NB * NB)) : ((size_t)tid + (size_t)MX * dom));
             const float gx = __ldg(gp), gy = __ldg(gp + 1), gz = __ldg(gp + 2);
 
             const float half_dt = 0.5f * A.dt;
@@ -442,6 +443,7 @@ namespace cb200
         A.pou = d_pou.p;
         A.H = d_H.p;
         A.g = d_g.p;
+        A.g_uniform = uniform_metric ? 1 : 0;
         A.D = d_D.p;
         A.whf = d_whf.p;
         A.cs = d_cs.p;
@@ -481,8 +483,8 @@ namespace cb200
                 for (int k = 0; k < 4; ++k)
                     for (int i = 0; i < 4; ++i) {
                         C.D[k][i] = D[k + 4 * i];
-                        C.gx[i][k] = g[3 * (k + 4 * i) + 0];
-                        C.gz[i][k] = g[3 * (k + 4 * i) + 2];
+                        C.gx[i][k] = g_first[3 * (k + 4 * i) + 0];
+                        C.gz[i][k] = g_first[3 * (k + 4 * i) + 2];
                     }
                 const int per_cta = V2_THREADS / 16;
                 ddh_kernel_reg4<<<(n_launch + per_cta - 1) / per_cta, V2_THREADS, 0, s>>>(C, A, n_launch);
@@ -508,6 +510,7 @@ namespace cb200
 
     void DDH::action(const float * x, float * y, cudaStream_t s)
     {
+        NvtxRange nvtx_("cuddh::DDH::action");
         // source/DDH.cpp:611-639: update = T(lambda); out = lambda - update
         run(nullptr, nullptr, x, y, s);
         axpby<float>(2 * n_lambda, 1.0f, x, -1.0f, y, s);
@@ -515,11 +518,13 @@ namespace cb200
 
     void DDH::rhs(const double * f, float * b, cudaStream_t s)
     {
+        NvtxRange nvtx_("cuddh::DDH::rhs");
         run(f, nullptr, nullptr, b, s); // :641-667
     }
 
     void DDH::postprocess(const float * lambda, const double * f, double * u, cudaStream_t s)
     {
+        NvtxRange nvtx_("cuddh::DDH::postprocess");
         run(f, u, lambda, nullptr, s); // :669-695
     }
 
@@ -552,6 +557,7 @@ namespace cb200
 
     void DdhDist::exchange_and_finish(const float * x, float * t, int mode, cudaStream_t s)
     {
+        NvtxRange nvtx_("cuddh::DDH trace exchange");
         if (comm && world > 1 && !segs.empty()) {
             comm_exchange(comm, segs, d_send.p, d_recv.p, sizeof(float2), s);
             const int64_t nr = (int64_t)recv_idx.size();
@@ -575,6 +581,7 @@ namespace cb200
 
     void DdhDist::action(const float * x, float * y, cudaStream_t s)
     {
+        NvtxRange nvtx_("cuddh::DDH::action (distributed)");
         ensure_device();
         DDH::Redirect r{d_bout.p, (int64_t)ddh->n1 * ddh->n1 * dom_begin, d_send.p};
         ddh->run(nullptr, nullptr, x, y, s, dom_begin, dom_end, &r);

@@ -36,7 +36,11 @@ namespace cb200
 
         // reference-layout host arrays (kept for parity tests / introspection)
         std::vector<int> B, gI, sI;
-        std::vector<float> m, gmi, a, H, D, wh_filter, cs, sn, g;
+        std::vector<float> m, gmi, a, H, D, wh_filter, cs, sn;
+        std::vector<float> g_first;       // (3, nb, nb) geometric factors of one element (all elements alike on uniform_rect)
+        mutable std::vector<float> g;     // (3, nb, nb, mx_elem, dom), built on demand by full_metric()
+        bool uniform_metric = false;
+        const std::vector<float> & full_metric() const;
 
         // device arrays in the kernel's grid layout: per subdomain, per unique DOF (Y*n1 + X)
         DevBuf<int> d_gid, d_bin, d_bout;

@@ -292,10 +292,8 @@ namespace cb200
         const double * qw = fem->basis->w.data();
         const int64_t g_elem = mesh.n_elem;
         std::vector<double> detJ((size_t)nb2 * g_elem);
-        g.assign((size_t)3 * nb2 * mx_elem * n_domains, 0.0f);
-        std::vector<float> g_elem3((size_t)3 * nb2 * g_elem);
-        parallel_for(g_elem, [&](int64_t el_b, int64_t el_e, int) {
-        for (int64_t el = el_b; el < el_e; ++el) {
+        // geometric factors of ONE element at the GLL nodes (the formula of source/DDH.cpp:31-58), FP32
+        auto element_metric = [this, q, qw, &mesh](int64_t el, float * out3 /* 3*nb2 */, double * det_out /* nb2 or null */) {
             double c[8];
             mesh.corners(el, c);
             for (int j = 0; j < nb; ++j)
@@ -306,35 +304,32 @@ namespace cb200
                     const double X_eta = 0.25 * ((1.0 - xi0) * (c[6] - c[0]) + (1.0 + xi0) * (c[4] - c[2]));
                     const double Y_eta = 0.25 * ((1.0 - xi0) * (c[7] - c[1]) + (1.0 + xi0) * (c[5] - c[3]));
                     const double det = X_xi * Y_eta - Y_xi * X_eta;
-                    const size_t at = (size_t)i + nb * (j + (size_t)nb * el);
-                    detJ[at] = det;
+                    const size_t at = (size_t)i + nb * j;
+                    if (det_out)
+                        det_out[at] = det;
                     const double W = qw[i] * qw[j];
-                    g_elem3[3 * at + 0] = (float)(W * (Y_eta * Y_eta + X_eta * X_eta) / det);
-                    g_elem3[3 * at + 1] = (float)(-W * (Y_xi * Y_eta + X_xi * X_eta) / det);
-                    g_elem3[3 * at + 2] = (float)(W * (Y_xi * Y_xi + X_xi * X_xi) / det);
+                    out3[3 * at + 0] = (float)(W * (Y_eta * Y_eta + X_eta * X_eta) / det);
+                    out3[3 * at + 1] = (float)(-W * (Y_xi * Y_eta + X_xi * X_eta) / det);
+                    out3[3 * at + 2] = (float)(W * (Y_xi * Y_xi + X_xi * X_xi) / det);
                 }
-        }
-        });
-        parallel_for(n_domains, [&](int64_t pb, int64_t pe, int) {
-        for (int64_t p = pb; p < pe; ++p)
-            for (int el = 0; el < E.s_elems[p]; ++el) {
-                const int g_el = E.elems[(size_t)el + (size_t)mx_elem * p];
-                std::memcpy(&g[3 * (size_t)nb2 * (el + (size_t)mx_elem * p)], &g_elem3[3 * (size_t)nb2 * g_el], sizeof(float) * 3 * nb2);
-            }
-        });
-
-        tm.lap("ddh: metrics g");
-        // is the metric diagonal and the same in every element? (true for Mesh2D::uniform_rect; decides the kernel variant)
-        reg_tiled_ok = (getenv("CUDDH_B200_DDH_V1") == nullptr);
-        if (reg_tiled_ok) {
-            // a few ulps of slack: uniform_rect vertices are a + i*h, so per-element metrics may differ in the last bit on
-            // domains that are not powers of two; the register-tiled kernel uses the first element's values
-            std::atomic<int> bad{0};
-            const size_t per = (size_t)3 * nb2;
-            const float * g0p = &g[0]; // first element of the first subdomain
+        };
+        // One pass over the elements: Jacobian determinants (lumped masses below) and - without storing 3*nb2 floats per element -
+        // whether every element has the metric of the first element of the first subdomain (diagonal, equal up to a few ulps:
+        // uniform_rect vertices are a + i*h, so on domains that are not powers of two the last bit may differ). That is always
+        // the case on the meshes DDH accepts; the kernels then read ONE 3*nb2 table (g_first) instead of an array of
+        // 3*nb2*n_elem floats (805 MB at 2048^2), which get_array("g") / a non-uniform mesh still build on demand.
+        const size_t per = (size_t)3 * nb2;
+        g_first.resize(per);
+        element_metric(E.elems[0], g_first.data(), nullptr);
+        std::atomic<int> bad{0};
+        {
+            const float * g0p = g_first.data();
             parallel_for(g_elem, [&](int64_t el_b, int64_t el_e, int) {
-                for (int64_t el = el_b; el < el_e && !bad.load(std::memory_order_relaxed); ++el) {
-                    const float * ge = &g_elem3[per * (size_t)el];
+                std::vector<float> ge(per);
+                for (int64_t el = el_b; el < el_e; ++el) {
+                    element_metric(el, ge.data(), &detJ[(size_t)nb2 * el]);
+                    if (bad.load(std::memory_order_relaxed))
+                        continue;
                     for (size_t w = 0; w < per; ++w) {
                         const size_t node0 = w - w % 3;
                         const float ref = std::max(g0p[node0], g0p[node0 + 2]);
@@ -347,9 +342,13 @@ namespace cb200
                     }
                 }
             });
-            reg_tiled_ok = bad.load() == 0;
         }
-
+        uniform_metric = bad.load() == 0;
+        tm.lap("ddh: metrics + uniformity");
+        // is the metric diagonal and the same in every element? (decides the kernel variant)
+        reg_tiled_ok = uniform_metric && (getenv("CUDDH_B200_DDH_V1") == nullptr);
+        if (!uniform_metric)
+            full_metric();
         tm.lap("ddh: reg_tiled check");
         // global inverse lumped mass (:556-565)
         std::vector<double> mi((size_t)g_ndof, 0.0);
@@ -462,6 +461,43 @@ namespace cb200
         tm.lap("ddh: pou transpose");
     }
 
+    const std::vector<float> & DDH::full_metric() const
+    {
+        // (3, nb, nb, mx_elem, dom) in the reference's layout (source/DDH.cpp:533-537), built on demand
+        if (g.empty()) {
+            const Mesh & mesh = *fem->mesh;
+            const Ensemble & E = *en;
+            const int nb2 = nb * nb;
+            const double * q = fem->basis->x.data();
+            const double * qw = fem->basis->w.data();
+            g.assign((size_t)3 * nb2 * mx_elem * n_domains, 0.0f);
+            parallel_for(n_domains, [&](int64_t pb, int64_t pe, int) {
+                for (int64_t p = pb; p < pe; ++p)
+                    for (int el = 0; el < E.s_elems[p]; ++el) {
+                        const int64_t g_el = E.elems[(size_t)el + (size_t)mx_elem * p];
+                        float * out3 = &g[3 * (size_t)nb2 * (el + (size_t)mx_elem * p)];
+                        double c[8];
+                        mesh.corners(g_el, c);
+                        for (int j = 0; j < nb; ++j)
+                            for (int i = 0; i < nb; ++i) {
+                                const double xi0 = q[i], xi1 = q[j];
+                                const double X_xi = 0.25 * ((1.0 - xi1) * (c[2] - c[0]) + (1.0 + xi1) * (c[4] - c[6]));
+                                const double Y_xi = 0.25 * ((1.0 - xi1) * (c[3] - c[1]) + (1.0 + xi1) * (c[5] - c[7]));
+                                const double X_eta = 0.25 * ((1.0 - xi0) * (c[6] - c[0]) + (1.0 + xi0) * (c[4] - c[2]));
+                                const double Y_eta = 0.25 * ((1.0 - xi0) * (c[7] - c[1]) + (1.0 + xi0) * (c[5] - c[3]));
+                                const double det = X_xi * Y_eta - Y_xi * X_eta;
+                                const size_t at = (size_t)i + nb * j;
+                                const double W = qw[i] * qw[j];
+                                out3[3 * at + 0] = (float)(W * (Y_eta * Y_eta + X_eta * X_eta) / det);
+                                out3[3 * at + 1] = (float)(-W * (Y_xi * Y_eta + X_xi * X_eta) / det);
+                                out3[3 * at + 2] = (float)(W * (Y_xi * Y_xi + X_xi * X_xi) / det);
+                            }
+                    }
+            });
+        }
+        return g;
+    }
+
     void DDH::ensure_device()
     {
         if (on_device)
@@ -473,7 +509,10 @@ namespace cb200
         d_m.upload(hg_m);
         d_pou.upload(hg_pou);
         d_H.upload(hg_H);
-        d_g.upload(g);
+        if (uniform_metric)
+            d_g.upload(g_first);
+        else
+            d_g.upload(full_metric());
         d_D.upload(D);
         d_whf.upload(wh_filter);
         d_cs.upload(cs);
@@ -505,7 +544,7 @@ namespace cb200
         else if (n == "a") pick_f(a);
         else if (n == "H") pick_f(H);
         else if (n == "D") pick_f(D);
-        else if (n == "g") pick_f(g);
+        else if (n == "g") pick_f(full_metric());
         else if (n == "wh_filter") pick_f(wh_filter);
         else if (n == "cs") pick_f(cs);
         else if (n == "sn") pick_f(sn);

@@ -596,6 +596,7 @@ namespace cb200
     GmresResult gmres(int64_t n, T * x, ApplyFn<T> A, void * ctx, const T * b, int m, int maxit, T tol, int verbose,
                       double max_seconds, cudaStream_t s, const GmresOptions & opt)
     {
+        NvtxRange nvtx_solve(sizeof(T) == 8 ? "cuddh::gmres<double>" : "cuddh::gmres<float>");
         GmresResult out;
         out.success = false;
         out.num_iter = 0;
@@ -695,6 +696,7 @@ namespace cb200
 
         int it = 1;
         for (; it < maxit; ++it) {
+            NvtxRange nvtx_cycle("gmres restart cycle");
             axpby<T>(n, one / r_nrm, r, zero, V, s); // v0 = r / ||r||
             std::fill(eta.begin(), eta.end(), T(0));
             eta[0] = r_nrm;
@@ -709,6 +711,7 @@ namespace cb200
 
                 if (ev.on)
                     CB_CUDA(cudaEventRecord(ev.a, s));
+                NvtxRange nvtx_orth(cgs ? "gmres orthogonalise (CGS2)" : "gmres orthogonalise (MGS)");
                 bool zero_w = false;
                 if (cgs) {
                     cgs_dots(w, k1);

@@ -1161,6 +1161,7 @@ namespace cb200
 
     void VolumeOp::apply(double c, int accumulate, const double * x, double * y, cudaStream_t s, int phases)
     {
+        NvtxRange nvtx_(stiff ? "cuddh::StiffnessMatrix::action" : "cuddh::MassMatrix::action");
         Plan & plan = *this->plan;
         PlanDev pd{plan.d_hdr.p, plan.d_gid.p, plan.d_slot.p, plan.d_L.p, plan.d_cptr.p, plan.d_cent.p, plan.PE, plan.d_Ig.p, reinterpret_cast<const uint2 *>(plan.d_cent4.p), plan.d_target.p};
         LaunchFn fn = generic ? nullptr : (stiff ? find_instance<true>(nb, nq) : find_instance<false>(nb, nq));
@@ -1353,6 +1354,7 @@ namespace cb200
 
     void FaceMassOp::apply(double c, int accumulate, const double * x, double * y, cudaStream_t s)
     {
+        NvtxRange nvtx_("cuddh::FaceMassMatrix::action");
         if (fs->fdof == 0)
             return;
         facemass_action_kernel<<<blocks_for(fs->fdof, 128), 128, 0, s>>>(fs->fdof, nb, nq, d_P.p, d_a.p, fs->d_I.p, fs->d_inc_ptr.p,
@@ -1472,6 +1474,7 @@ namespace cb200
 
     void SlabHalo::exchange(double * y, cudaStream_t s)
     {
+        NvtxRange nvtx_("cuddh::SlabHalo::exchange");
         const int64_t ne = n_bottom + n_top;
         if (ne == 0 || world == 1)
             return;
@@ -1542,6 +1545,7 @@ namespace cb200
 
     void HelmholtzOp::apply(const double * x, double * y, cudaStream_t s, int phases)
     {
+        NvtxRange nvtx_("cuddh::Helmholtz::action");
         // examples/Helmholtz.hpp:28-56:  Au = S u - w^2 M u - w H v ;  Av = -(S v - w^2 M v + w H u)
         const int64_t n = fem->ndof;
         const double * u = x;
@@ -1593,6 +1597,7 @@ namespace cb200
 
     void HelmholtzOp::apply_slab(const double * x, double * y, SlabHalo & halo, cudaStream_t s)
     {
+        NvtxRange nvtx_("cuddh::Helmholtz::action (slab + halo exchange)");
         CB_REQUIRE(halo.ndof == fem->ndof && halo.n_fields == 2, "apply_slab: halo was built for another space");
         if (halo.world == 1) {
             apply(x, y, s);
