@@ -500,10 +500,12 @@ def _callback(A, kind):
 MGS, CGS2 = 0, 1
 
 
-def gmres(n, x, A, b, m, maxit, tol=None, P=None, verbose=0, max_seconds=6 * 60 * 60, orth=-1, comm=None, mask=None, time_orth=False):
+def gmres(n, x, A, b, m, maxit, tol=None, P=None, verbose=0, max_seconds=6 * 60 * 60, orth=-1, comm=None, mask=None, time_orth=False,
+          flexible=False):
     """include/gmres.hpp:33-36. x, b: device vectors (torch float64 -> FP64 solver, float32 -> FP32 solver).
     A (and P): operators of this module, or any object with .action(x_ptr, y_ptr) on raw device addresses.
-    orth: MGS (the reference's arithmetic) / CGS2 / -1 = library default; comm + mask: distributed vectors (Comm, uint8 tensor)."""
+    orth: MGS (the reference's arithmetic) / CGS2 / -1 = library default; comm + mask: distributed vectors (Comm, uint8 tensor).
+    flexible=True: P is applied on the RIGHT and afresh to every basis vector (FGMRES), so it may be an inner iterative solve."""
     import torch
     single = isinstance(x, torch.Tensor) and x.dtype == torch.float32
     cap = maxit + 2
@@ -511,7 +513,7 @@ def gmres(n, x, A, b, m, maxit, tol=None, P=None, verbose=0, max_seconds=6 * 60 
     tim = np.zeros(cap)
     so = capi.SolverOut()
     st = capi.GmresStats()
-    opts = capi.GmresOptions(int(orth), comm._h if comm is not None else None, _ptr(mask), int(bool(time_orth)))
+    opts = capi.GmresOptions(int(orth), comm._h if comm is not None else None, _ptr(mask), int(bool(time_orth)), int(bool(flexible)))
     fa, ca, keep_a = _callback(A, "f" if single else "d")
     del _callback_error[:]
     if single:
@@ -627,6 +629,47 @@ class DDH:
 
     def _as_apply(self):
         return C.cast(load().cuddh_b200_ddh_as_apply, C.c_void_p), self._h
+
+
+class DDHPreconditioner:
+    """path B as a preconditioner of path A. P r ~ A^{-1} r for the FP64 Helmholtz composite A of
+    examples/Helmholtz.hpp: the residual [r_u; r_v] of A [u; v] = b is the load [F; G] = [r_u; -r_v] of the time-harmonic
+    problem DDH solves (the composite negates its second block row, examples/Helmholtz.hpp:55), so
+        P r = postprocess( gmres_f32( DDH, rhs( w * [r_u; -r_v] ) ) ),      w_i = 1 / (number of subdomains that hold DOF i)
+    - one substructured FP32 DDH-GMRES solve (WaveHoltz local solves, GLL-collocated operators) per application. The weight w is
+    needed because DDH::rhs hands the ASSEMBLED load entry to every subdomain that holds the DOF (source/DDH.cpp:208-212), so a
+    load on an interface node would otherwise count 2 (4 at cross points) times; on uniform_rect the equal split is also the
+    lumped-mass share m * gmi that postprocess uses as partition of unity. P is an inner iterative solve, i.e. not a fixed linear
+    map: use it with gmres(..., P=this, flexible=True). The reference has no such composition (its DDH is the system operator of
+    the interface problem), so there is no parity oracle for this class - its test checks the outer solve against a
+    direct FP64 solve of the assembled operator."""
+
+    def __init__(self, ddh, m=20, maxit=100, tol=1e-4, orth=-1):
+        import torch
+        self.ddh, self.m, self.maxit, self.tol, self.orth = ddh, m, maxit, tol, orth
+        self.n = ddh.fem.size()
+        nl = ddh.size()
+        g = ddh.array("gI")
+        mult = np.bincount(g[g >= 0], minlength=self.n).astype(np.float64)
+        w = 1.0 / np.maximum(mult, 1.0)
+        self.w = torch.as_tensor(np.concatenate([w, -w]), device="cuda")
+        self.f = torch.empty(2 * self.n, dtype=torch.float64, device="cuda")
+        self.b = torch.empty(nl, dtype=torch.float32, device="cuda")
+        self.lam = torch.empty(nl, dtype=torch.float32, device="cuda")
+        self.inner_restarts, self.inner_matvecs, self.applications = 0, 0, 0
+
+    def action(self, xp, yp):
+        import torch
+        from .parallel import _as_tensor
+        x = xp if isinstance(xp, torch.Tensor) else _as_tensor(xp, 2 * self.n, torch.float64)
+        torch.mul(x, self.w, out=self.f)  # the only torch op of this add-on: split the load, flip the sign of the second block
+        self.ddh.rhs(self.f, self.b)
+        fill(self.lam.numel(), 0.0, self.lam)
+        out = gmres(self.lam.numel(), self.lam, self.ddh, self.b, self.m, self.maxit, self.tol, orth=self.orth)
+        self.inner_restarts += out.num_iter
+        self.inner_matvecs += out.num_matvec
+        self.applications += 1
+        self.ddh.postprocess(self.lam, self.f, yp)
 
 
 class HelmholtzSlab:

@@ -21,7 +21,7 @@ class SolverOut(C.Structure):
 
 
 class GmresOptions(C.Structure):
-    _fields_ = [("orth", C.c_int), ("comm", C.c_void_p), ("d_mask", C.c_void_p), ("time_orth", C.c_int)]
+    _fields_ = [("orth", C.c_int), ("comm", C.c_void_p), ("d_mask", C.c_void_p), ("time_orth", C.c_int), ("flexible", C.c_int)]
 
 
 class GmresStats(C.Structure):

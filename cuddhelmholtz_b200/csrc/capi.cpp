@@ -584,7 +584,14 @@ int cuddh_b200_gmres_d_ex(int64_t n, double * x, cuddh_apply_d_fn A, void * A_ct
     CB_REQUIRE(A != nullptr, "gmres: null operator callback");
     const GmresOptions go = make_options(opts);
     GmresResult r;
-    if (P) { // gmres.cpp:242-251: solve P A x = P b
+    if (P && opts && opts->flexible) { // FGMRES: A P y = b, x = P y, P applied afresh to every basis vector
+        UserApply<double> ua{A, A_ctx}, up{P, P_ctx};
+        GmresOptions gf = go;
+        gf.right_precond = (void *)&UserApply<double>::apply;
+        gf.right_precond_ctx = &up;
+        r = gmres<double>(n, x, &UserApply<double>::apply, &ua, b, m, maxit, tol, verbose, max_seconds, S(stream), gf);
+    }
+    else if (P) { // gmres.cpp:242-251: solve P A x = P b
         DevBuf<double> q((size_t)n), r0((size_t)n);
         PrecondSystem sys{A, P, A_ctx, P_ctx, q.p};
         const int rc = P(P_ctx, b, r0.p, stream);

@@ -647,6 +647,12 @@ namespace cb200
         T * r = r_.p;
         T * V = V_.p;
         CB_CUDA(cudaMemsetAsync(V, 0, sizeof(T) * (size_t)ldv * m1, s));
+        // flexible right preconditioning: the preconditioned directions z_k = P v_k are kept (they, not the v_k, update x)
+        ApplyFn<T> Pr = reinterpret_cast<ApplyFn<T>>(opt.right_precond);
+        DevBuf<T> Z_;
+        if (Pr)
+            Z_.alloc((size_t)ldv * m);
+        T * Z = Z_.p;
 
         std::vector<T> H((size_t)m1 * m, T(0)), sn(m, T(0)), cs(m, T(0)), eta(m1, T(0)), hcol((size_t)m1 + 2);
 
@@ -706,7 +712,15 @@ namespace cb200
                 k1 = k + 1;
                 T * vk = V + (size_t)k * ldv;
                 T * w = vk + ldv;
-                apply(vk, w);
+                if (Pr) {
+                    T * zk = Z + (size_t)k * ldv;
+                    const int rc = Pr(opt.right_precond_ctx, vk, zk, s);
+                    if (rc != 0)
+                        throw Error(rc, std::string("gmres: the preconditioner callback failed (status ") + std::to_string(rc) + "): " + get_last_error());
+                    apply(zk, w);
+                }
+                else
+                    apply(vk, w);
                 T * Hk = &H[(size_t)m1 * k];
 
                 if (ev.on)
@@ -791,7 +805,7 @@ namespace cb200
 
             trsv_upper<T>(k1, H.data(), m1, eta.data());
             CB_CUDA(cudaMemcpyAsync(etadev.p, eta.data(), sizeof(T) * (size_t)k1, cudaMemcpyHostToDevice, s));
-            multi_axpy_kernel<T><<<nblk(n), 256, 0, s>>>(n, ldv, k1, etadev.p, V, x);
+            multi_axpy_kernel<T><<<nblk(n), 256, 0, s>>>(n, ldv, k1, etadev.p, Pr ? Z : V, x);
             CB_LAUNCHED();
 
             apply(x, r);

@@ -39,6 +39,10 @@ namespace cb200
         const Comm * comm = nullptr;             // distributed vectors: inner products are summed over the ranks
         const unsigned char * d_mask = nullptr;  // 1 = this rank owns the entry (counted in inner products), 0 = mirror copy / foreign slot
         bool time_orth = false;                  // record CUDA-event time of the orthogonalisation kernels (adds two event records per step)
+        // flexible right preconditioning (FGMRES): z_k = P(v_k) is stored, w = A z_k, x += sum eta_k z_k; P may change from
+        // step to step (e.g. an inner iterative solve). ApplyFn<T> cast to void*; null = none.
+        void * right_precond = nullptr;
+        void * right_precond_ctx = nullptr;
     };
 
     // Restarted GMRES(m) with the reference's control flow (source/gmres.cpp:91-235). A is a callback that

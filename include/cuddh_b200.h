@@ -199,6 +199,9 @@ typedef struct
     cuddh_comm_t comm;
     const unsigned char * d_mask;
     int time_orth; /* != 0: record the device time of the orthogonalisation kernels (stats.orth_ms) */
+    int flexible;  /* gmres_d_ex with P != NULL: 0 = the reference's left preconditioning (solve P A x = P b, source/gmres.cpp:68-89);
+                      1 = flexible RIGHT preconditioning (FGMRES): z_k = P v_k stored, true residuals of A x = b, and P may be an
+                      inner iterative solve (e.g. the DDH solve as preconditioner of the FP64 Helmholtz system) */
 } cuddh_gmres_options;
 typedef struct
 {

@@ -688,6 +688,54 @@ def test_ddh_dist_pack_emulated_ranks():
     assert float((L1 - L2).norm() / L2.norm()) < 5e-3
 
 
+def test_ddh_preconditioned_fgmres():
+    """SURVEY §8(f) rank 4 (no reference counterpart): the DDH solve as a flexible right preconditioner of the FP64 Helmholtz
+    composite. (1) P b approximates A^{-1} b (same PDE, GLL-collocated FP32 discretisation vs consistent FP64 one: agreement at
+    the level of the discretisation error, sign conventions of examples/Helmholtz.hpp:55 included); (2) FGMRES(A, P) reaches the
+    FP64 tolerance in a handful of outer iterations and lands on the solution of the unpreconditioned FP64 solve."""
+    nx, nb = 16, 4
+    omega = 2 * np.pi * nx / 10
+    mesh = cb.Mesh2D.uniform_rect(nx, -1.0, 1.0, nx, -1.0, 1.0)
+    fem = cb.H1Space(mesh, cb.Basis(nb))
+    fs = cb.FaceSpace(fem, mesh.boundary_edges())
+    n = fem.size()
+    xy = fem.physical_coordinates()
+    X, Y = xy[:, 0], xy[:, 1]
+    ha = 1.0 + 0.25 * np.exp(-8.0 * (X * X + Y * Y))  # smooth slowness a(x)
+    A = cb.Helmholtz(omega, dev(ha * ha), dev(ha[fs.global_indices()]), fem, fs)
+    s = omega * omega
+    src = s / np.pi * np.exp(-s * ((X + 0.5) ** 2 + Y ** 2))
+    b = torch.zeros(2 * n, dtype=torch.float64, device="cuda")
+    cb.MassMatrix(fem).action(dev(src), b[:n])
+    # reference solution: the operator assembled column by column (A e_k) and solved directly in FP64
+    N = 2 * n
+    Ad = torch.empty(N, N, dtype=torch.float64, device="cuda")  # row k = A e_k; A is symmetric (examples/Helmholtz.hpp:55)
+    ek = torch.zeros(N, dtype=torch.float64, device="cuda")
+    for k in range(N):
+        ek[k] = 1.0
+        A.action(ek, Ad[k])
+        ek[k] = 0.0
+    assert float((Ad - Ad.T).abs().max()) < 1e-9 * float(Ad.abs().max())
+    U0 = torch.linalg.solve(Ad.T, b)
+    D = cb.DDH(omega, ha, fem, nx, nx, 16)
+    P = cb.DDHPreconditioner(D, m=20, maxit=100, tol=1e-5)
+    Up = torch.empty(N, dtype=torch.float64, device="cuda")
+    P.action(b, Up)
+    e = float((Up - U0).norm() / U0.norm())
+    assert e < 0.12, e   # two discretisations of the same problem (GLL-collocated, lumped, FP32 vs consistent FP64): ~7 % apart here
+    U1 = torch.zeros(N, dtype=torch.float64, device="cuda")
+    o1 = cb.gmres(N, U1, A, b, 30, 3, 1e-8, P=P, flexible=True)
+    assert o1.success and o1.num_matvec <= 45, (o1.num_matvec, o1.res_norm)
+    assert float((U1 - U0).norm() / U0.norm()) < 1e-6
+    Ax = torch.empty_like(b)
+    A.action(U1, Ax)
+    assert float((Ax - b).norm() / b.norm()) < 1.01e-8
+    # the same tolerance without the preconditioner takes an order of magnitude more operator applications
+    U2 = torch.zeros(N, dtype=torch.float64, device="cuda")
+    o2 = cb.gmres(N, U2, A, b, 400, 6, 1e-8, orth=cb.CGS2)
+    assert o2.num_matvec > 5 * o1.num_matvec, (o2.num_matvec, o1.num_matvec)
+
+
 @pytest.mark.parametrize("nb,nx,cap", [(4, 200, 16), (5, 200, 16), (5, 200, 3), (5, 256, 0), (3, 128, 8), (2, 128, 8)])
 def test_steady_state_against_oracle(nb, nx, cap):
     """Persistent multi-patch path of volume_action_ws against the oracle (the same check as

@@ -23,6 +23,16 @@ def ref(*args, timeout=600):
         return read_rdmp(f.name)
 
 
+SPREAD_NOTE = ("north_star: +-1; the reference's own count is not reproducible on long solves - FP32 shared-memory atomicAdd in "
+               "source/DDH.cpp:108 - observed 80..82 restarts over three runs at (nx, n_basis) = (8, 8), against a bitwise reproducible 80 here")
+
+
+def restart_slack(ref_it):
+    """+-1 restart for every solve that converges within 30 restarts (north_star); longer solves get the reference's own
+    run-to-run spread (about 2.5 % of the count, see SPREAD_NOTE), never less than 1"""
+    return 1 if ref_it <= 30 else max(1, int(round(0.025 * ref_it)))
+
+
 def product_mesh(spec):
     if spec.startswith("rect:"):
         nx = int(spec[5:])
@@ -202,10 +212,8 @@ def test_helmholtz_gmres_matches_reference(spec, nb, m, maxit, tol):
     U = torch.zeros(2 * n, dtype=torch.float64, device="cuda")
     out = cb.gmres(2 * n, U, A, dev(r["b"]), m, maxit, tol)
     assert out.success == bool(r["success"][0])
-    # restart count: +-1, widened to 5 % for long solves - the reference's own count moves from run to run there (FP32
-    # shared-memory atomics: observed 80..82 restarts at (nx, nb) = (8, 8) against a reproducible 80 here)
     ref_it = int(r["num_iter"][0])
-    assert abs(out.num_iter - ref_it) <= max(1, int(round(0.05 * ref_it))), (out.num_iter, ref_it)
+    assert abs(out.num_iter - ref_it) <= restart_slack(ref_it), "restarts %d vs reference %d (%s)" % (out.num_iter, ref_it, SPREAD_NOTE)
     k = min(len(out.res_norm), len(r["res_norm"]))
     if out.success:
         assert rel(host(U), r["U"]) < 1e-3
@@ -256,10 +264,8 @@ def test_ddh_matches_reference(nx, nb):
     U = torch.empty(2 * fem.size(), dtype=torch.float64, device="cuda")
     D.postprocess(L, f, U)
     assert out.success == bool(r["success"][0])
-    # restart count: +-1, widened to 5 % for long solves - the reference's own count moves from run to run there (FP32
-    # shared-memory atomics: observed 80..82 restarts at (nx, nb) = (8, 8) against a reproducible 80 here)
     ref_it = int(r["num_iter"][0])
-    assert abs(out.num_iter - ref_it) <= max(1, int(round(0.05 * ref_it))), (out.num_iter, ref_it)
+    assert abs(out.num_iter - ref_it) <= restart_slack(ref_it), "restarts %d vs reference %d (%s)" % (out.num_iter, ref_it, SPREAD_NOTE)
     if out.success:
         assert rel(host(U), r["U"]) < 1e-3, rel(host(U), r["U"])
     else:
