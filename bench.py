@@ -332,41 +332,83 @@ def main():
 
 
 def roofline_block(cb, torch, slab, x, y, nb, nx, ndof, ms_step, K):
+    """roofline of the dominant kernel (the fused Helmholtz volume kernel; > 90 % of the step), timed alone with CUDA events on its
+    stream. `achieved` / `frac` use the ALGORITHMIC bytes of SURVEY §8(d) (the reference's stored-metric formulation: 24 nq_S^2 + 8
+    nq_M^2 + 4 nb^2 + 32 (nb-1)^2 per element). On a uniform (all-affine) mesh the library runs the stiffness phase from three
+    per-element constants instead of the stored metric, so fewer bytes actually move: `moved` carries the roofline of THAT
+    formulation, and `stored_metric` the same measurement with the stored-metric kernel (CUDDH_B200_AFFINE=0) - both rooflines."""
     peak, peak_src = measured_peaks()
     nqs, nqm = nb + 1, 1 + 3 * nb // 2 + 1
     u, yy = x[:ndof], y[:ndof]
     reps = max(K, 20)
+
+    def measure(op, xa, ya, step_ms=None):
+        # the dominant kernel cannot take longer than the step it is part of: re-measure (clock ramp) if it seems to
+        for attempt in range(3):
+            ms_patch, ms_rest = op.time_phases(xa, ya, reps)
+            if step_ms is None or ms_patch + ms_rest <= 1.02 * step_ms:
+                break
+        return ms_patch, ms_rest
+
     fused = slab.op.is_fused()
     if fused:
         op, xa, ya = slab.op, x, y
-        kname = "volume_action_ws<%d,%d,stiffness,%d> (fused S - w^2 M on [u;v])" % (nb, nqs, nqm)
-        tkey = "helmholtz_%d_%d_%d_nx%d" % (nb, nqs, nqm, nx)
+        kname = "volume_action_ws<%d,%d,stiffness,%d%s> (fused S - w^2 M on [u;v])" % (nb, nqs, nqm, ",affine" if op.is_affine() else "")
+        tkey = "helmholtz%s_%d_%d_%d_nx%d" % ("_affine" if op.is_affine() else "", nb, nqs, nqm, nx)
     else:
         op, xa, ya = cb.StiffnessMatrix(slab.fem), u, yy
         kname, tkey = "volume_action_kernel<%d,%d,stiffness>" % (nb, nqs), "stiffness_%d_%d_nx%d" % (nb, nqs, nx)
-    # the dominant kernel cannot take longer than the step it is part of: re-measure (clock ramp, another process) if it seems to
-    for attempt in range(3):
-        ms_patch, ms_rest = op.time_phases(xa, ya, reps)
-        if not fused or ms_patch + ms_rest <= 1.02 * ms_step:
-            break
-    bytes_k = op.algorithmic_bytes()
+    ms_patch, ms_rest = measure(op, xa, ya, ms_step if fused else None)
+    bytes_k, bytes_m = op.algorithmic_bytes(), op.moved_bytes()
     roof = {"bound": "hbm", "kernel": kname, "achieved": bytes_k / (ms_patch * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "peak_source": peak_src, "ms_per_launch": ms_patch, "algorithmic_bytes": bytes_k, "rest_of_step_ms": ms_rest,
             "timing": "median of %d launches after 3 warm applies, CUDA events on the launch stream" % reps,
-            "consistent_with_step": bool(not fused or ms_patch + ms_rest <= 1.02 * ms_step), "traffic": None}
+            "consistent_with_step": bool(not fused or ms_patch + ms_rest <= 1.02 * ms_step), "traffic": None,
+            "formulation": ("stiffness metric from 3 per-element constants (all elements affine), mass metric stored" if op.is_affine()
+                            else "stored metric (the reference's formulation)")}
     roof["frac"] = roof["achieved"] / peak
+    roof["moved"] = {"bytes": bytes_m, "achieved": bytes_m / (ms_patch * 1e-3) / 1e9, "frac": bytes_m / (ms_patch * 1e-3) / 1e9 / peak,
+                     "note": "algorithmic bytes of the formulation this kernel runs (equal to algorithmic_bytes unless affine)"}
+    flops = float(nx) * nx * 2 * (8 * nqs * nb * (nb + nqs) + 6 * nqs * nqs + 4 * nqm * nb * (nb + nqm) + nqm * nqm)
+    roof["fp64"] = {"flops": flops, "achieved_tflops": flops / (ms_patch * 1e-3) / 1e12,
+                    "note": "SURVEY §8(a) flop counts of S and M on both fields; the B200 FP64 FMA pipe issues one warp DFMA per 2 cycles per "
+                            "SM sub-partition (~37 TFLOP/s at 1965 MHz), see profiles/r02_notes.md for the ncu pipe utilisation"}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
             roof["traffic"] = json.load(open(tr)).get(tkey)
         except Exception:
             pass
+    if fused and op.is_affine():  # the other roofline: the stored-metric kernel on the same data
+        os.environ["CUDDH_B200_AFFINE"] = "0"
+        try:
+            gen = cb.Helmholtz(slab.op.omega, slab._a2, slab._af, slab.fem, slab.fs_phys)
+            assert not gen.is_affine()
+            yg = torch.empty_like(y)
+            gen.action(x, yg)
+            gp, gr = measure(gen, x, yg)
+            agree = float((yg - y).norm() / y.norm()) if slab.world == 1 else None  # y holds the last apply of the same x (N = 1)
+            gb = gen.algorithmic_bytes()
+            roof["stored_metric"] = {"kernel": "volume_action_ws<%d,%d,stiffness,%d> (CUDDH_B200_AFFINE=0)" % (nb, nqs, nqm), "ms_per_launch": gp,
+                                     "rest_of_step_ms": gr, "achieved": gb / (gp * 1e-3) / 1e9, "frac": gb / (gp * 1e-3) / 1e9 / peak,
+                                     "rel_diff_vs_affine_result": agree}
+            try:
+                roof["stored_metric"]["traffic"] = json.load(open(tr)).get("helmholtz_%d_%d_%d_nx%d" % (nb, nqs, nqm, nx))
+            except Exception:
+                pass
+            del gen, yg
+        except Exception as e:
+            roof["stored_metric"] = "failed: %r" % (e,)
+        finally:
+            del os.environ["CUDDH_B200_AFFINE"]
+        torch.cuda.empty_cache()
     Sop = cb.StiffnessMatrix(slab.fem)
     sp_, ss_ = Sop.time_phases(u, yy, reps)
     Mop = cb.MassMatrix(slab._a2, slab.fem)
     mp_, ms_ = Mop.time_phases(u, yy, reps)
-    per_op = {"stiffness": {"ms": sp_ + ss_, "gdofs": ndof / ((sp_ + ss_) * 1e-3) / 1e9, "kernel_ms": sp_,
-                            "hbm_frac_kernel": Sop.algorithmic_bytes() / (sp_ * 1e-3) / 1e9 / peak},
+    per_op = {"stiffness": {"ms": sp_ + ss_, "gdofs": ndof / ((sp_ + ss_) * 1e-3) / 1e9, "kernel_ms": sp_, "affine": Sop.is_affine(),
+                            "hbm_frac_kernel": Sop.algorithmic_bytes() / (sp_ * 1e-3) / 1e9 / peak,
+                            "hbm_frac_kernel_moved_bytes": Sop.moved_bytes() / (sp_ * 1e-3) / 1e9 / peak},
               "mass_weighted": {"ms": mp_ + ms_, "gdofs": ndof / ((mp_ + ms_) * 1e-3) / 1e9, "kernel_ms": mp_,
                                 "hbm_frac_kernel": Mop.algorithmic_bytes() / (mp_ * 1e-3) / 1e9 / peak},
               "helmholtz_composite": {"ms": ms_step, "hbm_frac_fused_formulation": slab.op.algorithmic_bytes() / (ms_step * 1e-3) / 1e9 / peak}}

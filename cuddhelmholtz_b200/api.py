@@ -308,6 +308,13 @@ class Operator:
     def algorithmic_bytes(self):
         return int(load().cuddh_b200_operator_bytes(self._h))
 
+    def moved_bytes(self):
+        """bytes of the formulation this handle runs (affine meshes: per-element metric constants instead of the stored metric)"""
+        return int(load().cuddh_b200_operator_bytes_moved(self._h))
+
+    def is_affine(self):
+        return bool(load().cuddh_b200_operator_is_affine(self._h))
+
     def kernel_kind(self):
         """0 lane-per-row / generic kernel, 1 warp-specialised thread-per-element kernel, 2 fused Helmholtz kernel, -1 n/a."""
         return int(load().cuddh_b200_operator_kernel_kind(self._h))

@@ -95,6 +95,8 @@ def _proto(lib):
         "cuddh_b200_operator_destroy": (C.c_int, [c_vp]),
         "cuddh_b200_operator_bytes": (c_i64, [c_vp]),
         "cuddh_b200_operator_kernel_kind": (C.c_int, [c_vp]),
+        "cuddh_b200_operator_bytes_moved": (c_i64, [c_vp]),
+        "cuddh_b200_operator_is_affine": (C.c_int, [c_vp]),
         "cuddh_b200_h1space_check_plan": (C.c_int, [c_vp, C.c_int, P(c_i64)]),
         "cuddh_b200_axpby_d": (C.c_int, [c_i64, C.c_double, c_dp, C.c_double, c_dp, c_vp]),
         "cuddh_b200_axpby_f": (C.c_int, [c_i64, C.c_float, c_dp, C.c_float, c_dp, c_vp]),

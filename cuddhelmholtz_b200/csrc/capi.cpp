@@ -451,6 +451,22 @@ int64_t cuddh_b200_operator_bytes(cuddh_operator_t op)
     }
     return 0;
 }
+int64_t cuddh_b200_operator_bytes_moved(cuddh_operator_t op)
+{
+    if (op->vol)
+        return (int64_t)op->vol->moved_bytes();
+    if (op->helm)
+        return (int64_t)op->helm->moved_bytes();
+    return 0;
+}
+int cuddh_b200_operator_is_affine(cuddh_operator_t op)
+{
+    if (op->vol)
+        return op->vol->affine ? 1 : 0;
+    if (op->helm)
+        return op->helm->S->affine ? 1 : 0;
+    return 0;
+}
 int cuddh_b200_operator_kernel_kind(cuddh_operator_t op)
 {
     if (op->vol)

@@ -215,6 +215,9 @@ namespace cb200
         std::unique_ptr<Plan> plan_tpe;  // node-major plan with 32-multiple patches (thread-per-element kernels), lazy
         DevBuf<int> d_tr_ptr, d_tr_src;  // transposed map DOF -> element-local entries (ordered assembly), lazy
         void ensure_transpose();
+        // every element a parallelogram (constant Jacobian)? true for Mesh2D::uniform_rect; decided once, on the host
+        bool all_affine();
+        int affine_state = -1;
 
         H1Space(const Mesh * mesh, int nb);
         const int * device_I();

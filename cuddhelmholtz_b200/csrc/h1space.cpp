@@ -9,6 +9,8 @@
 //
 // Compile without FP contraction (-ffp-contract=off) so xy is bit-identical to the reference's host pass.
 #include "common.hpp"
+#include <atomic>
+#include <cmath>
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -99,6 +101,27 @@ namespace cb200
             d_xy.upload(xy);
         return d_xy.p;
     }
+    bool H1Space::all_affine()
+    {
+        if (affine_state < 0) {
+            // x0 - x1 + x2 - x3 == 0 (both coordinates) up to rounding of the vertex coordinates
+            std::atomic<int> bad{0};
+            const Mesh & m = *mesh;
+            parallel_for(m.n_elem, [&](int64_t b, int64_t e, int) {
+                for (int64_t el = b; el < e && !bad.load(std::memory_order_relaxed); ++el) {
+                    double c[8];
+                    m.corners(el, c);
+                    const double ex = c[0] - c[2] + c[4] - c[6], ey = c[1] - c[3] + c[5] - c[7];
+                    const double h = std::fabs(c[2] - c[0]) + std::fabs(c[3] - c[1]) + std::fabs(c[6] - c[0]) + std::fabs(c[7] - c[1]);
+                    if (std::fabs(ex) + std::fabs(ey) > 1e-14 * h)
+                        bad.store(1, std::memory_order_relaxed);
+                }
+            });
+            affine_state = bad.load() ? 0 : 1;
+        }
+        return affine_state == 1;
+    }
+
     const double * H1Space::device_corners()
     {
         if (!d_corners.p) {

@@ -60,6 +60,9 @@ namespace cb200
             double Pcol[NB][NQP];
             double Drow[STIFF ? NQ : 1][NBP];
             double Dcol[STIFF ? NB : 1][NQP];
+            // rows scaled by the quadrature weight, PWrow[q][k] = w_q P(q,k): back-contractions of the affine stiffness phase
+            double PWrow[STIFF ? NQ : 1][NBP];
+            double DWrow[STIFF ? NQ : 1][NBP];
         };
 
         // Padded layout of the per-element transpose scratch: element stride S, row stride RS, offset HALF of the second
@@ -636,6 +639,32 @@ namespace cb200
             G[metric_index(p, e, PE, NQ, EPW, n_pass, 3, i, j, 2)] = g2;
         }
 
+        // affine stiffness: gA, gB, gC of the element in slot (p, e), layout ((p * 3 + c) * PE + e); Jacobian of a parallelogram
+        // (source/Element.cpp:21-27 with x1 - x0 == x2 - x3), the W = w_i w_j factor lives in the kernel's weighted tables
+        __global__ void setup_stiffness_affine_kernel(const int64_t n_slots, const int PE, const int * __restrict__ slot_elem,
+                                                      const double * __restrict__ corners, double * __restrict__ Gc)
+        {
+            const int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+            if (slot >= n_slots)
+                return;
+            const int64_t p = slot / PE;
+            const int e = (int)(slot - p * PE);
+            const int el = slot_elem[slot];
+            double gA = 0.0, gB = 0.0, gC = 0.0;
+            if (el >= 0) {
+                double J[4];
+                bilinear_jacobian(corners + 8 * (size_t)el, 0.0, 0.0, J);
+                const double X_xi = J[0], Y_xi = J[1], X_eta = J[2], Y_eta = J[3];
+                const double det = X_xi * Y_eta - X_eta * Y_xi;
+                gA = (Y_eta * Y_eta + X_eta * X_eta) / det;
+                gB = -(Y_xi * Y_eta + X_xi * X_eta) / det;
+                gC = (Y_xi * Y_xi + X_xi * X_xi) / det;
+            }
+            Gc[((size_t)p * 3 + 0) * PE + e] = gA;
+            Gc[((size_t)p * 3 + 1) * PE + e] = gB;
+            Gc[((size_t)p * 3 + 2) * PE + e] = gC;
+        }
+
         __global__ void setup_mass_kernel(const int64_t n_slots, const int PE, const int NB, const int NQ, const int EPW,
                                           const int n_pass, const int * __restrict__ slot_elem,
                                           const double * __restrict__ corners, const int * __restrict__ I,
@@ -978,11 +1007,15 @@ namespace cb200
                     if (STIFF) {
                         tab.Drow[q][k] = op.D[q + NQ * k];
                         tab.Dcol[k][q] = op.D[q + NQ * k];
+                        if (!op.wq.empty()) {
+                            tab.PWrow[q][k] = op.wq[q] * op.P[q + NQ * k];
+                            tab.DWrow[q][k] = op.wq[q] * op.D[q + NQ * k];
+                        }
                     }
                 }
         }
 
-        template <int NB, int NQ, bool STIFF, int NQ2, int RING = 0>
+        template <int NB, int NQ, bool STIFF, int NQ2, int RING = 0, bool AFFINE = false>
         void launch_ws(const VolumeOp & op, const VolumeOp * op2, const PlanDev & pd, const Plan & plan, const WsArgs & args, cudaStream_t s)
         {
             CB_REQUIRE(plan.PE == 128, "warp-specialised kernel: patches must hold 128 elements");
@@ -998,7 +1031,7 @@ namespace cb200
             std::memset(&tab2, 0, sizeof(tab2));
             if constexpr (NQ2 > 0)
                 fill_tables(tab2, *op2);
-            auto kern = volume_action_ws<NB, NQ, STIFF, NQ2, RING>;
+            auto kern = volume_action_ws<NB, NQ, STIFF, NQ2, RING, AFFINE>;
             // one wave of resident CTAs, cached per device (function attributes are per device too)
             static int grid_of_device[MAX_DEVICES] = {};
             int dev = 0;
@@ -1056,13 +1089,14 @@ namespace cb200
             CB_LAUNCHED();
         }
 
-        template <int NB, int NQ, bool STIFF, int RING = 0>
+        template <int NB, int NQ, bool STIFF, int RING = 0, bool AFFINE = false>
         void launch_volume_ws(VolumeOp & op, const PlanDev & pd, const Plan & plan, double c, int accumulate, const double * x,
                               double * y, cudaStream_t s)
         {
             WsArgs a{};
             a.G1 = reinterpret_cast<const double2 *>(op.d_G.p);
             a.G2 = nullptr;
+            a.Gc = op.d_Gc.p;
             a.x = x;
             a.y = y;
             a.partial = op.d_partial.p;
@@ -1071,12 +1105,22 @@ namespace cb200
             a.accumulate = accumulate;
             a.n_patches = (int)plan.n_patches;
             a.n_fields = 1;
-            launch_ws<NB, NQ, STIFF, 0, RING>(op, nullptr, pd, plan, a, s);
+            launch_ws<NB, NQ, STIFF, 0, RING, AFFINE>(op, nullptr, pd, plan, a, s);
         }
 
         using LaunchFn = void (*)(VolumeOp &, const PlanDev &, const Plan &, double, int, const double *, double *, cudaStream_t);
 
         // thread-per-element instances: n_basis <= 5 (U and the result fit in registers next to the row temporaries)
+        // stiffness on all-affine meshes (VolumeOp::affine): per-element metric constants, no metric stream
+        LaunchFn find_affine_instance(int nb, int nq)
+        {
+            if (nb == 5 && nq == 6)
+                return &launch_volume_ws<5, 6, true, 0, true>;
+            if (nb == 4 && nq == 5)
+                return &launch_volume_ws<4, 5, true, 0, true>;
+            return nullptr;
+        }
+
         template <bool STIFF>
         LaunchFn find_tpe_instance(int nb, int nq)
         {
@@ -1133,8 +1177,15 @@ namespace cb200
             return nullptr;
         }
         using FusedFn = void (*)(const VolumeOp &, const VolumeOp *, const PlanDev &, const Plan &, const WsArgs &, cudaStream_t);
-        FusedFn find_fused_instance(int nb, int nqs, int nqm)
+        FusedFn find_fused_instance(int nb, int nqs, int nqm, bool affine = false)
         {
+            if (affine) {
+                if (nb == 5 && nqs == 6 && nqm == 9)
+                    return &launch_ws<5, 6, true, 9, 5, true>;
+                if (nb == 4 && nqs == 5 && nqm == 8)
+                    return &launch_ws<4, 5, true, 8, 5, true>;
+                return nullptr;
+            }
             static const int ring = env_int("CUDDH_B200_RING", 5);
 #define CB_CASE(NB_, NQS_, NQM_)                                                                                       \
     if (nb == NB_ && nqs == NQS_ && nqm == NQM_)                                                                       \
@@ -1166,7 +1217,7 @@ namespace cb200
         PlanDev pd{plan.d_hdr.p, plan.d_gid.p, plan.d_slot.p, plan.d_L.p, plan.d_cptr.p, plan.d_cent.p, plan.PE, plan.d_Ig.p, reinterpret_cast<const uint2 *>(plan.d_cent4.p), plan.d_target.p};
         LaunchFn fn = generic ? nullptr : (stiff ? find_instance<true>(nb, nq) : find_instance<false>(nb, nq));
         if (tpe)
-            fn = stiff ? find_tpe_instance<true>(nb, nq) : find_tpe_instance<false>(nb, nq);
+            fn = affine ? find_affine_instance(nb, nq) : (stiff ? find_tpe_instance<true>(nb, nq) : find_tpe_instance<false>(nb, nq));
         if (!(phases & 1)) {
         }
         else if (fn)
@@ -1197,9 +1248,17 @@ namespace cb200
         return per * (size_t)fem->n_elem;
     }
 
+    size_t VolumeOp::moved_bytes() const
+    {
+        if (!affine)
+            return algorithmic_bytes();
+        const size_t per = 24 + 4 * (size_t)nb * nb + 16 * (size_t)(nb - 1) * (nb - 1);
+        return per * (size_t)fem->n_elem;
+    }
+
     namespace
     {
-        void init_volume_common(VolumeOp & op, H1Space * fem, int nq, bool stiff, bool force_generic)
+        void init_volume_common(VolumeOp & op, H1Space * fem, int nq, bool stiff, bool force_generic, bool want_affine = false)
         {
             op.fem = fem;
             op.nb = fem->nb;
@@ -1212,13 +1271,18 @@ namespace cb200
             LaunchFn ft = stiff ? find_tpe_instance<true>(op.nb, nq) : find_tpe_instance<false>(op.nb, nq);
             op.tpe = !op.generic && ft != nullptr && env_int("CUDDH_B200_TPE", 1) != 0;
             op.nk = (stiff ? 3 : 1) * nq;
+            op.affine = want_affine && stiff && op.tpe && find_affine_instance(op.nb, nq) != nullptr && env_int("CUDDH_B200_AFFINE", 1) != 0 &&
+                        fem->all_affine();
             if (op.tpe) { // thread-per-element layout: [pair of metric values][element], see volume_action_ws
                 op.plan = &fem->get_plan_tpe();
                 op.epw = 0;
                 op.lw = 0;
                 op.n_pass = 0;
                 const int KR = (op.nk + 1) & ~1;
-                op.d_G.alloc((size_t)op.plan->n_patches * (size_t)(nq * KR) * op.plan->PE);
+                if (op.affine)
+                    op.d_Gc.alloc((size_t)op.plan->n_patches * 3 * op.plan->PE);
+                else
+                    op.d_G.alloc((size_t)op.plan->n_patches * (size_t)(nq * KR) * op.plan->PE);
             }
             else {
                 op.plan = &fem->get_plan();
@@ -1229,7 +1293,8 @@ namespace cb200
             }
             Plan & plan = *op.plan;
             op.d_partial.alloc((size_t)std::max<int64_t>(plan.n_slots_total, 1));
-            CB_CUDA(cudaMemset(op.d_G.p, 0, op.d_G.n * sizeof(double)));
+            if (op.d_G.n)
+                CB_CUDA(cudaMemset(op.d_G.p, 0, op.d_G.n * sizeof(double)));
         }
     } // namespace
 
@@ -1239,9 +1304,10 @@ namespace cb200
         if (nq <= 0)
             nq = fem->nb + 1; // mesh.max_element_order() (=1) + n_basis, StiffnessMatrix.cpp:45
         CB_REQUIRE(nq <= 24, "StiffnessMatrix::action does not support quadrature rules with more than 24 points.");
-        init_volume_common(*op, fem, nq, true, getenv("CUDDH_B200_FORCE_GENERIC") != nullptr);
+        init_volume_common(*op, fem, nq, true, getenv("CUDDH_B200_FORCE_GENERIC") != nullptr, quad_type == GAUSS_LEGENDRE);
         std::vector<double> xq(nq), wq(nq);
         quadrature_rule(nq, quad_type, xq.data(), wq.data());
+        op->wq = wq;
         op->P.resize((size_t)nq * fem->nb);
         op->D.resize((size_t)nq * fem->nb);
         fem->basis->eval(nq, xq.data(), op->P.data());
@@ -1253,8 +1319,11 @@ namespace cb200
         d_w.upload(wq);
         Plan & plan = *op->plan;
         const int64_t n_slots = plan.n_patches * plan.PE;
-        setup_stiffness_kernel<<<blocks_for(n_slots * nq * nq, 256), 256>>>(n_slots, plan.PE, nq, op->epw, op->n_pass, plan.d_slot_elem.p,
-                                                                            fem->device_corners(), d_x.p, d_w.p, op->d_G.p);
+        if (op->affine)
+            setup_stiffness_affine_kernel<<<blocks_for(n_slots, 256), 256>>>(n_slots, plan.PE, plan.d_slot_elem.p, fem->device_corners(), op->d_Gc.p);
+        else
+            setup_stiffness_kernel<<<blocks_for(n_slots * nq * nq, 256), 256>>>(n_slots, plan.PE, nq, op->epw, op->n_pass, plan.d_slot_elem.p,
+                                                                                fem->device_corners(), d_x.p, d_w.p, op->d_G.p);
         CB_LAUNCHED();
         CB_CUDA(cudaDeviceSynchronize());
         return op;
@@ -1536,7 +1605,8 @@ namespace cb200
         op->S = make_stiffness(fem, 0, GAUSS_LEGENDRE);
         op->M = make_mass(fem, d_a2, 0);
         op->H = make_facemass(fs, d_a, 0);
-        op->fused = op->S->tpe && op->M->tpe && op->S->plan == op->M->plan && find_fused_instance(op->S->nb, op->S->nq, op->M->nq) != nullptr &&
+        op->fused = op->S->tpe && op->M->tpe && op->S->plan == op->M->plan &&
+                    find_fused_instance(op->S->nb, op->S->nq, op->M->nq, op->S->affine) != nullptr &&
                     env_int("CUDDH_B200_FUSED", 1) != 0;
         if (op->fused)
             op->d_partial2.alloc(2 * (size_t)std::max<int64_t>(op->S->plan->n_slots_total, 1));
@@ -1561,6 +1631,7 @@ namespace cb200
             WsArgs a{};
             a.G1 = reinterpret_cast<const double2 *>(S->d_G.p);
             a.G2 = reinterpret_cast<const double2 *>(M->d_G.p);
+            a.Gc = S->d_Gc.p;
             a.x = x;
             a.y = y;
             a.partial = d_partial2.p;
@@ -1573,7 +1644,7 @@ namespace cb200
             a.n_patches = (int)plan.n_patches;
             a.n_fields = 2;
             if (phases & 1)
-                find_fused_instance(S->nb, S->nq, M->nq)(*S, M.get(), pd, plan, a, s);
+                find_fused_instance(S->nb, S->nq, M->nq, S->affine)(*S, M.get(), pd, plan, a, s);
             if (!(phases & 2))
                 return;
             if (plan.n_shared > 0) {
@@ -1620,6 +1691,13 @@ namespace cb200
             apply(x, y, s);
             halo.exchange(y, s);
         }
+    }
+
+    size_t HelmholtzOp::moved_bytes() const
+    {
+        const size_t nb = S->nb, nqs = S->nq, nqm = M->nq;
+        const size_t metric_s = S->affine ? 24 : 24 * nqs * nqs;
+        return (metric_s + 8 * nqm * nqm + 4 * nb * nb + 32 * (nb - 1) * (nb - 1)) * (size_t)fem->n_elem;
     }
 
     size_t HelmholtzOp::algorithmic_bytes() const

@@ -17,7 +17,10 @@ namespace cb200
         bool stiff = false;
         std::vector<double> P, D;     // (nq, nb) column-major tables
         DevBuf<double> d_P, d_D;      // device copies (generic kernel)
+        std::vector<double> wq;       // quadrature weights (stiffness; folded into the tables of the affine path)
         DevBuf<double> d_G;           // plan-ordered metric data: stiffness 3 comps, mass 1 comp
+        DevBuf<double> d_Gc;          // affine stiffness: per patch (3, PE) element constants gA, gB, gC instead of d_G
+        bool affine = false;          // stiffness on a mesh whose elements are all parallelograms: metric = w_i w_j * per-element constants
         DevBuf<double> d_partial;     // partial sums of patch-boundary DOFs
         int epw = 0, lw = 0, n_pass = 0, nk = 0;  // layout constants (see operators.cu)
         bool generic = false;
@@ -26,7 +29,8 @@ namespace cb200
 
         // phases: bit 0 = patch kernel, bit 1 = shared-DOF assembly pass (3 = the full action)
         void apply(double c, int accumulate, const double * x, double * y, cudaStream_t s, int phases = 3);
-        size_t algorithmic_bytes() const; // SURVEY §8(d) per-element bytes * n_elem
+        size_t algorithmic_bytes() const; // SURVEY §8(d) per-element bytes * n_elem (the reference's stored-metric formulation)
+        size_t moved_bytes() const;       // the same count for the formulation this handle actually runs (affine: 24 B of metric per element)
     };
 
     std::unique_ptr<VolumeOp> make_stiffness(H1Space * fem, int nq, int quad_type);
@@ -107,6 +111,7 @@ namespace cb200
         // neighbour exchange, add. 4 launches + one grouped send/recv (fused path).
         void apply_slab(const double * x, double * y, SlabHalo & halo, cudaStream_t s);
         size_t algorithmic_bytes() const;
+        size_t moved_bytes() const;
     };
     std::unique_ptr<HelmholtzOp> make_helmholtz(double omega, const double * d_a2, const double * d_a, H1Space * fem, FaceSpace * fs);
 } // namespace cb200

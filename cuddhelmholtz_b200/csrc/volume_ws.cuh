@@ -351,6 +351,61 @@
             }
         }
 
+        // Stiffness phase on AFFINE elements (parallelograms - every element of Mesh2D::uniform_rect): the Jacobian is constant per
+        // element, so G(tx, ty) = w_tx w_ty (gA, gB, gC) with three per-element numbers (source/StiffnessMatrix.cpp:5-38 evaluates
+        // the same expression point by point). The weights are folded into the back-contraction tables (PWrow = w_q P(q,.),
+        // DWrow = w_q D(q,.)), so the phase needs NO metric stream (24 instead of 24 nq^2 bytes per element), no ring slot, no
+        // mbarrier and no row barrier, and not one flop more than the stored-metric formulation:
+        //   F0' = gA Dx + gB Dy ; F1' = gB Dx + gC Dy ; a0 += PW(ty,.) F0' ; a1 += DW(ty,.) F1' ; out += DW(tx,.) a0 + PW(tx,.) a1
+        // Same numbers as the general path up to re-association (~1e-16 relative; the 1e-12 parity tests cover both paths).
+        template <int NB, int NQ>
+        __device__ __forceinline__ void contract_stiff_affine(const Tables<NB, NQ, true> & tab, const double (&U)[NB * NB], const double gA,
+                                                              const double gB, const double gC, double (&out)[NB * NB], const int zero)
+        {
+#pragma unroll 1
+            for (int tx = 0; tx < NQ; ++tx) {
+                const int z = tx * zero; // 0 at run time; keeps the ty-indexed table loads inside the rolled loop
+                double pu[NB], du[NB];
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int ii = 0; ii < NB; ++ii) {
+                        const double u = U[ii + NB * j];
+                        s0 = fma(tab.Prow[tx][ii], u, s0);
+                        s1 = fma(tab.Drow[tx][ii], u, s1);
+                    }
+                    pu[j] = s0;
+                    du[j] = s1;
+                }
+                double a0[NB], a1[NB];
+#pragma unroll
+                for (int q = 0; q < NB; ++q)
+                    a0[q] = a1[q] = 0.0;
+#pragma unroll
+                for (int ty = 0; ty < NQ; ++ty) {
+                    double Dx = 0.0, Dy = 0.0;
+#pragma unroll
+                    for (int l = 0; l < NB; ++l) {
+                        Dx = fma(tab.Prow[ty + z][l], du[l], Dx);
+                        Dy = fma(tab.Drow[ty + z][l], pu[l], Dy);
+                    }
+                    const double F0 = gA * Dx + gB * Dy;
+                    const double F1 = gB * Dx + gC * Dy;
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) {
+                        a0[q] = fma(tab.PWrow[ty + z][q], F0, a0[q]);
+                        a1[q] = fma(tab.DWrow[ty + z][q], F1, a1[q]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < NB; ++q)
+#pragma unroll
+                    for (int ii = 0; ii < NB; ++ii)
+                        out[ii + NB * q] = fma(tab.DWrow[tx][ii], a0[q], fma(tab.PWrow[tx][ii], a1[q], out[ii + NB * q]));
+            }
+        }
+
         // second-phase placeholder for the single-operator instances
         struct NoTables
         {
@@ -368,6 +423,7 @@
         {
             const double2 * G1;
             const double2 * G2;
+            const double * Gc; // AFFINE instances: per patch (3, 128) metric constants gA, gB, gC of every element slot
             const double * x;
             double * y;
             double * partial;
@@ -377,7 +433,9 @@
             int accumulate, n_patches, n_fields, zero;
         };
 
-        template <int NB, int NQ, bool STIFF, int NQ2, int RING>
+        // AFFINE (stiffness instances on meshes whose elements are all parallelograms): first phase = contract_stiff_affine, the
+        // ring (if any) carries the mass phase only.
+        template <int NB, int NQ, bool STIFF, int NQ2, int RING, bool AFFINE = false>
         __global__ void __launch_bounds__(256, 2)
         volume_action_ws(const __grid_constant__ Tables<NB, NQ, STIFF> tab, const __grid_constant__ typename Phase2<NB, NQ2>::type tab2,
                          const PlanDev plan, const __grid_constant__ WsArgs args)
@@ -393,7 +451,9 @@
             constexpr int FULL = 1, READY = 4, HELPER = 7; // named barrier ids (0 is __syncthreads)
             constexpr int NG = (NB2 + 3) / 4;                // groups of four nodes in the global index map
             constexpr int NI = (NB > 2 ? NB - 2 : 0) * (NB > 2 ? NB - 2 : 0); // element-interior nodes
-            constexpr bool HEAVY = STIFF && NB >= 5 && NQ2 > 0 && RING == 0; // register-path fused instance only
+            constexpr bool HEAVY = STIFF && NB >= 5 && NQ2 > 0 && RING == 0 && !AFFINE; // register-path fused instance only
+            static_assert(!AFFINE || STIFF, "AFFINE is a property of the stiffness phase");
+            static_assert(!AFFINE || NQ2 == 0 || RING > 0, "fused AFFINE instances feed the mass phase from the ring");
 
             // shared-memory metric ring (RING > 0): chunk = CHUNK_PAIRS x PE 16-byte pairs
             constexpr int CP1 = ring_cp(NPR1), CP2 = NQ2 > 0 ? ring_cp(NPR2) : 0;
@@ -466,7 +526,8 @@
                     if (f == 0) {
                         const int p2 = p + stride;
                         if (t == 0) {
-                            bulk_prefetch_l2(args.G1 + (size_t)p * g_patch1, g_patch1 * sizeof(double2));
+                            if (!AFFINE)
+                                bulk_prefetch_l2(args.G1 + (size_t)p * g_patch1, g_patch1 * sizeof(double2));
                             if (NQ2 > 0)
                                 bulk_prefetch_l2(args.G2 + (size_t)p * g_patch2, g_patch2 * sizeof(double2));
                         }
@@ -600,7 +661,8 @@
                 double g0[RING > 0 ? 1 : GK], g1[RING > 0 ? 1 : GK];
                 // ---- shared-memory metric ring: consumer state (all threads) and producer cursor (thread 0) ----
                 RingState rs{ring, smem_u32(mbars), 0, 0};
-                int cur_i = 0, cur_ph = 0, cur_r = 0, cur_h = 0; // next chunk of the stream to be issued: (patch iteration, phase, row, chunk)
+                constexpr int FIRST_PH = AFFINE ? 1 : 0; // AFFINE: the stream holds the mass rows only
+                int cur_i = 0, cur_ph = FIRST_PH, cur_r = 0, cur_h = 0; // next chunk of the stream to be issued: (patch iteration, phase, row, chunk)
                 auto issue = [&](const int slot) {
                     if (cur_i >= n_iter)
                         return;
@@ -621,7 +683,7 @@
                         if (++cur_r == nq) {
                             cur_r = 0;
                             if (++cur_ph == (NQ2 > 0 ? 2 : 1)) {
-                                cur_ph = 0;
+                                cur_ph = FIRST_PH;
                                 ++cur_i;
                             }
                         }
@@ -638,7 +700,7 @@
                         for (int k = 0; k < RING; ++k)
                             issue(k);
                 }
-                else {
+                else if constexpr (!AFFINE) {
                     const double2 * gpi = args.G1 + (size_t)cta * g_patch1 + e;
 #pragma unroll
                     for (int m = 0; m < NPR1; ++m) {
@@ -664,7 +726,19 @@
 #pragma unroll
                     for (int k = 0; k < NB2; ++k)
                         out[k] = 0.0;
-                    if constexpr (RING > 0) {
+                    if constexpr (AFFINE) {
+                        // metric constants of this thread's element; U in registers for both phases
+                        const double * gc = args.Gc + (size_t)p * (3 * PE) + e;
+                        const double gA = __ldg(gc), gB = __ldg(gc + PE), gC = __ldg(gc + 2 * PE);
+                        double U[NB2];
+#pragma unroll
+                        for (int k = 0; k < NB2; ++k)
+                            U[k] = b[k * PE];
+                        contract_stiff_affine<NB, NQ>(tab, U, gA, gB, gC, out, args.zero);
+                        if constexpr (NQ2 > 0)
+                            contract_phase_ring<NB, NQ2, false, PE, RING, CHUNK_PAIRS>(tab2, U, rs, e, out, args.msc, args.zero, t == 0, issue);
+                    }
+                    else if constexpr (RING > 0) {
                         // the ring leaves room in the register file: U stays in registers for all rows of both phases
                         double U[NB2];
 #pragma unroll

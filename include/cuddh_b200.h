@@ -132,6 +132,12 @@ int cuddh_b200_operator_time_phases(cuddh_operator_t op, const double * x, doubl
 int cuddh_b200_operator_destroy(cuddh_operator_t op);
 /* algorithmic bytes of one apply, 0 if not defined for this operator */
 int64_t cuddh_b200_operator_bytes(cuddh_operator_t op);
+/* the same count for the formulation the handle actually runs: on meshes whose elements are all parallelograms (every
+ * Mesh2D::uniform_rect) the stiffness metric is w_i w_j times three per-element constants, recomputed in registers instead of
+ * streamed (24 instead of 24 nq^2 bytes per element). bench.py reports both rooflines.
+ * CUDDH_B200_AFFINE=0 in the environment forces the stored-metric kernels. */
+int64_t cuddh_b200_operator_bytes_moved(cuddh_operator_t op);
+int cuddh_b200_operator_is_affine(cuddh_operator_t op);
 /* which kernel family serves this handle: 0 = lane-per-row patch kernel / generic, 1 = warp-specialised thread-per-element
  * kernel (n_basis <= 5), 2 = Helmholtz handle on the fused S - w^2 M path; -1 = not a volume operator */
 int cuddh_b200_operator_kernel_kind(cuddh_operator_t op);

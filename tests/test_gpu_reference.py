@@ -103,13 +103,19 @@ def test_operator_actions_match_reference_kernels(spec, nb):
 # prefetch, per-patch cluster barrier) against the reference's own kernels: every case gives each persistent CTA SEVERAL
 # patches - by size (256^2: 512 patches on <= 296 CTAs; 1024^2: 8192) or by capping the CTA count - and the warped mesh gives
 # every element its own metric block, so a stale ring slot or a wrong-patch read cannot hide.
-STEADY = [("rect:64", 4, 8), ("rect:64", 5, 8), ("rect:64", 5, 2), ("warp:200", 4, 16), ("warp:200", 5, 16), ("warp:256", 5, 0),
-          ("rect:256", 4, 0), ("rect:256", 5, 0), ("rect:256", 8, 0), ("warp:96", 8, 0), ("rect:1024", 5, 0)]
+# 4th entry: the stiffness formulation on uniform (all-affine) meshes - True = per-element metric constants (the default there),
+# False = CUDDH_B200_AFFINE=0, the stored-metric ring kernels that every other mesh uses
+STEADY = [("rect:64", 4, 8, True), ("rect:64", 5, 8, True), ("rect:64", 5, 2, False), ("rect:64", 4, 8, False),
+          ("warp:200", 4, 16, False), ("warp:200", 5, 16, False), ("warp:256", 5, 0, False),
+          ("rect:256", 4, 0, True), ("rect:256", 5, 0, True), ("rect:256", 5, 0, False), ("rect:256", 8, 0, False), ("warp:96", 8, 0, False),
+          ("rect:1024", 5, 0, True)]
 
 
-@pytest.mark.parametrize("spec,nb,cap", STEADY)
-def test_steady_state_matches_reference_kernels(spec, nb, cap, tmp_path):
+@pytest.mark.parametrize("spec,nb,cap,affine", STEADY)
+def test_steady_state_matches_reference_kernels(spec, nb, cap, affine, tmp_path, monkeypatch):
     omega = 10.0
+    if spec.startswith("rect:") and not affine:
+        monkeypatch.setenv("CUDDH_B200_AFFINE", "0")
     if spec.startswith("warp:"):
         xy, el = warped_mesh(int(spec[5:]))
         path = str(tmp_path / "warped.txt")
@@ -132,7 +138,7 @@ def test_steady_state_matches_reference_kernels(spec, nb, cap, tmp_path):
         S = cb.StiffnessMatrix(fem)
         n_patch = fem.check_plan(1)["n_patches"] if nb <= 5 else 0
         if nb <= 5:
-            assert S.kernel_kind() == 1
+            assert S.kernel_kind() == 1 and S.is_affine() == affine
             ctas = cap if cap else 296
             assert n_patch >= 1.7 * ctas, (n_patch, ctas)  # several patches per persistent CTA
         S.action(u, y)
@@ -146,7 +152,7 @@ def test_steady_state_matches_reference_kernels(spec, nb, cap, tmp_path):
         assert rel(host(y), r["Mw_acc"]) < tol
         A = cb.Helmholtz(omega, a2, af, fem, fs)
         if nb <= 5:
-            assert A.kernel_kind() == 2
+            assert A.kernel_kind() == 2 and A.is_affine() == affine
         Ax = torch.empty(2 * n, dtype=torch.float64, device="cuda")
         A.action(X, Ax)
         assert rel(host(Ax), r["helm_Ax"]) < tol
