@@ -608,6 +608,10 @@ def extras(args, cb, torch, slab, x, y):
         out["n_basis_8"] = high_order_ops(cb, torch, args.nx, 8, peak)
     except Exception as e:
         out["n_basis_8"] = "failed: %r" % (e,)
+    try:  # BASELINE configs[4] order on one GPU: n_basis 8 DDH action, the reference's block 16 and the config's block 32
+        out["ddh_n_basis_8"] = ddh_high_order(cb, torch, drv if os.path.exists(drv) else None)
+    except Exception as e:
+        out["ddh_n_basis_8"] = "failed: %r" % (e,)
     try:
         out["ddh_example_128"] = ddh_example(cb, torch, drv if os.path.exists(drv) else None)
     except Exception as e:
@@ -635,6 +639,37 @@ def high_order_ops(cb, torch, nx, nb, peak):
                      "hbm_frac_patch_kernel": op.algorithmic_bytes() / (pms * 1e-3) / 1e9 / peak}
         del op
         torch.cuda.empty_cache()
+    return res
+
+
+def ddh_high_order(cb, torch, drv, nx=128, nb=8):
+    """one DDH action at n_basis 8 (generic one-thread-per-node kernel: no register-tiled variant for this order yet)"""
+    omega = 2 * np.pi * nx / 10
+    mesh = cb.Mesh2D.uniform_rect(nx, -1.0, 1.0, nx, -1.0, 1.0)
+    fem = cb.H1Space(mesh, cb.Basis(nb))
+    res = {"nx": nx, "n_basis": nb, "omega": omega}
+    for block in (16, 32):
+        D = cb.DDH(omega, np.ones(fem.size()), fem, nx, nx, block)
+        m = D.size()
+        x = torch.rand(m, dtype=torch.float32, device="cuda")
+        y = torch.empty_like(x)
+        D.action(x, y)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        D.action(x, y)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        res["block_%d" % block] = {"n_domains": D.info()["n_domains"], "nt": D.info()["nt"], "action_ms": ms, "kernel_kind": D.kernel_kind(),
+                                   "action_fp32_tflops": D.flops() / (ms * 1e-3) / 1e12}
+        del D, x, y
+    if drv:
+        try:
+            r = subprocess.run([drv, "time_ddh", str(nx), str(nb), repr(float(omega)), "1"], capture_output=True, text=True, timeout=900)
+            res["reference_gpu_kernel_block_16"] = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as e:
+            res["reference_gpu_kernel_block_16"] = "failed: %r" % (e,)
     return res
 
 
