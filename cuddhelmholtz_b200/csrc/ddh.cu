@@ -410,6 +410,265 @@ namespace cb200
                 }
         }
 
+        // ------------------------------------------------------------------------------------------------------
+        // Register-tiled variant for n_basis 8 / block 16 (2 x 2 elements per subdomain, the reference's default block for that
+        // order) on uniform meshes: FOUR threads per element, each owning a 4 x 4 tile of the element's 8 x 8 nodes, 16 threads =
+        // one subdomain, two subdomains per warp - the thread geometry of ddh_kernel_reg4. An 8-term derivative sum takes four
+        // values from the own tile and four from the partner tile of the same element (one shfl.xor per value: lane ^ 1 in x,
+        // lane ^ 4 in y).
+        // Every thread works in a MIRRORED frame: the tile index kk = 0..3 counts from the element edge the tile touches
+        // (k = kk for the low tile, k = 7 - kk for the high tile; same for l). Because the Lobatto derivative matrix is
+        // antisymmetric under reversal, D[7-a][7-b] = -D[a][b], both tiles then use the SAME coefficients D[kk][0..7] (constant-bank
+        // operands, no per-thread table): the high tile computes -d/dx, its flux carries the same sign, and the divergence brings a
+        // second factor -1, so the signs cancel inside a tile; only flux values RECEIVED from the partner tile (opposite
+        // orientation) are negated. The metric g(l,k) = w_k w_l c is symmetric under the mirror.
+        // The nodes two elements share sit at kk = 0 (ll = 0) of the two tiles that touch the common edge: lanes ^ 3 (^ 12).
+        // ------------------------------------------------------------------------------------------------------
+        struct DDHConst8
+        {
+            float D[8][8];   // D(k, i)
+            float gx[4][4];  // [l][k] metric x-x entry on the low-low tile (the other tiles are its mirror images)
+            float gz[4][4];
+        };
+
+        __global__ void __launch_bounds__(V2_THREADS)
+        ddh_kernel_reg8(const __grid_constant__ DDHConst8 C, const DDHArgs A, const int n_dom_launch)
+        {
+            constexpr int NB = 8, NEL = 2, N1 = NEL * (NB - 1) + 1, ND = N1 * N1, WH_MAXIT = 5;
+            __shared__ float4 s_F[4][V2_THREADS], s_G[4][V2_THREADS], s_im[4][V2_THREADS], s_H[4][V2_THREADS];
+
+            const int tid = threadIdx.x;
+            const int sub = tid >> 4;
+            const int tx = tid & 3, ty = (tid >> 2) & 3;
+            const int ex = tx >> 1, ey = ty >> 1, sx = tx & 1, sy = ty & 1;
+            const int dom_local = blockIdx.x * (V2_THREADS / 16) + sub;
+            const bool valid = dom_local < n_dom_launch;
+            const int dom = A.dom0 + (valid ? dom_local : 0);
+            const bool edgeX = (tx == 1) || (tx == 2); // this tile touches the edge shared by the two elements of its row
+            const bool edgeY = (ty == 1) || (ty == 2);
+            // true element-local node of tile entry (ll, kk)
+            auto node_k = [&](const int kk) { return sx ? (NB - 1 - kk) : kk; };
+            auto node_l = [&](const int ll) { return sy ? (NB - 1 - ll) : ll; };
+
+            float p[4][4], q[4][4], u[4][4], v[4][4];
+            float lam[4][4], mu[4][4], ai[4][4];
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                float Fr[4], Gr[4], im[4], Hr[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const size_t o = (size_t)((ey * (NB - 1) + node_l(l)) * N1 + ex * (NB - 1) + node_k(k)) + (size_t)ND * dom;
+                    const float a = __ldg(A.a + o), mi = __ldg(A.m + o);
+                    float F = 0.0f, G = 0.0f, Hi = __ldg(A.H + o);
+                    if (A.x) {
+                        const int gi = __ldg(A.gid + o);
+                        F = (float)A.x[gi];
+                        G = (float)A.x[A.g_ndof + gi];
+                    }
+                    float lm = 0.0f, mm = 0.0f;
+                    if (A.lambda) {
+                        const int idx = __ldg(A.bin + o);
+                        if (idx >= 0) {
+                            lm = A.lambda[idx];
+                            mm = A.lambda[A.n_lambda + idx];
+                            F += Hi * lm;
+                            G += Hi * mm;
+                        }
+                    }
+                    lam[l][k] = lm;
+                    mu[l][k] = mm;
+                    ai[l][k] = a;
+                    Fr[k] = F;
+                    Gr[k] = G;
+                    im[k] = 1.0f / (a * a * mi);
+                    Hr[k] = Hi * a;
+                    p[l][k] = q[l][k] = u[l][k] = v[l][k] = 0.0f;
+                }
+                s_F[l][tid] = make_float4(Fr[0], Fr[1], Fr[2], Fr[3]);
+                s_G[l][tid] = make_float4(Gr[0], Gr[1], Gr[2], Gr[3]);
+                s_im[l][tid] = make_float4(im[0], im[1], im[2], im[3]);
+                s_H[l][tid] = make_float4(Hr[0], Hr[1], Hr[2], Hr[3]);
+            }
+            // (each thread reads back only what it wrote: no barrier needed)
+
+            // z <- assembled S w  (w, z: [ll][kk] in the mirrored frame of this tile)
+            auto stiffness = [&](const float (&w)[4][4], float (&z)[4][4]) {
+                float fx[4][4], fy[4][4];
+                {
+                    // partner tiles, re-indexed so that entry j continues the own row / column: mirrored index 4 + j = partner's 3 - j
+                    float wp[4][4];
+#pragma unroll
+                    for (int l = 0; l < 4; ++l)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            wp[l][j] = __shfl_xor_sync(0xffffffffu, w[l][3 - j], 1);
+#pragma unroll
+                    for (int l = 0; l < 4; ++l)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            float Ux = 0.0f;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                Ux = fmaf(C.D[k][i], w[l][i], Ux);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                Ux = fmaf(C.D[k][4 + i], wp[l][i], Ux);
+                            fx[l][k] = C.gx[l][k] * Ux;
+                        }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            wp[j][k] = __shfl_xor_sync(0xffffffffu, w[3 - j][k], 4);
+#pragma unroll
+                    for (int l = 0; l < 4; ++l)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            float Uy = 0.0f;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                Uy = fmaf(C.D[l][i], w[i][k], Uy);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                Uy = fmaf(C.D[l][4 + i], wp[i][k], Uy);
+                            fy[l][k] = C.gz[l][k] * Uy;
+                        }
+                }
+                {
+                    // fluxes of the partner tiles: opposite orientation -> opposite sign convention
+                    float fp[4][4];
+#pragma unroll
+                    for (int l = 0; l < 4; ++l)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            fp[l][j] = -__shfl_xor_sync(0xffffffffu, fx[l][3 - j], 1);
+#pragma unroll
+                    for (int l = 0; l < 4; ++l)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            float Su = 0.0f;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                Su = fmaf(C.D[i][k], fx[l][i], Su);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                Su = fmaf(C.D[4 + i][k], fp[l][i], Su);
+                            z[l][k] = Su;
+                        }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            fp[j][k] = -__shfl_xor_sync(0xffffffffu, fy[3 - j][k], 4);
+#pragma unroll
+                    for (int l = 0; l < 4; ++l)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            float Su = z[l][k];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                Su = fmaf(C.D[i][l], fy[i][k], Su);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                Su = fmaf(C.D[4 + i][l], fp[i][k], Su);
+                            z[l][k] = Su;
+                        }
+                }
+                // assembly across the element edges inside the subdomain: x first, then y of the x-summed values (all copies of
+                // a shared node apply the same commutative two-term sums and stay bitwise identical)
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    const float other = __shfl_xor_sync(0xffffffffu, z[l][0], 3);
+                    z[l][0] += edgeX ? other : 0.0f;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float other = __shfl_xor_sync(0xffffffffu, z[0][k], 12);
+                    z[0][k] += edgeY ? other : 0.0f;
+                }
+            };
+
+            const float half_dt = 0.5f * A.dt, dt = A.dt;
+            for (int whit = 0; whit < WH_MAXIT; ++whit) {
+                const float dK0 = __ldg(A.whf);
+#pragma unroll
+                for (int l = 0; l < 4; ++l)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        p[l][k] = u[l][k];
+                        q[l][k] = v[l][k];
+                        u[l][k] *= dK0;
+                        v[l][k] *= dK0;
+                    }
+                for (int it = 1; it <= A.nt; ++it) {
+                    const float c0 = __ldg(A.cs + 2 * it - 2), s0 = __ldg(A.sn + 2 * it - 2);
+                    const float c1 = __ldg(A.cs + 2 * it - 1), s1 = __ldg(A.sn + 2 * it - 1);
+                    const float dK = __ldg(A.whf + it);
+                    float z[4][4], ph[4][4], qh[4][4];
+                    stiffness(p, z);
+#pragma unroll
+                    for (int l = 0; l < 4; ++l) {
+                        const float4 F4 = s_F[l][tid], G4 = s_G[l][tid], I4 = s_im[l][tid], H4 = s_H[l][tid];
+                        const float Fr[4] = {F4.x, F4.y, F4.z, F4.w}, Gr[4] = {G4.x, G4.y, G4.z, G4.w};
+                        const float im[4] = {I4.x, I4.y, I4.z, I4.w}, Hr[4] = {H4.x, H4.y, H4.z, H4.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float zz = z[l][k] - Hr[k] * q[l][k];
+                            float dq = zz + c0 * Fr[k];
+                            dq += s0 * Gr[k];
+                            dq *= im[k];
+                            ph[l][k] = p[l][k] - half_dt * q[l][k];
+                            qh[l][k] = q[l][k] + half_dt * dq;
+                            p[l][k] -= dt * qh[l][k];
+                        }
+                    }
+                    stiffness(ph, z);
+#pragma unroll
+                    for (int l = 0; l < 4; ++l) {
+                        const float4 F4 = s_F[l][tid], G4 = s_G[l][tid], I4 = s_im[l][tid], H4 = s_H[l][tid];
+                        const float Fr[4] = {F4.x, F4.y, F4.z, F4.w}, Gr[4] = {G4.x, G4.y, G4.z, G4.w};
+                        const float im[4] = {I4.x, I4.y, I4.z, I4.w}, Hr[4] = {H4.x, H4.y, H4.z, H4.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float zz = z[l][k] - Hr[k] * qh[l][k];
+                            float dq = zz + c1 * Fr[k];
+                            dq += s1 * Gr[k];
+                            dq *= im[k];
+                            q[l][k] += dt * dq;
+                            u[l][k] += dK * p[l][k];
+                            v[l][k] += dK * q[l][k];
+                        }
+                    }
+                }
+            }
+
+            const float rw = 1.0f / A.omega;
+            if (!valid)
+                return;
+#pragma unroll
+            for (int l = 0; l < 4; ++l)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    // one writer per node: the copy in the right / upper element owns a shared node
+                    const int kt = node_k(k), lt = node_l(l);
+                    const bool canon = (kt < NB - 1 || ex == NEL - 1) && (lt < NB - 1 || ey == NEL - 1);
+                    if (!canon)
+                        continue;
+                    const size_t o = (size_t)((ey * (NB - 1) + lt) * N1 + ex * (NB - 1) + kt) + (size_t)ND * dom;
+                    const float vv = v[l][k] * rw;
+                    if (A.contrib) {
+                        const float M = __ldg(A.pou + o);
+                        A.contrib[2 * o] = (double)(M * u[l][k]);
+                        A.contrib[2 * o + 1] = (double)(M * vv);
+                    }
+                    if (A.update) {
+                        const int idx = __ldg(A.bout + (o - A.bout_off));
+                        const float S = 2.0f * ai[l][k] * A.omega;
+                        write_trace(A, idx, -lam[l][k] - S * vv, -mu[l][k] + S * u[l][k]);
+                    }
+                }
+        }
+
         __global__ void pou_gather_kernel(const int64_t g_ndof, const int * __restrict__ ptr, const int * __restrict__ src,
                                           const double * __restrict__ contrib, double * __restrict__ y)
         {
@@ -488,6 +747,19 @@ namespace cb200
                     }
                 const int per_cta = V2_THREADS / 16;
                 ddh_kernel_reg4<<<(n_launch + per_cta - 1) / per_cta, V2_THREADS, 0, s>>>(C, A, n_launch);
+            }
+            else if (nb == 8 && block == 16 && reg_tiled_ok) {
+                DDHConst8 C;
+                for (int k = 0; k < 8; ++k)
+                    for (int i = 0; i < 8; ++i)
+                        C.D[k][i] = D[k + 8 * i];
+                for (int l = 0; l < 4; ++l)
+                    for (int k = 0; k < 4; ++k) {
+                        C.gx[l][k] = g_first[3 * (k + 8 * l) + 0];
+                        C.gz[l][k] = g_first[3 * (k + 8 * l) + 2];
+                    }
+                const int per_cta = V2_THREADS / 16;
+                ddh_kernel_reg8<<<(n_launch + per_cta - 1) / per_cta, V2_THREADS, 0, s>>>(C, A, n_launch);
             }
             else if (nb == 4 && block == 16)
                 ddh_kernel<4, 4><<<n_launch, threads, 0, s>>>(A);
