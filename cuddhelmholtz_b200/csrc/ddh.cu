@@ -431,21 +431,36 @@ namespace cb200
             float gz[4][4];
         };
 
+        // NEL = 2: block 16 (16 threads per subdomain, four subdomains per CTA, every exchange a shuffle). NEL = 4: block 32 (BASELINE
+        // configs[4]): 8 x 8 tiles = the 64 threads of the CTA = two warps; the only exchange that crosses the warps is the edge row
+        // between the second and third element row (8 threads x 4 values per stiffness), which goes through a double-buffered
+        // shared-memory slot and one __syncthreads.
+        template <int NEL>
         __global__ void __launch_bounds__(V2_THREADS)
         ddh_kernel_reg8(const __grid_constant__ DDHConst8 C, const DDHArgs A, const int n_dom_launch)
         {
-            constexpr int NB = 8, NEL = 2, N1 = NEL * (NB - 1) + 1, ND = N1 * N1, WH_MAXIT = 5;
+            constexpr int NB = 8, N1 = NEL * (NB - 1) + 1, ND = N1 * N1, WH_MAXIT = 5;
+            constexpr int TG = 2 * NEL;              // tiles per subdomain side
+            constexpr int TPS = TG * TG;             // threads per subdomain (16 or 64)
+            constexpr bool XWARP = TPS > 32;         // the y exchange between tile rows TG/2 - 1 and TG/2 crosses the warp boundary
+            static_assert(NEL == 2 || NEL == 4, "block 16 or 32");
             __shared__ float4 s_F[4][V2_THREADS], s_G[4][V2_THREADS], s_im[4][V2_THREADS], s_H[4][V2_THREADS];
+            __shared__ float4 s_edge[2][2][XWARP ? TG : 1]; // [parity][lower / upper tile row][tx]
 
             const int tid = threadIdx.x;
-            const int sub = tid >> 4;
-            const int tx = tid & 3, ty = (tid >> 2) & 3;
+            const int lane = tid & 31;
+            const int sub = tid / TPS;
+            const int tx = tid % TG, ty = (tid / TG) % TG;
             const int ex = tx >> 1, ey = ty >> 1, sx = tx & 1, sy = ty & 1;
-            const int dom_local = blockIdx.x * (V2_THREADS / 16) + sub;
+            const int dom_local = blockIdx.x * (V2_THREADS / TPS) + sub;
             const bool valid = dom_local < n_dom_launch;
             const int dom = A.dom0 + (valid ? dom_local : 0);
-            const bool edgeX = (tx == 1) || (tx == 2); // this tile touches the edge shared by the two elements of its row
-            const bool edgeY = (ty == 1) || (ty == 2);
+            // tiles that touch an edge shared by two elements of the subdomain, and the lane of the tile across that edge
+            const bool edgeX = tx > 0 && tx < TG - 1, edgeY = ty > 0 && ty < TG - 1;
+            const int srcX = edgeX ? (sx ? lane + 1 : lane - 1) : lane;
+            const bool crossY = XWARP && (ty == TG / 2 - 1 || ty == TG / 2);
+            const int srcY = (edgeY && !crossY) ? (sy ? lane + TG : lane - TG) : lane;
+            int par = 0; // parity of the shared-memory edge slot (XWARP)
             // true element-local node of tile entry (ll, kk)
             auto node_k = [&](const int kk) { return sx ? (NB - 1 - kk) : kk; };
             auto node_l = [&](const int ll) { return sy ? (NB - 1 - ll) : ll; };
@@ -519,7 +534,7 @@ namespace cb200
                     for (int j = 0; j < 4; ++j)
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            wp[j][k] = __shfl_xor_sync(0xffffffffu, w[3 - j][k], 4);
+                            wp[j][k] = __shfl_xor_sync(0xffffffffu, w[3 - j][k], TG);
 #pragma unroll
                     for (int l = 0; l < 4; ++l)
 #pragma unroll
@@ -559,7 +574,7 @@ namespace cb200
                     for (int j = 0; j < 4; ++j)
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            fp[j][k] = -__shfl_xor_sync(0xffffffffu, fy[3 - j][k], 4);
+                            fp[j][k] = -__shfl_xor_sync(0xffffffffu, fy[3 - j][k], TG);
 #pragma unroll
                     for (int l = 0; l < 4; ++l)
 #pragma unroll
@@ -578,13 +593,28 @@ namespace cb200
                 // a shared node apply the same commutative two-term sums and stay bitwise identical)
 #pragma unroll
                 for (int l = 0; l < 4; ++l) {
-                    const float other = __shfl_xor_sync(0xffffffffu, z[l][0], 3);
+                    const float other = __shfl_sync(0xffffffffu, z[l][0], srcX);
                     z[l][0] += edgeX ? other : 0.0f;
+                }
+                if constexpr (XWARP) {
+                    if (crossY)
+                        s_edge[par][ty - (TG / 2 - 1)][tx] = make_float4(z[0][0], z[0][1], z[0][2], z[0][3]);
+                    __syncthreads();
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const float other = __shfl_xor_sync(0xffffffffu, z[0][k], 12);
-                    z[0][k] += edgeY ? other : 0.0f;
+                    const float other = __shfl_sync(0xffffffffu, z[0][k], srcY);
+                    z[0][k] += (edgeY && !crossY) ? other : 0.0f;
+                }
+                if constexpr (XWARP) {
+                    if (crossY) {
+                        const float4 o4 = s_edge[par][1 - (ty - (TG / 2 - 1))][tx];
+                        z[0][0] += o4.x;
+                        z[0][1] += o4.y;
+                        z[0][2] += o4.z;
+                        z[0][3] += o4.w;
+                    }
+                    par ^= 1; // the slot written two calls ago is free again: every thread passed the barrier of the call in between
                 }
             };
 
@@ -748,7 +778,7 @@ namespace cb200
                 const int per_cta = V2_THREADS / 16;
                 ddh_kernel_reg4<<<(n_launch + per_cta - 1) / per_cta, V2_THREADS, 0, s>>>(C, A, n_launch);
             }
-            else if (nb == 8 && block == 16 && reg_tiled_ok) {
+            else if (nb == 8 && reg_tiled_ok) {
                 DDHConst8 C;
                 for (int k = 0; k < 8; ++k)
                     for (int i = 0; i < 8; ++i)
@@ -758,8 +788,12 @@ namespace cb200
                         C.gx[l][k] = g_first[3 * (k + 8 * l) + 0];
                         C.gz[l][k] = g_first[3 * (k + 8 * l) + 2];
                     }
-                const int per_cta = V2_THREADS / 16;
-                ddh_kernel_reg8<<<(n_launch + per_cta - 1) / per_cta, V2_THREADS, 0, s>>>(C, A, n_launch);
+                if (block == 16) {
+                    const int per_cta = V2_THREADS / 16;
+                    ddh_kernel_reg8<2><<<(n_launch + per_cta - 1) / per_cta, V2_THREADS, 0, s>>>(C, A, n_launch);
+                }
+                else
+                    ddh_kernel_reg8<4><<<n_launch, V2_THREADS, 0, s>>>(C, A, n_launch);
             }
             else if (nb == 4 && block == 16)
                 ddh_kernel<4, 4><<<n_launch, threads, 0, s>>>(A);

@@ -67,7 +67,7 @@ namespace cb200
         void get_array(const char * name, void * out, int64_t cap_bytes, int64_t * count) const;
         double flops() const;
 
-        int kernel_kind() const { return ((nb == 4 || nb == 8) && block == 16 && reg_tiled_ok) ? 1 : 0; } // 1 = register-tiled kernel (ddh_kernel_reg4 / reg8)
+        int kernel_kind() const { return (((nb == 4 && block == 16) || nb == 8) && reg_tiled_ok) ? 1 : 0; } // 1 = register-tiled kernel (ddh_kernel_reg4 / reg8)
 
         // outgoing-trace redirection of a distributed run (DdhDist): slots owned by another rank go to a packed send buffer
         struct Redirect
