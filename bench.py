@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--no-ddh", action="store_true", help="skip the DDH block (config 3 action / cycle and the 512^2 solve)")
     ap.add_argument("--ddh-nx", type=int, default=2048)
     ap.add_argument("--ddh-solve-nx", type=int, default=512)
+    ap.add_argument("--ddh-ho-nx", type=int, default=512, help="mesh of the scaled-down high-order (configs[4]) DDH action")
     ap.add_argument("--ddh-box-seconds", type=float, default=45.0, help="time box of the GMRES(30) restart cycle at config 3")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -516,6 +517,34 @@ def ddh_block(args, cb, torch, dist, comm, rank, world, local_rank):
             out["roofline_fp32"]["frac"] = c3["action_fp32_tflops"] / (peak * world)
     del A, D, b, y, L, f, fem, mesh
     torch.cuda.empty_cache()
+
+    # ---------------- BASELINE configs[4] order, scaled to 1/16 of its subdomains: n_basis 8, block 32, same nt ----------------
+    try:
+        nx5, omega5 = args.ddh_ho_nx, 400.0 * args.ddh_ho_nx / 2048.0
+        mesh, fem, ha, f, n = ddh_problem(cb, torch, nx5, 8, omega5)
+        D = cb.DDH(omega5, ha, fem, nx5, nx5, 32)
+        A = cb.DDHDist(D, comm, rank, world)
+        m5 = D.size()
+        b = torch.empty(m5, dtype=torch.float32, device="cuda")
+        y = torch.empty(m5, dtype=torch.float32, device="cuda")
+        barrier()
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record()
+        A.rhs(f, b)
+        e1.record()
+        A.action(b, y)
+        e2.record()
+        barrier()
+        a5 = tmax(e1.elapsed_time(e2))
+        out["config5_scaled"] = {"nx": nx5, "n_basis": 8, "omega": omega5, "block": 32, "n_domains": D.info()["n_domains"], "nt": D.info()["nt"],
+                                 "n_lambda": m5, "kernel_kind": D.kernel_kind(), "rhs_ms": tmax(e0.elapsed_time(e1)), "action_ms": a5,
+                                 "action_fp32_tflops": D.flops() / (a5 * 1e-3) / 1e12,
+                                 "note": "configs[4] (2048^2, omega 400, block 32) has 16x the subdomains and the same nt; its action scales "
+                                         "linearly in the subdomain count (%.1f s on this many GPUs by this measurement)" % (16 * a5 / 1e3)}
+        del A, D, b, y, f, fem, mesh
+        torch.cuda.empty_cache()
+    except Exception as e:
+        out["config5_scaled"] = "failed: %r" % (e,)
 
     # ---------------- the convergent solve: examples/DDH.cpp flow at 512^2 (omega = 2 pi nx / 10, GMRES(20), tol 1e-4) ----------------
     nx = args.ddh_solve_nx
