@@ -698,6 +698,10 @@ class HelmholtzSlab:
     def bytes_per_apply(self):
         return int(load().cuddh_b200_slab_bytes(self._h))
 
+    def uses_peer_memory(self):
+        """True: rows travel as NVLink stores into the neighbours' buffers + epoch flags; False: ncclSend / ncclRecv"""
+        return bool(load().cuddh_b200_slab_uses_peer_memory(self._h))
+
     def apply(self, x, y):
         check(load().cuddh_b200_helmholtz_apply_slab(self.op._h, self._h, _ptr(x), _ptr(y), _stream()))
 

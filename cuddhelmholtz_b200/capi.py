@@ -132,6 +132,7 @@ def _proto(lib):
         "cuddh_b200_slab_create": (C.c_int, [c_vp, C.c_int, C.c_int, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, P(c_vp)]),
         "cuddh_b200_slab_destroy": (C.c_int, [c_vp]),
         "cuddh_b200_slab_bytes": (c_i64, [c_vp]),
+        "cuddh_b200_slab_uses_peer_memory": (C.c_int, [c_vp]),
         "cuddh_b200_slab_exchange": (C.c_int, [c_vp, c_dp, c_vp]),
         "cuddh_b200_slab_mask": (c_vp, [c_vp]),
         "cuddh_b200_helmholtz_apply_slab": (C.c_int, [c_vp, c_vp, c_dp, c_dp, c_vp]),

@@ -855,6 +855,7 @@ int cuddh_b200_slab_destroy(cuddh_slab_t h)
     return 0;
 }
 int64_t cuddh_b200_slab_bytes(cuddh_slab_t h) { return h->h->bytes_per_apply(); }
+int cuddh_b200_slab_uses_peer_memory(cuddh_slab_t h) { return h->h->peer ? 1 : 0; }
 int cuddh_b200_slab_exchange(cuddh_slab_t h, double * y, void * stream)
 {
     CB_TRY

@@ -792,10 +792,45 @@ namespace cb200
             const int * plain;      // row entries packed by plain copy
             double * send;
             int64_t n_bottom, n_top, n_plain;
+            // peer path (NVLink stores into the neighbours' receive buffers instead of a send buffer + ncclSend/ncclRecv):
+            double * peer_dst[2];               // where the bottom / top segment of THIS apply goes in the lower / upper neighbour's memory
+            unsigned long long * peer_flag[2];  // the neighbours' arrival flags for this rank
+            unsigned * ticket;                  // last-block detection of the packing launch
+            unsigned long long epoch;           // value to publish (monotone: one per exchange)
+            int peer;
         };
         __device__ __forceinline__ int64_t halo_pos(const HaloDev & h, const int f, const int e)
         {
             return e < h.n_bottom ? f * h.n_bottom + e : 2 * h.n_bottom + f * h.n_top + (e - h.n_bottom);
+        }
+        __device__ __forceinline__ void halo_put(const HaloDev & h, const int f, const int e, const double v)
+        {
+            const int64_t pos = halo_pos(h, f, e);
+            if (!h.peer)
+                h.send[pos] = v;
+            else if (pos < 2 * h.n_bottom)
+                h.peer_dst[0][pos] = v;
+            else
+                h.peer_dst[1][pos - 2 * h.n_bottom] = v;
+        }
+        // peer path: after the last block of the packing launch has made its stores visible system-wide, publish the epoch in the
+        // neighbours' flags (release at system scope). Every thread of the launch must call this exactly once, at its end.
+        __device__ __forceinline__ void halo_publish(const HaloDev & h)
+        {
+            if (!h.peer)
+                return;
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const unsigned total = gridDim.x * gridDim.y;
+                if (atomicAdd(h.ticket, 1u) == total - 1) {
+                    *h.ticket = 0;
+                    __threadfence_system();
+                    for (int side = 0; side < 2; ++side)
+                        if (h.peer_flag[side])
+                            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(h.peer_flag[side]), "l"(h.epoch) : "memory");
+                }
+            }
         }
 
         // the two boundary terms of the Helmholtz composite in one launch: blockIdx.y = 0: y[0:n] += c H x[n:2n]; 1: y[n:2n] += c H x[0:n].
@@ -813,36 +848,38 @@ namespace cb200
                 const int64_t k = (int64_t)(blockIdx.x - face_blocks) * blockDim.x + threadIdx.x;
                 if (k < halo.n_plain) {
                     const int e = halo.plain[k];
-                    halo.send[halo_pos(halo, fld, e)] = yd[halo.row_dof[e]];
+                    halo_put(halo, fld, e, yd[halo.row_dof[e]]);
                 }
-                return;
             }
-            const int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-            if (d >= fdof)
-                return;
-            const double * xs = fld == 0 ? x + n : x;
-            double sum = 0.0;
-            for (int t = inc_ptr[d]; t < inc_ptr[d + 1]; ++t) {
-                const int fk = inc[t];
-                const int f = fk / NB, k = fk - f * NB;
-                const int * Ifa = If + (size_t)NB * f;
-                double Mu = 0.0;
-                for (int i = 0; i < NQ; ++i) {
-                    double pu = 0.0;
-                    for (int l = 0; l < NB; ++l)
-                        pu += P[i + NQ * l] * xs[proj[Ifa[l]]];
-                    pu *= a[i + (size_t)NQ * f];
-                    Mu += P[i + NQ * k] * pu;
+            else {
+                const int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+                if (d < fdof) {
+                    const double * xs = fld == 0 ? x + n : x;
+                    double sum = 0.0;
+                    for (int t = inc_ptr[d]; t < inc_ptr[d + 1]; ++t) {
+                        const int fk = inc[t];
+                        const int f = fk / NB, k = fk - f * NB;
+                        const int * Ifa = If + (size_t)NB * f;
+                        double Mu = 0.0;
+                        for (int i = 0; i < NQ; ++i) {
+                            double pu = 0.0;
+                            for (int l = 0; l < NB; ++l)
+                                pu += P[i + NQ * l] * xs[proj[Ifa[l]]];
+                            pu *= a[i + (size_t)NQ * f];
+                            Mu += P[i + NQ * k] * pu;
+                        }
+                        sum += c * Mu;
+                    }
+                    const double v = yd[proj[d]] + sum;
+                    yd[proj[d]] = v;
+                    if (halo.face_entry) {
+                        const int e = halo.face_entry[d];
+                        if (e >= 0)
+                            halo_put(halo, fld, e, v);
+                    }
                 }
-                sum += c * Mu;
             }
-            const double v = yd[proj[d]] + sum;
-            yd[proj[d]] = v;
-            if (halo.face_entry) {
-                const int e = halo.face_entry[d];
-                if (e >= 0)
-                    halo.send[halo_pos(halo, fld, e)] = v;
-            }
+            halo_publish(halo);
         }
 
         // stand-alone pack of every row entry (SlabHalo::exchange) and the add of the received rows
@@ -850,13 +887,41 @@ namespace cb200
         {
             const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
             if (e < halo.n_bottom + halo.n_top)
-                halo.send[halo_pos(halo, blockIdx.y, (int)e)] = y[blockIdx.y * n + halo.row_dof[e]];
+                halo_put(halo, blockIdx.y, (int)e, y[blockIdx.y * n + halo.row_dof[e]]);
+            halo_publish(halo);
         }
-        __global__ void halo_add_kernel(const HaloDev halo, const double * __restrict__ recv, const int64_t n, double * __restrict__ y)
+        // recv: this rank's receive buffer of the current parity. Peer path: wait (acquire at system scope) until both neighbours
+        // have published `epoch` in this rank's flags; their stores bypass this SM's L1, so the data is read with ld.cg.
+        __global__ void halo_add_kernel(const HaloDev halo, const double * __restrict__ recv, const int64_t n, double * __restrict__ y,
+                                        const unsigned long long * __restrict__ own_flags, const int wait_bottom, const int wait_top)
         {
+            if (halo.peer) {
+                if (threadIdx.x == 0) {
+                    unsigned long long t0 = 0;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                    for (int side = 0; side < 2; ++side) {
+                        if (!(side == 0 ? wait_bottom : wait_top))
+                            continue;
+                        unsigned long long seen = 0;
+                        for (;;) {
+                            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(own_flags + side) : "memory");
+                            if (seen >= halo.epoch)
+                                break;
+                            unsigned long long t1;
+                            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                            if (t1 - t0 > 120000000000ull) // two minutes without the neighbour's rows: fail loudly instead of hanging the GPU
+                                __trap();
+                            __nanosleep(200);
+                        }
+                    }
+                }
+                __syncthreads();
+            }
             const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-            if (e < halo.n_bottom + halo.n_top)
-                y[blockIdx.y * n + halo.row_dof[e]] += recv[halo_pos(halo, blockIdx.y, (int)e)]; // own + received: same sum on both sides
+            if (e < halo.n_bottom + halo.n_top) {
+                const double r = halo.peer ? __ldcg(recv + halo_pos(halo, blockIdx.y, (int)e)) : recv[halo_pos(halo, blockIdx.y, (int)e)];
+                y[blockIdx.y * n + halo.row_dof[e]] += r; // own + received: same sum on both sides
+            }
         }
 
         __global__ void setup_facemass_kernel(const int64_t nf, const int NB, const int NQ, const double * __restrict__ wq,
@@ -1442,9 +1507,28 @@ namespace cb200
 
     namespace
     {
+        // device view for ONE exchange; begin_exchange() has advanced the epoch
         HaloDev halo_dev(SlabHalo & h)
         {
-            return HaloDev{h.d_row_dof.p, h.d_face_entry.p, h.d_plain.p, h.d_send.p, h.n_bottom, h.n_top, h.n_plain};
+            HaloDev d{};
+            d.row_dof = h.d_row_dof.p;
+            d.face_entry = h.d_face_entry.p;
+            d.plain = h.d_plain.p;
+            d.send = h.d_send.p;
+            d.n_bottom = h.n_bottom;
+            d.n_top = h.n_top;
+            d.n_plain = h.n_plain;
+            d.peer = h.peer ? 1 : 0;
+            if (h.peer) {
+                const int par = (int)(h.epoch & 1);
+                for (int side = 0; side < 2; ++side) {
+                    d.peer_dst[side] = h.peer_recv[side] ? h.peer_recv[side] + par * h.peer_tot[side] + h.peer_off[side] : nullptr;
+                    d.peer_flag[side] = h.peer_flag[side];
+                }
+                d.ticket = h.d_ticket.p;
+                d.epoch = h.epoch;
+            }
+            return d;
         }
     } // namespace
 
@@ -1460,6 +1544,96 @@ namespace cb200
         facemass_pair_kernel<<<dim3(fb + pb, 2), 128, 0, s>>>(fs->fdof, nb, nq, d_P.p, d_a.p, fs->d_I.p, fs->d_inc_ptr.p, fs->d_inc.p,
                                                               fs->d_proj.p, c, n, x, y, hd, (int)fb);
         CB_LAUNCHED();
+    }
+
+    // ---- peer path of the halo exchange: CUDA IPC mappings of the neighbours' receive buffers ----
+    namespace
+    {
+        struct PeerHello // what neighbours tell each other at setup (through NCCL, 128 bytes)
+        {
+            cudaIpcMemHandle_t handle;
+            int64_t n_bottom, tot;
+            char pad[128 - sizeof(cudaIpcMemHandle_t) - 16];
+        };
+        static_assert(sizeof(PeerHello) == 128, "hello size");
+    } // namespace
+
+    SlabHalo::~SlabHalo()
+    {
+        for (int side = 0; side < 2; ++side)
+            if (peer_base[side])
+                cudaIpcCloseMemHandle(peer_base[side]);
+    }
+
+    void SlabHalo::setup_peer()
+    {
+        peer = false;
+        if (!comm || world == 1 || env_int("CUDDH_B200_PEER", 1) == 0)
+            return;
+        const int64_t tot = (int64_t)n_fields * (n_bottom + n_top);
+        // own block: two parity buffers + two arrival flags (64-byte aligned tail)
+        const size_t flag_off = (((size_t)2 * tot * sizeof(double)) + 63) & ~size_t(63);
+        d_peer_block.alloc(flag_off + 64);
+        CB_CUDA(cudaMemset(d_peer_block.p, 0, d_peer_block.n));
+        d_ticket.alloc(1);
+        CB_CUDA(cudaMemset(d_ticket.p, 0, sizeof(unsigned)));
+        own_recv = reinterpret_cast<double *>(d_peer_block.p);
+        own_flags = reinterpret_cast<unsigned long long *>(d_peer_block.p + flag_off);
+        own_tot = tot;
+        PeerHello mine{};
+        int ok = cudaIpcGetMemHandle(&mine.handle, d_peer_block.p) == cudaSuccess ? 1 : 0;
+        if (!ok)
+            cudaGetLastError();
+        mine.n_bottom = n_bottom;
+        mine.tot = tot;
+        // hello exchange with the two neighbours (device staging: slot 0 <-> lower neighbour, slot 1 <-> upper neighbour)
+        DevBuf<unsigned char> d_hs(256), d_hr(256);
+        PeerHello both[2] = {mine, mine};
+        CB_CUDA(cudaMemcpy(d_hs.p, both, 256, cudaMemcpyHostToDevice));
+        std::vector<PeerSeg> hs;
+        if (n_bottom > 0)
+            hs.push_back(PeerSeg{rank - 1, 0, 128, 0, 128});
+        if (n_top > 0)
+            hs.push_back(PeerSeg{rank + 1, 128, 128, 128, 128});
+        comm_exchange(comm, hs, d_hs.p, d_hr.p, 1, 0);
+        CB_CUDA(cudaDeviceSynchronize());
+        PeerHello theirs[2];
+        CB_CUDA(cudaMemcpy(theirs, d_hr.p, 256, cudaMemcpyDeviceToHost));
+        for (int side = 0; side < 2 && ok; ++side) {
+            if ((side == 0 ? n_bottom : n_top) == 0)
+                continue;
+            void * base = nullptr;
+            if (cudaIpcOpenMemHandle(&base, theirs[side].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = 0;
+                break;
+            }
+            peer_base[side] = base;
+            const int64_t ptot = theirs[side].tot;
+            const size_t pflag = (((size_t)2 * ptot * sizeof(double)) + 63) & ~size_t(63);
+            peer_recv[side] = reinterpret_cast<double *>(base);
+            peer_tot[side] = ptot;
+            // my bottom segment is the lower neighbour's TOP segment (after its own bottom segment); my top segment is the upper
+            // neighbour's bottom segment (offset 0). Flags: I am the lower neighbour's upper side (flag 1) and vice versa.
+            peer_off[side] = side == 0 ? 2 * theirs[side].n_bottom : 0;
+            peer_flag[side] = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(base) + pflag) + (side == 0 ? 1 : 0);
+        }
+        // all ranks or none: a rank that cannot map its neighbours sends everybody back to ncclSend / ncclRecv
+        DevBuf<double> d_ok(1);
+        const double bad = ok ? 0.0 : 1.0;
+        CB_CUDA(cudaMemcpy(d_ok.p, &bad, sizeof(double), cudaMemcpyHostToDevice));
+        comm_allreduce_sum(comm, d_ok.p, 1, 0);
+        double nbad = 0.0;
+        CB_CUDA(cudaMemcpy(&nbad, d_ok.p, sizeof(double), cudaMemcpyDeviceToHost));
+        peer = nbad == 0.0;
+        if (!peer)
+            for (int side = 0; side < 2; ++side) {
+                if (peer_base[side])
+                    cudaIpcCloseMemHandle(peer_base[side]);
+                peer_base[side] = nullptr;
+                peer_recv[side] = nullptr;
+                peer_flag[side] = nullptr;
+            }
     }
 
     std::unique_ptr<SlabHalo> make_slab_halo(const Comm * comm, int rank, int world, int64_t ndof, FaceSpace * fs_phys, int64_t n_bottom,
@@ -1514,6 +1688,7 @@ namespace cb200
             h->segs.push_back(PeerSeg{rank - 1, 0, 2 * n_bottom, 0, 2 * n_bottom});
         if (n_top > 0)
             h->segs.push_back(PeerSeg{rank + 1, 2 * n_bottom, 2 * n_top, 2 * n_bottom, 2 * n_top});
+        h->setup_peer();
         return h;
     }
 
@@ -1537,7 +1712,9 @@ namespace cb200
         const int64_t ne = n_bottom + n_top;
         if (ne == 0)
             return;
-        halo_add_kernel<<<dim3(blocks_for(ne, 256), (unsigned)n_fields), 256, 0, s>>>(halo_dev(*this), d_recv.p, ndof, y);
+        const double * recv = peer ? own_recv + (epoch & 1) * own_tot : d_recv.p;
+        halo_add_kernel<<<dim3(blocks_for(ne, 256), (unsigned)n_fields), 256, 0, s>>>(halo_dev(*this), recv, ndof, y, own_flags, n_bottom > 0 ? 1 : 0,
+                                                                                      n_top > 0 ? 1 : 0);
         CB_LAUNCHED();
     }
 
@@ -1547,9 +1724,11 @@ namespace cb200
         const int64_t ne = n_bottom + n_top;
         if (ne == 0 || world == 1)
             return;
+        ++epoch;
         halo_pack_kernel<<<dim3(blocks_for(ne, 256), (unsigned)n_fields), 256, 0, s>>>(halo_dev(*this), ndof, y);
         CB_LAUNCHED();
-        comm_exchange(comm, segs, d_send.p, d_recv.p, sizeof(double), s);
+        if (!peer)
+            comm_exchange(comm, segs, d_send.p, d_recv.p, sizeof(double), s);
         unpack_add(y, s);
     }
 
@@ -1683,8 +1862,10 @@ namespace cb200
                     plan.n_shared, plan.d_sh_gid.p, plan.d_sh_ptr.p, d_partial2.p, std::max<int64_t>(plan.n_slots_total, 1), y, fem->ndof, 1.0, -1.0);
                 CB_LAUNCHED();
             }
+            ++halo.epoch;
             H->apply_h1_pair(-omega, x, y, fem->ndof, s, &halo);
-            comm_exchange(halo.comm, halo.segs, halo.d_send.p, halo.d_recv.p, sizeof(double), s);
+            if (!halo.peer)
+                comm_exchange(halo.comm, halo.segs, halo.d_send.p, halo.d_recv.p, sizeof(double), s);
             halo.unpack_add(y, s);
         }
         else {

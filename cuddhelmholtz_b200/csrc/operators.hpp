@@ -83,6 +83,23 @@ namespace cb200
         DevBuf<int> d_plain;                       // row entries that are not physical-boundary face DOFs (packed by copy)
         DevBuf<double> d_send, d_recv;             // [bottom: field 0 entries, field 1 entries | top: field 0, field 1]
         int64_t n_plain = 0;
+        // peer path (default when every rank can map its neighbours' buffers with CUDA IPC; CUDDH_B200_PEER=0 or a failed mapping
+        // anywhere -> ncclSend / ncclRecv): the packing launch stores the rows straight into the neighbours' receive buffers over
+        // NVLink and publishes an epoch in their flags, the add kernel acquires its own flags. Two parity buffers: a neighbour can be
+        // at most one exchange ahead (its next pack needs this rank's rows of the current exchange).
+        bool peer = false;
+        unsigned long long epoch = 0;
+        DevBuf<unsigned char> d_peer_block;       // own: [2 parities][n_fields * (n_bottom + n_top)] doubles, then 2 arrival flags
+        DevBuf<unsigned> d_ticket;
+        double * own_recv = nullptr;
+        unsigned long long * own_flags = nullptr; // [0]: from the lower neighbour, [1]: from the upper neighbour
+        int64_t own_tot = 0;
+        void * peer_base[2] = {nullptr, nullptr};
+        double * peer_recv[2] = {nullptr, nullptr};
+        unsigned long long * peer_flag[2] = {nullptr, nullptr};
+        int64_t peer_tot[2] = {0, 0}, peer_off[2] = {0, 0};
+        void setup_peer();
+        ~SlabHalo();
         HelmholtzOp * op = nullptr;         // bound operator (gmres callback), not owned
         DevBuf<unsigned char> d_mask;              // (n_fields * ndof) 1 = owned: the lower rank owns a mirrored row (built lazily)
         const unsigned char * mask();

@@ -98,19 +98,34 @@ class GpuSlabHelmholtz:
         dev = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda")
         self._a2, self._af = dev(c * c), dev(c[self.fs_phys.global_indices()])
         self.op = cb.Helmholtz(omega, self._a2, self._af, self.fem, self.fs_phys)
-        self.lib = None
+        self.lib, self.comm, self._lanes = None, comm, {}
         if comm is not None and world > 1:
-            none = np.zeros(0, np.int32)
-            self.lib = cb.HelmholtzSlab(self.op, comm, rank, world, self.fem, self.fs_phys,
-                                        self.fs["bottom"].global_indices() if rank > 0 else none,
-                                        self.fs["top"].global_indices() if rank < world - 1 else none)
+            self.lib = self._make_lib()
             self.exchange = self.lib.exchange
         else:
             self.exchange = SlabExchange(self, rank, world, offsets=(0, self.ndof), device="cuda", group=group)
 
+    def _make_lib(self):
+        none = np.zeros(0, np.int32)
+        return self.cb.HelmholtzSlab(self.op, self.comm, self.rank, self.world, self.fem, self.fs_phys,
+                                     self.fs["bottom"].global_indices() if self.rank > 0 else none,
+                                     self.fs["top"].global_indices() if self.rank < self.world - 1 else none)
+
+    def lane(self, k):
+        """a further exchange handle on the same operator for requests kept in flight on stream k (the exchanges of one handle
+        must be stream-ordered); collective: every rank must create its lanes in the same order"""
+        if self.lib is None:
+            return self
+        if k not in self._lanes:
+            self._lanes[k] = self.lib if k == 0 else self._make_lib()
+        return self._lanes[k]
+
     def exchange_info(self):
         if self.lib is not None:
-            return {"bytes_per_apply": self.lib.bytes_per_apply(), "path": "library: pack fused into the face-mass launch, grouped ncclSend/ncclRecv, add kernel"}
+            how = ("NVLink stores into the neighbours' receive buffers (CUDA IPC) + epoch flags" if self.lib.uses_peer_memory()
+                   else "grouped ncclSend/ncclRecv")
+            return {"bytes_per_apply": self.lib.bytes_per_apply(), "peer_memory": self.lib.uses_peer_memory(),
+                    "path": "library: pack fused into the face-mass launch, %s, add kernel" % how}
         return {"bytes_per_apply": getattr(self.exchange, "bytes_per_apply", 0), "path": "torch.distributed send/recv + restrict / prolong kernels"}
 
     def n_vec_rows(self):

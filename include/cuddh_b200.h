@@ -235,6 +235,11 @@ int cuddh_b200_slab_create(cuddh_comm_t comm, int rank, int world, cuddh_h1space
                            const int * h_bottom, int64_t n_top, const int * h_top, cuddh_slab_t * out);
 int cuddh_b200_slab_destroy(cuddh_slab_t h);
 int64_t cuddh_b200_slab_bytes(cuddh_slab_t h);                                   /* bytes sent per apply */
+/* 1: the interface rows travel as NVLink stores into the neighbours' receive buffers (CUDA IPC mappings made at create time) with an
+ * epoch flag (release / acquire at system scope) - no NCCL call on the data path; 0: grouped ncclSend / ncclRecv (CUDDH_B200_PEER=0, or
+ * some rank could not map its neighbours). The exchanges of ONE slab handle must be stream-ordered (two receive buffers alternate);
+ * requests kept in flight on several streams need one slab handle each. */
+int cuddh_b200_slab_uses_peer_memory(cuddh_slab_t h);
 int cuddh_b200_slab_exchange(cuddh_slab_t h, double * y, void * stream);         /* y[rows] += neighbours' y[rows], y = [u; v] */
 const unsigned char * cuddh_b200_slab_mask(cuddh_slab_t h);                      /* DEVICE, 2*ndof bytes */
 int cuddh_b200_helmholtz_apply_slab(cuddh_operator_t op, cuddh_slab_t h, const double * x, double * y, void * stream);

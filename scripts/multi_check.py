@@ -34,7 +34,11 @@ try:
     # ---------------- path A ----------------
     coef = lambda x, y: 1.0 + 0.5 * np.sin(np.pi * x) * np.cos(np.pi * y)
     nx, nb, omega = 128, 5, 20.0
-    lib = GpuSlabHelmholtz(nx, nx, nb, omega, coef, rank, world, comm=comm)
+    lib = GpuSlabHelmholtz(nx, nx, nb, omega, coef, rank, world, comm=comm)     # peer-memory exchange when CUDA IPC maps the neighbours
+    os.environ["CUDDH_B200_PEER"] = "0"
+    lib_nccl = GpuSlabHelmholtz(nx, nx, nb, omega, coef, rank, world, comm=comm)  # the ncclSend / ncclRecv path of the same library code
+    del os.environ["CUDDH_B200_PEER"]
+    assert not lib_nccl.lib.uses_peer_memory()
     ref = GpuSlabHelmholtz(nx, nx, nb, omega, coef, rank, world, comm=None)
     n = lib.ndof
     x = torch.as_tensor(np.random.default_rng(7 + rank).uniform(-1, 1, 2 * n), device="cuda")
@@ -42,12 +46,21 @@ try:
     lib.exchange(x)      # library stand-alone exchange: consistent input
     ref.exchange(x2)
     assert torch.equal(x, x2), "stand-alone exchange differs"
-    y, y2 = torch.empty_like(x), torch.empty_like(x)
-    for _ in range(3):   # repeated applies reuse the send / recv buffers
+    y, y2, y3 = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    for _ in range(5):   # repeated applies reuse the send / recv buffers (both parities of the peer path)
         lib.apply(x, y)
         ref.apply(x, y2)
+        lib_nccl.apply(x, y3)
     torch.cuda.synchronize()
     assert torch.equal(y, y2), "library slab apply differs from the torch.distributed exchange: %g" % float((y - y2).abs().max())
+    assert torch.equal(y3, y2), "library slab apply (NCCL path) differs from the torch.distributed exchange"
+    # back-to-back applies without host synchronisation in between (epochs / parity buffers under load)
+    ys = [torch.empty_like(x) for _ in range(8)]
+    for k in range(8):
+        lib.apply(x if k % 2 == 0 else y, ys[k])
+    torch.cuda.synchronize()
+    ref.apply(y, y2)
+    assert torch.equal(ys[0], y) and torch.equal(ys[1], y2) and torch.equal(ys[7], ys[1]), "back-to-back applies differ"
     # mirrored rows: my top row == the bottom row of rank + 1 (bit for bit)
     rows = {}
     for which, peer in (("bottom", rank - 1), ("top", rank + 1)):
@@ -119,8 +132,8 @@ try:
     assert o.success and os_.success and abs(o.num_iter - os_.num_iter) <= 1, (o.num_iter, os_.num_iter)
     assert float((U - Us).norm() / Us.norm()) < 1e-3
     if rank == 0:
-        print("multi_check: world %d  slab apply bitwise ok, slab gmres %d matvecs / %d allreduces, ddh solve %d restarts (single GPU %d), "
-              "exchange %d B per action" % (world, o1.num_matvec, o1.allreduces, o.num_iter, os_.num_iter, A.info()["bytes_per_action"]))
+        print("multi_check: world %d  slab apply bitwise ok (peer memory: %s), slab gmres %d matvecs / %d allreduces, ddh solve %d restarts (single GPU %d), "
+              "exchange %d B per action" % (world, lib.lib.uses_peer_memory(), o1.num_matvec, o1.allreduces, o.num_iter, os_.num_iter, A.info()["bytes_per_action"]))
 except Exception:
     ok, msg = False, traceback.format_exc()
 flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
