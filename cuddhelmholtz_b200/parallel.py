@@ -350,8 +350,8 @@ def slab_gmres(apply, x, b, mask, m, maxit, tol=1e-6, group=None, world=1):
             out["allreduces"] += 1
         return t
 
-    def dot(a, c):
-        return float(reduce_(torch.dot(mask * a, c).reshape(1).double())[0])
+    def dot(a, c):  # local partial sums in FP64 whatever the vector type (the FP32 path of DDH included)
+        return float(reduce_(torch.dot((mask * a).double(), c.double()).reshape(1))[0])
 
     bnrm = np.sqrt(dot(b, b))
     V = torch.zeros(m + 1, n, dtype=x.dtype, device=x.device)
@@ -376,8 +376,9 @@ def slab_gmres(apply, x, b, mask, m, maxit, tol=1e-6, group=None, world=1):
             out["num_matvec"] += 1
             mw = mask * w
             red = torch.empty(k1 + 1, dtype=torch.float64, device=x.device)  # partial sums travel in FP64 (FP32 path too)
-            red[:k1] = (V[:k1] @ mw).double()
-            red[k1] = torch.dot(mw, w).double()
+            mw64 = mw.double()
+            red[:k1] = V[:k1].double() @ mw64 if x.dtype != torch.float64 else V[:k1] @ mw64
+            red[k1] = torch.dot(mw64, w.double())
             red = reduce_(red).cpu().numpy()
             h, ww = red[:k1], red[k1]
             w = w - torch.as_tensor(h, dtype=x.dtype, device=x.device) @ V[:k1]
