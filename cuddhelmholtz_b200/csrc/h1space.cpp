@@ -25,6 +25,57 @@ namespace cb200
         const int ne_int = nb - 2;
         CB_REQUIRE((double)nel * nb * nb < 2.0e9, "H1Space: n_elem * n_basis^2 exceeds 32-bit DOF ids");
         I.assign((size_t)nb * nb * nel, -1);
+        const double * q = basis->x.data();
+        const bool closed_form = mesh->nx > 0 && !(getenv("CUDDH_B200_CLOSED_FORM") && atoi(getenv("CUDDH_B200_CLOSED_FORM")) == 0);
+        if (closed_form) {
+            // Mesh2D::uniform_rect: the first-touch scan below has a closed form (oracle/setup_np.py:uniform_rect_closed_form, pinned to
+            // the reference's arrays up to 1024^2): element (ex, ey) introduces the nodes with (i > 0 or ex == 0) and (j > 0 or ey == 0),
+            // numbered in (j, i) order after all nodes of the elements before it; every other node belongs to the element to its left /
+            // below. Nodal coordinates: the LAST element that touches a node wins in the reference's loop, i.e. an element writes node
+            // (i, j) unless a right / upper neighbour also holds it. Both loops run on all host threads (disjoint writes).
+            const int64_t nx = mesh->nx, ny = mesh->ny;
+            const int p = nb - 1;
+            std::vector<int64_t> base((size_t)nel + 1, 0); // first global id introduced by element el
+            for (int64_t el = 0; el < nel; ++el) {
+                const int64_t ex = el % nx, ey = el / nx;
+                base[el + 1] = base[el] + (int64_t)(ex == 0 ? nb : p) * (ey == 0 ? nb : p);
+            }
+            ndof = base[nel];
+            auto gid = [&](int64_t gx, int64_t gy) -> int {
+                const int64_t ox = gx == 0 ? 0 : (gx - 1) / p, oy = gy == 0 ? 0 : (gy - 1) / p; // owning element
+                const int64_t oi = gx - p * ox, oj = gy - p * oy;                              // its local node
+                const int64_t ni = ox == 0 ? nb : p;
+                return (int)(base[ox + nx * oy] + (oj - (oy > 0 ? 1 : 0)) * ni + (oi - (ox > 0 ? 1 : 0)));
+            };
+            xy.assign(2 * (size_t)ndof, 0.0);
+            parallel_for(ny, [&](int64_t jb, int64_t je, int) {
+                for (int64_t ey = jb; ey < je; ++ey)
+                    for (int64_t ex = 0; ex < nx; ++ex) {
+                        const int64_t el = ex + nx * ey;
+                        int * Ie = &I[(size_t)nb * nb * el];
+                        double c[8];
+                        mesh->corners(el, c);
+                        for (int j = 0; j < nb; ++j)
+                            for (int i = 0; i < nb; ++i) {
+                                const int id = gid(ex * p + i, ey * p + j);
+                                Ie[i + nb * j] = id;
+                                if ((i < p || ex == nx - 1) && (j < p || ey == ny - 1)) { // this element is the last one to touch the node
+                                    const double xi0 = q[i], xi1 = q[j];
+                                    const double b[4] = {0.25 * (1.0 - xi0) * (1.0 - xi1), 0.25 * (1.0 + xi0) * (1.0 - xi1),
+                                                         0.25 * (1.0 + xi0) * (1.0 + xi1), 0.25 * (1.0 - xi0) * (1.0 + xi1)};
+                                    double x0 = 0.0, x1 = 0.0;
+                                    for (int k = 0; k < 4; ++k) {
+                                        x0 += c[2 * k] * b[k];
+                                        x1 += c[2 * k + 1] * b[k];
+                                    }
+                                    xy[2 * (size_t)id] = x0;
+                                    xy[2 * (size_t)id + 1] = x1;
+                                }
+                            }
+                    }
+            });
+            return;
+        }
         std::vector<int> vertex_id((size_t)mesh->n_nodes, -1);
         std::vector<int> edge_id((size_t)mesh->n_edges * (size_t)std::max(ne_int, 0), -1);
         const int * elems = mesh->elems.data();
@@ -67,7 +118,6 @@ namespace cb200
         ndof = next;
 
         xy.assign(2 * (size_t)ndof, 0.0);
-        const double * q = basis->x.data();
         for (int64_t el = 0; el < nel; ++el) {
             double c[8];
             mesh->corners(el, c);

@@ -9,6 +9,7 @@
 #include "common.hpp"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <limits>
 
 namespace cb200
@@ -136,9 +137,86 @@ namespace cb200
                 el[4 * e + 2] = v00 + 1 + (nx + 1);
                 el[4 * e + 3] = v00 + (nx + 1);
             }
-        auto m = from_vertices(np, coo.data(), nel, el.data());
+        if (getenv("CUDDH_B200_CLOSED_FORM") && atoi(getenv("CUDDH_B200_CLOSED_FORM")) == 0) { // the generic edge-table path
+            auto m = from_vertices(np, coo.data(), nel, el.data());
+            m->nx = nx;
+            m->ny = ny;
+            return m;
+        }
+        // Closed form of from_vertices() on this vertex / element layout (bit-identical arrays, checked by tests/test_host_setup.py):
+        // elements are visited in order el = i + nx j, sides 0..3 = bottom, right, top, left; an element FIRST touches its right and
+        // top edge always, its bottom edge only in the first row and its left edge only in the first column, so the edge ids are a
+        // prefix sum, every interior edge has delta = +1 (both elements traverse it in the same direction), and no edge table is
+        // needed. Runs on all host threads.
+        CB_REQUIRE(np < (int64_t)std::numeric_limits<int>::max() && 4 * nel < (int64_t)std::numeric_limits<int>::max(),
+                   "Mesh2D::from_vertices: mesh too large for 32-bit vertex / edge ids");
+        std::unique_ptr<Mesh> m(new Mesh);
+        m->n_nodes = np;
+        m->n_elem = nel;
         m->nx = nx;
         m->ny = ny;
+        m->xy = std::move(coo);
+        m->elems = std::move(el);
+        const int64_t n_edges = (int64_t)nx * (ny + 1) + (int64_t)ny * (nx + 1);
+        m->n_edges = n_edges;
+        // first edge id of every element: 2 + (first row) + (first column) new edges per element
+        auto first_id = [nx](int64_t i, int64_t j) -> int64_t {
+            // elements before (i, j): j full rows + i elements of row j
+            const int64_t rows = j, before = rows * nx + i;
+            int64_t id = 2 * before;
+            id += (j == 0) ? i : nx;            // bottom edges: only elements of the first row own one
+            id += rows + ((i > 0) ? 1 : 0);     // left edges: the first element of every row owns one
+            return id;
+        };
+        m->edges.assign(8 * (size_t)n_edges, 0);
+        m->elem_edges.assign(4 * (size_t)nel, -1);
+        m->edge_meas.resize((size_t)n_edges);
+        int * E = m->edges.data();
+        const int * EL = m->elems.data();
+        const double * XY = m->xy.data();
+        static const int side_a[4] = {0, 1, 3, 0};
+        static const int side_b[4] = {1, 2, 2, 3};
+        parallel_for(ny, [&](int64_t jb, int64_t je, int) {
+            for (int64_t j = jb; j < je; ++j)
+                for (int64_t i = 0; i < nx; ++i) {
+                    const int64_t e_id = i + (int64_t)nx * j;
+                    const int64_t base = first_id(i, j);
+                    const int own0 = (j == 0) ? 1 : 0, own3 = (i == 0) ? 1 : 0;
+                    const int64_t id_of[4] = {own0 ? base : first_id(i, j - 1) + ((j - 1 == 0) ? 1 : 0) + 1, // top edge of the element below
+                                              base + own0, base + own0 + 1,
+                                              own3 ? base + own0 + 2 : first_id(i - 1, j) + ((j == 0) ? 1 : 0)}; // right edge of the left neighbour
+                    for (int s = 0; s < 4; ++s) {
+                        m->elem_edges[4 * e_id + s] = (int)id_of[s];
+                        const bool own = (s == 1 || s == 2) || (s == 0 && own0) || (s == 3 && own3);
+                        if (!own)
+                            continue;
+                        int * rec = E + 8 * id_of[s];
+                        const int c0 = EL[4 * e_id + side_a[s]], c1 = EL[4 * e_id + side_b[s]];
+                        rec[0] = c0;
+                        rec[1] = c1;
+                        rec[2] = (int)e_id;
+                        rec[4] = s;
+                        rec[6] = 1;
+                        // second element: the right edge is the left side of (i+1, j), the top edge the bottom side of (i, j+1)
+                        const bool interior = (s == 1 && i + 1 < nx) || (s == 2 && j + 1 < ny);
+                        rec[3] = interior ? (int)(s == 1 ? e_id + 1 : e_id + nx) : -1;
+                        rec[5] = interior ? (s == 1 ? 3 : 0) : -1;
+                        rec[7] = interior ? 0 : 1;
+                        const double ddx = XY[2 * (size_t)c1] - XY[2 * (size_t)c0], ddy = XY[2 * (size_t)c1 + 1] - XY[2 * (size_t)c0 + 1];
+                        m->edge_meas[(size_t)id_of[s]] = std::hypot(ddx, ddy) / 2; // StraightEdge: include/Edge.hpp:95-113
+                    }
+                }
+        });
+        double hmin = std::numeric_limits<double>::infinity(), hmax = -1;
+        m->boundary_edges.reserve(2 * ((size_t)nx + ny));
+        m->interior_edges.reserve((size_t)n_edges);
+        for (int64_t e = 0; e < n_edges; ++e) {
+            (E[8 * e + 7] ? m->boundary_edges : m->interior_edges).push_back((int)e);
+            hmin = std::min(hmin, 2.0 * m->edge_meas[(size_t)e]);
+            hmax = std::max(hmax, 2.0 * m->edge_meas[(size_t)e]);
+        }
+        m->min_h = hmin;
+        m->max_h = hmax;
         return m;
     }
 } // namespace cb200

@@ -104,6 +104,25 @@ def test_h1_hashes_larger(gold, key):
     assert fnv1a64(fs.subspace_indices()) == h["face_I"] and fnv1a64(fs.global_indices()) == h["face_proj"]
 
 
+@pytest.mark.parametrize("nx,ny,nb", [(1, 1, 2), (1, 5, 3), (7, 1, 4), (13, 9, 5), (5, 11, 9), (33, 17, 2)])
+def test_uniform_rect_closed_form_equals_generic_path(monkeypatch, nx, ny, nb):
+    # Mesh2D::uniform_rect / H1Space take closed forms of the edge table and of the first-touch numbering on structured meshes
+    # (csrc/mesh.cpp, csrc/h1space.cpp); CUDDH_B200_CLOSED_FORM=0 forces the generic from_vertices / first-touch scan
+    # (source/Mesh2D.cpp:59-171, source/H1Space.cpp:11-127). Every array must be bit-identical, also on non-square, non-symmetric boxes.
+    def build():
+        mesh = cb.Mesh2D.uniform_rect(nx, -0.3, 1.7, ny, 0.1, 0.9)
+        fem = cb.H1Space(mesh, cb.Basis(nb))
+        fs = cb.FaceSpace(fem, mesh.boundary_edges())
+        return [mesh.edges().copy(), mesh.boundary_edges().copy(), np.array([mesh.min_h(), mesh.max_h(), mesh.n_edges(), fem.size()]),
+                fem.global_indices().copy(), fem.physical_coordinates().copy(), fs.subspace_indices().copy(), fs.global_indices().copy()]
+    monkeypatch.setenv("CUDDH_B200_CLOSED_FORM", "0")
+    generic = build()
+    monkeypatch.delenv("CUDDH_B200_CLOSED_FORM")
+    closed = build()
+    for a, b in zip(generic, closed):
+        assert a.shape == b.shape and np.array_equal(a, b)
+
+
 def test_uniform_rect_2048_is_not_corrupt():
     # the reference's 32-bit edge key corrupts uniform_rect(2048) (6 293 504 edges, 73 413 630 DOFs).
     # Closed forms: edges = 2 nx (nx+1); ndof = (nx (nb-1) + 1)^2. Checked at 2048 x 64 to keep the CPU suite short,
