@@ -316,7 +316,8 @@ class Operator:
         return bool(load().cuddh_b200_operator_is_affine(self._h))
 
     def kernel_kind(self):
-        """0 lane-per-row / generic kernel, 1 warp-specialised thread-per-element kernel, 2 fused Helmholtz kernel, -1 n/a."""
+        """0 lane-per-row / generic kernel, 1 warp-specialised thread-per-element kernel, 2 fused Helmholtz kernel,
+        3 warp-specialised thread-pair-per-element kernel (n_basis 6-9), -1 n/a."""
         return int(load().cuddh_b200_operator_kernel_kind(self._h))
 
     def is_fused(self):

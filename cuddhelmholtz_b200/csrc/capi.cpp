@@ -470,9 +470,9 @@ int cuddh_b200_operator_is_affine(cuddh_operator_t op)
 int cuddh_b200_operator_kernel_kind(cuddh_operator_t op)
 {
     if (op->vol)
-        return op->vol->tpe ? 1 : 0;
+        return op->vol->tpe ? 1 : (op->vol->pair ? 3 : 0);
     if (op->helm)
-        return op->helm->fused ? 2 : (op->helm->S->tpe ? 1 : 0);
+        return op->helm->fused ? 2 : (op->helm->S->tpe ? 1 : (op->helm->S->pair ? 3 : 0));
     return -1;
 }
 

@@ -313,7 +313,7 @@ namespace cb200
         if (tpe) { // one thread per element: a patch is one warpgroup (128 threads) of elements, 8 x 16 tiles (measured: 16 x 8,
                    // 32 x 4, 4 x 32 and 64 x 2 are within 1-5 % of it)
             px = 8;
-            py = 16;
+            py = nb >= 6 ? 8 : 16; // n_basis >= 6: thread-PAIR-per-element kernel (volume_action_pair), 64 elements per patch
             if (const char * e = getenv("CUDDH_B200_TPE_PX"))
                 px = std::max(1, atoi(e));
             if (const char * e = getenv("CUDDH_B200_TPE_PY"))

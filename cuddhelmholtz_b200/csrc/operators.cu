@@ -25,6 +25,7 @@
 #include "operators.hpp"
 #include <algorithm>
 #include <cmath>
+#include <type_traits>
 
 namespace cb200
 {
@@ -423,6 +424,7 @@ namespace cb200
         }
 
 #include "volume_ws.cuh" // the warp-specialised thread-per-element kernel and its metric ring (device code only)
+#include "volume_pair.cuh" // the thread-pair-per-element kernel of the high orders (device code only)
 
         // generic fallback for (nb, nq) pairs without a template instance: same algorithm and data layout
         // with EPW = 1 (one element per warp pass), runtime loops, tables in global memory.
@@ -608,6 +610,23 @@ namespace cb200
             return ((size_t)(p * n_pass + e / EPW) * NK + (NKI * ty + a)) * LW + (size_t)(e % EPW) * NQ + tx;
         }
 
+        // thread-pair layout of volume_action_pair (EPW == -1): [patch][row tx][pair of values][thread slot 0..127]; thread slot
+        // s = (e / 16) * 32 + h * 16 + e % 16 of half h holds, for its local quadrature column tt (ty = tt in the natural frame
+        // h = 0, ty = nq-1-tt in the mirrored frame h = 1), the NKI values at k = tt * NKI + a. The middle column of an odd nq
+        // belongs to h = 0 (the h = 1 copy stays zero); *sign is -1 for the off-diagonal stiffness term in the mirrored frame.
+        __device__ __forceinline__ size_t metric_index_pair(const int64_t p, const int e, const int NQ, const int NKI, const int tx,
+                                                            const int ty, const int a, double * sign)
+        {
+            const int TA = (NQ + 1) / 2;
+            const int h = ty < TA ? 0 : 1;
+            const int tt = h ? NQ - 1 - ty : ty;
+            const int KR = (NKI * TA + 1) & ~1, NPR = KR / 2;
+            const int k = tt * NKI + a;
+            const int s = (e >> 4) * 32 + h * 16 + (e & 15);
+            *sign = (h && NKI == 3 && a == 1) ? -1.0 : 1.0;
+            return ((((size_t)p * NQ + tx) * NPR + (k >> 1)) * 128 + s) * 2 + (k & 1);
+        }
+
         __global__ void setup_stiffness_kernel(const int64_t n_slots, const int PE, const int NQ, const int EPW,
                                                const int n_pass, const int * __restrict__ slot_elem,
                                                const double * __restrict__ corners, const double * __restrict__ xq,
@@ -633,6 +652,14 @@ namespace cb200
                 g0 = W * (Y_eta * Y_eta + X_eta * X_eta) / det;
                 g1 = -W * (Y_xi * Y_eta + X_xi * X_eta) / det;
                 g2 = W * (Y_xi * Y_xi + X_xi * X_xi) / det;
+            }
+            if (EPW < 0) {
+                double sg;
+                G[metric_index_pair(p, e, NQ, 3, i, j, 0, &sg)] = g0;
+                const size_t i1 = metric_index_pair(p, e, NQ, 3, i, j, 1, &sg);
+                G[i1] = sg * g1;
+                G[metric_index_pair(p, e, NQ, 3, i, j, 2, &sg)] = g2;
+                return;
             }
             G[metric_index(p, e, PE, NQ, EPW, n_pass, 3, i, j, 0)] = g0;
             G[metric_index(p, e, PE, NQ, EPW, n_pass, 3, i, j, 1)] = g1;
@@ -682,7 +709,8 @@ namespace cb200
             const int64_t p = slot / PE;
             const int e = (int)(slot - p * PE);
             const int el = slot_elem[slot];
-            const size_t idx = metric_index(p, e, PE, NQ, EPW, n_pass, 1, tx, ty, 0);
+            double sg_;
+            const size_t idx = EPW < 0 ? metric_index_pair(p, e, NQ, 1, tx, ty, 0, &sg_) : metric_index(p, e, PE, NQ, EPW, n_pass, 1, tx, ty, 0);
             double val = 0.0;
             if (el >= 0) {
                 double ppx = 0.0;
@@ -1087,9 +1115,11 @@ namespace cb200
             constexpr int NI = (NB > 2 ? NB - 2 : 0) * (NB > 2 ? NB - 2 : 0);
             constexpr int NPRa = TpeCfg<NB, NQ, STIFF>::KR / 2, NPRb = NQ2 > 0 ? TpeCfg<NB, (NQ2 > 0 ? NQ2 : 1), false>::KR / 2 : 0;
             constexpr int CHUNK_PAIRS = ring_cp(NPRa) > (NQ2 > 0 ? ring_cp(NPRb) : 0) ? ring_cp(NPRa) : ring_cp(NPRb);
-            constexpr int NBUF = RING > 2 ? 2 : 3; // as in the kernel
+            constexpr int NBUF = (RING > 2 || RING < 0) ? 2 : 3; // as in the kernel
+            constexpr int RSLOTS = RING < 0 ? -RING : RING;
+            constexpr int SLOT_PAIRS = (RING < 0 && AFFINE && NQ2 > 0) ? NPRb : CHUNK_PAIRS; // per-thread ring of mass rows: one slot = one row
             const size_t smem = sizeof(double) * NBUF * (size_t)NB * NB * 128 + sizeof(int) * NBUF * (size_t)NI * 128 +
-                                (size_t)RING * CHUNK_PAIRS * 128 * sizeof(double2) + (size_t)RING * 8 + 16;
+                                (size_t)RSLOTS * SLOT_PAIRS * 128 * sizeof(double2) + (size_t)RSLOTS * 8 + 16;
             Tables<NB, NQ, STIFF> tab;
             fill_tables(tab, op);
             typename Phase2<NB, NQ2>::type tab2;
@@ -1173,7 +1203,80 @@ namespace cb200
             launch_ws<NB, NQ, STIFF, 0, RING, AFFINE>(op, nullptr, pd, plan, a, s);
         }
 
+        // thread-pair-per-element kernel (volume_pair.cuh): n_basis 6-9
+        template <int NB, int NQ, bool STIFF, bool AFFINE = false>
+        void launch_volume_pair(VolumeOp & op, const PlanDev & pd, const Plan & plan, double c, int accumulate, const double * x, double * y,
+                                cudaStream_t s)
+        {
+            CB_REQUIRE(plan.PE == 64, "thread-pair kernel: patches must hold 64 elements");
+            constexpr int NI = (NB - 2) * (NB - 2);
+            const size_t smem = sizeof(double) * 2 * (size_t)NB * NB * 64 + sizeof(int) * 2 * (size_t)NI * 64 + 16;
+            PairTables<NB, NQ, STIFF> tab;
+            std::memset(&tab, 0, sizeof(tab));
+            for (int q = 0; q < NQ; ++q)
+                for (int k = 0; k < NB; ++k) {
+                    tab.Prow[q][k] = op.P[q + NQ * k];
+                    if (STIFF) {
+                        tab.Drow[q][k] = op.D[q + NQ * k];
+                        if (!op.wq.empty()) {
+                            tab.PWrow[q][k] = op.wq[q] * op.P[q + NQ * k];
+                            tab.DWrow[q][k] = op.wq[q] * op.D[q + NQ * k];
+                        }
+                    }
+                }
+            auto kern = volume_action_pair<NB, NQ, STIFF, AFFINE>;
+            static int grid_of_device[MAX_DEVICES] = {};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            CB_REQUIRE(dev >= 0 && dev < MAX_DEVICES, "device ordinal out of range");
+            int & grid = grid_of_device[dev];
+            if (!grid) {
+                CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)49152)));
+                CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                int sms = 148, occ = 1;
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+                grid = std::max(1, occ) * sms;
+            }
+            PairArgs a{};
+            a.G = reinterpret_cast<const double2 *>(op.d_G.p);
+            a.Gc = op.d_Gc.p;
+            a.x = x;
+            a.y = y;
+            a.partial = op.d_partial.p;
+            a.c = c;
+            a.msc = 1.0;
+            a.accumulate = accumulate;
+            a.n_patches = (int)plan.n_patches;
+            a.zero = 0;
+            const int cap = max_persistent_ctas();
+            const int wave = cap > 0 ? std::min(grid, cap) : grid;
+            const int g = (int)std::min<int64_t>(wave, plan.n_patches);
+            kern<<<g, 256, smem, s>>>(tab, pd, a);
+            CB_LAUNCHED();
+        }
+
         using LaunchFn = void (*)(VolumeOp &, const PlanDev &, const Plan &, double, int, const double *, double *, cudaStream_t);
+
+        template <bool STIFF>
+        LaunchFn find_pair_instance(int nb, int nq, bool affine = false)
+        {
+#define CB_CASE(NB_, NQ_)                                                                                              \
+    if (nb == NB_ && nq == NQ_) {                                                                                      \
+        if constexpr (STIFF) {                                                                                         \
+            if (affine)                                                                                                \
+                return &launch_volume_pair<NB_, NQ_, true, true>;                                                      \
+        }                                                                                                              \
+        return &launch_volume_pair<NB_, NQ_, STIFF, false>;                                                            \
+    }
+            // default rules nq = nb + 1 (reference StiffnessMatrix.cpp:45, MassMatrix.cpp:74)
+            CB_CASE(6, 7) CB_CASE(7, 8) CB_CASE(8, 9) CB_CASE(9, 10)
+            if constexpr (!STIFF) { // weighted mass: nq = 1 + 3nb/2 + 1 (MassMatrix.cpp:108)
+                CB_CASE(6, 11) CB_CASE(7, 12) CB_CASE(8, 14) CB_CASE(9, 15)
+            }
+#undef CB_CASE
+            return nullptr;
+        }
 
         // thread-per-element instances: n_basis <= 5 (U and the result fit in registers next to the row temporaries)
         // stiffness on all-affine meshes (VolumeOp::affine): per-element metric constants, no metric stream
@@ -1195,22 +1298,30 @@ namespace cb200
             // n_basis 5: metric data through the shared-memory ring (see contract_phase_ring)
             static const int ring = env_int("CUDDH_B200_RING1", 5);
             if constexpr (STIFF) {
+                if (ring == -5 && nb == 5 && nq == 6) // negative: per-thread cp.async ring (no row barrier)
+                    return &launch_volume_ws<5, 6, true, -5>;
                 if (ring == 2 && nb == 5 && nq == 6)
                     return &launch_volume_ws<5, 6, true, 2>;
                 if (ring == 5 && nb == 5 && nq == 6)
                     return &launch_volume_ws<5, 6, true, 5>;
                 static const int ring4 = env_int("CUDDH_B200_RING4", 5);
+                if (ring4 == -5 && nb == 4 && nq == 5)
+                    return &launch_volume_ws<4, 5, true, -5>;
                 if (ring4 == 2 && nb == 4 && nq == 5)
                     return &launch_volume_ws<4, 5, true, 2>;
                 if (ring4 == 5 && nb == 4 && nq == 5)
                     return &launch_volume_ws<4, 5, true, 5>;
             }
             else {
+                if (ring == -5 && nb == 5 && nq == 9)
+                    return &launch_volume_ws<5, 9, false, -5>;
                 if (ring == 2 && nb == 5 && nq == 9)
                     return &launch_volume_ws<5, 9, false, 2>;
                 if (ring == 5 && nb == 5 && nq == 9)
                     return &launch_volume_ws<5, 9, false, 5>;
                 static const int ring4 = env_int("CUDDH_B200_RING4", 5);
+                if (ring4 == -5 && nb == 4 && nq == 8)
+                    return &launch_volume_ws<4, 8, false, -5>;
                 if (ring4 == 2 && nb == 4 && nq == 8)
                     return &launch_volume_ws<4, 8, false, 2>;
                 if (ring4 == 5 && nb == 4 && nq == 8)
@@ -1245,10 +1356,16 @@ namespace cb200
         FusedFn find_fused_instance(int nb, int nqs, int nqm, bool affine = false)
         {
             if (affine) {
+                // mass rows through the shared-memory ring (5) or straight from global memory into registers (0)
+                static const int aring = env_int("CUDDH_B200_AFFINE_RING", -4);
+                // (negative: per-thread cp.async ring of that many rows)
                 if (nb == 5 && nqs == 6 && nqm == 9)
-                    return &launch_ws<5, 6, true, 9, 5, true>;
+                    return aring == 0 ? &launch_ws<5, 6, true, 9, 0, true> : aring == -3 ? &launch_ws<5, 6, true, 9, -3, true>
+                         : aring == -5 ? &launch_ws<5, 6, true, 9, -5, true> : aring == 5 ? &launch_ws<5, 6, true, 9, 5, true>
+                         : &launch_ws<5, 6, true, 9, -4, true>;
                 if (nb == 4 && nqs == 5 && nqm == 8)
-                    return &launch_ws<4, 5, true, 8, 5, true>;
+                    return aring == 0 ? &launch_ws<4, 5, true, 8, 0, true> : aring == 5 ? &launch_ws<4, 5, true, 8, 5, true>
+                         : &launch_ws<4, 5, true, 8, -4, true>;
                 return nullptr;
             }
             static const int ring = env_int("CUDDH_B200_RING", 5);
@@ -1256,11 +1373,15 @@ namespace cb200
     if (nb == NB_ && nqs == NQS_ && nqm == NQM_)                                                                       \
         return &launch_ws<NB_, NQS_, true, NQM_>;
             // shared-memory metric ring for the register-bound n_basis 5 instance
+            if (nb == 5 && nqs == 6 && nqm == 9 && ring == -5)
+                return &launch_ws<5, 6, true, 9, -5>;
             if (nb == 5 && nqs == 6 && nqm == 9 && ring == 2)
                 return &launch_ws<5, 6, true, 9, 2>;
             if (nb == 5 && nqs == 6 && nqm == 9 && ring == 5)
                 return &launch_ws<5, 6, true, 9, 5>;
             static const int ring4 = env_int("CUDDH_B200_RING4", 5);
+            if (nb == 4 && nqs == 5 && nqm == 8 && ring4 == -5)
+                return &launch_ws<4, 5, true, 8, -5>;
             if (nb == 4 && nqs == 5 && nqm == 8 && ring4 == 2)
                 return &launch_ws<4, 5, true, 8, 2>;
             if (nb == 4 && nqs == 5 && nqm == 8 && ring4 == 5)
@@ -1283,6 +1404,8 @@ namespace cb200
         LaunchFn fn = generic ? nullptr : (stiff ? find_instance<true>(nb, nq) : find_instance<false>(nb, nq));
         if (tpe)
             fn = affine ? find_affine_instance(nb, nq) : (stiff ? find_tpe_instance<true>(nb, nq) : find_tpe_instance<false>(nb, nq));
+        if (pair)
+            fn = stiff ? find_pair_instance<true>(nb, nq, affine) : find_pair_instance<false>(nb, nq);
         if (!(phases & 1)) {
         }
         else if (fn)
@@ -1338,7 +1461,22 @@ namespace cb200
             op.nk = (stiff ? 3 : 1) * nq;
             op.affine = want_affine && stiff && op.tpe && find_affine_instance(op.nb, nq) != nullptr && env_int("CUDDH_B200_AFFINE", 1) != 0 &&
                         fem->all_affine();
-            if (op.tpe) { // thread-per-element layout: [pair of metric values][element], see volume_action_ws
+            LaunchFn fp = stiff ? find_pair_instance<true>(op.nb, nq) : find_pair_instance<false>(op.nb, nq);
+            op.pair = !op.generic && !op.tpe && fp != nullptr && env_int("CUDDH_B200_PAIR", 1) != 0;
+            if (op.pair) { // thread-pair layout: [row][pair of metric values][thread slot], see volume_action_pair / metric_index_pair
+                op.affine = want_affine && stiff && env_int("CUDDH_B200_AFFINE", 1) != 0 && fem->all_affine();
+                op.plan = &fem->get_plan_tpe();
+                CB_REQUIRE(op.plan->PE == 64, "thread-pair kernel: the node-major plan must have 64-element patches");
+                op.epw = -1;
+                op.lw = 0;
+                op.n_pass = 0;
+                const int TA = (nq + 1) / 2, KR = ((stiff ? 3 : 1) * TA + 1) & ~1;
+                if (op.affine)
+                    op.d_Gc.alloc((size_t)op.plan->n_patches * 3 * op.plan->PE);
+                else
+                    op.d_G.alloc((size_t)op.plan->n_patches * (size_t)nq * KR * 128);
+            }
+            else if (op.tpe) { // thread-per-element layout: [pair of metric values][element], see volume_action_ws
                 op.plan = &fem->get_plan_tpe();
                 op.epw = 0;
                 op.lw = 0;

@@ -25,6 +25,7 @@ namespace cb200
         int epw = 0, lw = 0, n_pass = 0, nk = 0;  // layout constants (see operators.cu)
         bool generic = false;
         bool tpe = false;             // thread-per-element kernel + node-major plan (n_basis <= 5)
+        bool pair = false;            // thread-pair-per-element kernel + node-major plan of 64-element patches (n_basis 6-9)
         Plan * plan = nullptr;        // the assembly plan this operator was laid out for (owned by fem)
 
         // phases: bit 0 = patch kernel, bit 1 = shared-DOF assembly pass (3 = the full action)

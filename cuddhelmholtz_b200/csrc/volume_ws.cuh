@@ -59,6 +59,16 @@
         {
             asm volatile("barrier.cluster.arrive.relaxed.aligned;\nbarrier.cluster.wait.aligned;" ::: "memory");
         }
+        // split form: a thread arrives at the top of patch iteration k and waits for that arrival of everybody only at the top of
+        // iteration k + 1, so the two CTAs of a pair may drift by up to one patch without anybody stalling
+        __device__ __forceinline__ void cluster_arrive()
+        {
+            asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+        }
+        __device__ __forceinline__ void cluster_wait()
+        {
+            asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+        }
         // 16-byte metric pairs of one quadrature row that are no longer needed after quadrature point ty
         template <int NQ, int NKI, int KR>
         __host__ __device__ constexpr int pairs_done(int ty)
@@ -232,7 +242,10 @@
         };
 
         // one operator phase fed from the ring; `issue(slot)` (thread 0 only) starts the copy of the next chunk of the stream
-        template <int NB, int NQ, bool STIFF, int PE, int RING, int CHUNK_PAIRS, class IssueFn>
+        // TR: per-thread ring (see contract_mass_tring below) - every thread copies its own pairs with 16-byte cp.async, one group
+        // per chunk, waits with cp.async.wait_group and refills the chunks of a row after the row's values have been consumed:
+        // no mbarrier, no row barrier, no leader. `issue(slot)` is then called by every thread.
+        template <int NB, int NQ, bool STIFF, int PE, int RING, int CHUNK_PAIRS, bool TR = false, class IssueFn>
         __device__ __forceinline__ void contract_phase_ring(const Tables<NB, NQ, STIFF> & tab, const double (&U)[NB * NB], RingState & rs, const int e,
                                                             double (&out)[NB * NB], const double msc, const int zero, const bool leader,
                                                             IssueFn issue)
@@ -317,7 +330,12 @@
                     if (rr == 0 || tx0 + rr < NQ) {
 #pragma unroll
                         for (int h = 0; h < NH; ++h) {
-                            mbar_wait(rs.mbar + 8 * rs.slot, (unsigned)rs.parity);
+                            if constexpr (TR) {
+                                if (h == 0)
+                                    asm volatile("cp.async.wait_group %0;" ::"n"(RING - NH) : "memory"); // the NH oldest chunk groups have landed
+                            }
+                            else
+                                mbar_wait(rs.mbar + 8 * rs.slot, (unsigned)rs.parity);
                             const double2 * src = rs.ring + (size_t)rs.slot * (CHUNK_PAIRS * PE) + e;
 #pragma unroll
                             for (int m = 0; m < CP; ++m)
@@ -336,18 +354,25 @@
                 // the first-index contraction runs while the ring reads above are still in flight
                 double pu[NB], du[STIFF ? NB : 1];
                 row_first(tx0, pu, du);
-                named_sync(8, PE); // every thread of the warpgroup holds its pairs in registers: the slots are free
-                if (leader) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if constexpr (!TR) {
+                    named_sync(8, PE); // every thread of the warpgroup holds its pairs in registers: the slots are free
+                    if (leader) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #pragma unroll
-                    for (int rr = 0; rr < RG; ++rr)
-                        if (rr == 0 || tx0 + rr < NQ) {
+                        for (int rr = 0; rr < RG; ++rr)
+                            if (rr == 0 || tx0 + rr < NQ) {
 #pragma unroll
-                            for (int h = 0; h < NH; ++h)
-                                issue(freed[rr * NH + h]);
-                        }
+                                for (int h = 0; h < NH; ++h)
+                                    issue(freed[rr * NH + h]);
+                            }
+                    }
                 }
                 row_rest(tx0, g[0], pu, du);
+                if constexpr (TR) { // the row's values have been consumed (their shared-memory reads completed): refill its chunks
+#pragma unroll
+                    for (int h = 0; h < NH; ++h)
+                        issue(freed[h]);
+                }
             }
         }
 
@@ -406,6 +431,142 @@
             }
         }
 
+        // Weighted-mass phase fed straight from global memory (fused AFFINE instances with RING == 0): with the stiffness metric gone
+        // (contract_stiff_affine) the register file has room for TWO mass rows per thread (KR doubles each), so the rows can come
+        // in with plain 128-bit loads one row ahead of their use - no shared-memory ring, no mbarrier, no 128-thread row barrier
+        // and no refill work on a leader warp (profiles/r02_notes.md §1: 20 % of the compute warps' samples in the ring kernel).
+        // g0 / g1 hold rows 0 / 1 on entry (loaded by the caller BEFORE the stiffness phase, so they have landed long before);
+        // every 16-byte pair is replaced by the pair of row tx + 2 as soon as its last value has been used. The blocks were
+        // bulk-prefetched into L2 by the helper one patch ahead. Same arithmetic, value for value, as contract_phase_ring.
+        __device__ __forceinline__ double2 ld_metric_pair(const double2 * q)
+        {
+            double2 v;
+            asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(q));
+            return v;
+        }
+        template <int NB, int NQ, int PE>
+        __device__ __forceinline__ void contract_mass_direct(const Tables<NB, NQ, false> & tab, const double (&U)[NB * NB],
+                                                             double (&g0)[TpeCfg<NB, NQ, false>::KR], double (&g1)[TpeCfg<NB, NQ, false>::KR],
+                                                             const double2 * gp, double (&out)[NB * NB], const double msc, const int zero)
+        {
+            constexpr int KR = TpeCfg<NB, NQ, false>::KR, NPR = KR / 2;
+            auto do_row = [&](const int tx, double (&g)[KR], const double2 * gnext, const bool reload) {
+                const int z = tx * zero; // 0 at run time; keeps the ty-indexed table loads inside the rolled loop
+                double pu[NB];
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    double s0 = 0.0;
+#pragma unroll
+                    for (int ii = 0; ii < NB; ++ii)
+                        s0 = fma(tab.Prow[tx][ii], U[ii + NB * j], s0);
+                    pu[j] = s0;
+                }
+                double a0[NB];
+#pragma unroll
+                for (int q = 0; q < NB; ++q)
+                    a0[q] = 0.0;
+#pragma unroll
+                for (int ty = 0; ty < NQ; ++ty) {
+                    double ppu = 0.0;
+#pragma unroll
+                    for (int l = 0; l < NB; ++l)
+                        ppu = fma(tab.Prow[ty + z][l], pu[l], ppu);
+                    const double val = (g[ty] * msc) * ppu;
+#pragma unroll
+                    for (int q = 0; q < NB; ++q)
+                        a0[q] = fma(tab.Prow[ty + z][q], val, a0[q]);
+#pragma unroll
+                    for (int m = pairs_done<NQ, 1, KR>(ty - 1); m < pairs_done<NQ, 1, KR>(ty); ++m)
+                        if (reload) {
+                            const double2 v = ld_metric_pair(gnext + m * PE);
+                            g[2 * m] = v.x;
+                            g[2 * m + 1] = v.y;
+                        }
+                }
+#pragma unroll
+                for (int q = 0; q < NB; ++q)
+#pragma unroll
+                    for (int ii = 0; ii < NB; ++ii)
+                        out[ii + NB * q] = fma(tab.Prow[tx][ii], a0[q], out[ii + NB * q]);
+            };
+#pragma unroll 1
+            for (int tx = 0; tx < NQ; tx += 2) {
+                do_row(tx, g0, gp + (size_t)(tx + 2) * NPR * PE, tx + 2 < NQ);
+                if (tx + 1 < NQ)
+                    do_row(tx + 1, g1, gp + (size_t)(tx + 3) * NPR * PE, tx + 3 < NQ);
+            }
+        }
+
+        // Weighted-mass phase fed from a PER-THREAD shared-memory ring (fused AFFINE instances with RING < 0, depth -RING rows):
+        // every compute thread copies the rows of ITS OWN element with 16-byte cp.async (a warp's copies are one contiguous 512-byte
+        // run per pair) into its own column of the ring, -RING rows ahead of their use and across patches, and tracks completion with
+        // cp.async.wait_group. A thread only ever reads what it copied itself, so there is no mbarrier, no row barrier, no leader
+        // and no cross-warp coupling (the TMA ring above: 12 % of the compute warps' samples on the row barrier), and unlike the
+        // register-buffered variant (contract_mass_direct: 14 % long-scoreboard samples, one row ahead) the depth is not limited by
+        // the register file. Same arithmetic, value for value, as contract_phase_ring.
+        __device__ __forceinline__ void cp_async16(void * smem, const void * g)
+        {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+        }
+        template <int N>
+        __device__ __forceinline__ void cp_async_wait_group()
+        {
+            asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+        }
+        template <int NB, int NQ, int PE, int RD, class RequestFn>
+        __device__ __forceinline__ void contract_mass_tring(const Tables<NB, NQ, false> & tab, const double (&U)[NB * NB], const double2 * myring,
+                                                            int & slot, double (&out)[NB * NB], const double msc, const int zero,
+                                                            RequestFn request)
+        {
+            constexpr int KR = TpeCfg<NB, NQ, false>::KR, NPR = KR / 2;
+#pragma unroll 1
+            for (int tx = 0; tx < NQ; ++tx) {
+                const int z = tx * zero; // 0 at run time; keeps the ty-indexed table loads inside the rolled loop
+                cp_async_wait_group<RD - 1>(); // the oldest of the RD row groups in flight has landed
+                double g[KR];
+                const double2 * src = myring + (size_t)slot * (NPR * PE);
+#pragma unroll
+                for (int m = 0; m < NPR; ++m) {
+                    const double2 v = src[m * PE];
+                    g[2 * m] = v.x;
+                    g[2 * m + 1] = v.y;
+                }
+                double pu[NB];
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    double s0 = 0.0;
+#pragma unroll
+                    for (int ii = 0; ii < NB; ++ii)
+                        s0 = fma(tab.Prow[tx][ii], U[ii + NB * j], s0);
+                    pu[j] = s0;
+                }
+                double a0[NB];
+#pragma unroll
+                for (int q = 0; q < NB; ++q)
+                    a0[q] = 0.0;
+#pragma unroll
+                for (int ty = 0; ty < NQ; ++ty) {
+                    double ppu = 0.0;
+#pragma unroll
+                    for (int l = 0; l < NB; ++l)
+                        ppu = fma(tab.Prow[ty + z][l], pu[l], ppu);
+                    const double val = (g[ty] * msc) * ppu;
+#pragma unroll
+                    for (int q = 0; q < NB; ++q)
+                        a0[q] = fma(tab.Prow[ty + z][q], val, a0[q]);
+                }
+                // every value of the slot has been consumed (its loads completed long ago): refill it with the row RD further on
+                request(slot);
+                if (++slot == RD)
+                    slot = 0;
+#pragma unroll
+                for (int q = 0; q < NB; ++q)
+#pragma unroll
+                    for (int ii = 0; ii < NB; ++ii)
+                        out[ii + NB * q] = fma(tab.Prow[tx][ii], a0[q], out[ii + NB * q]);
+            }
+        }
+
         // second-phase placeholder for the single-operator instances
         struct NoTables
         {
@@ -453,20 +614,23 @@
             constexpr int NI = (NB > 2 ? NB - 2 : 0) * (NB > 2 ? NB - 2 : 0); // element-interior nodes
             constexpr bool HEAVY = STIFF && NB >= 5 && NQ2 > 0 && RING == 0 && !AFFINE; // register-path fused instance only
             static_assert(!AFFINE || STIFF, "AFFINE is a property of the stiffness phase");
-            static_assert(!AFFINE || NQ2 == 0 || RING > 0, "fused AFFINE instances feed the mass phase from the ring");
+            // fused AFFINE instances feed the mass phase from the ring (RING > 0) or straight from global memory (RING == 0)
 
             // shared-memory metric ring (RING > 0): chunk = CHUNK_PAIRS x PE 16-byte pairs
             constexpr int CP1 = ring_cp(NPR1), CP2 = NQ2 > 0 ? ring_cp(NPR2) : 0;
-            constexpr int CHUNK_PAIRS = CP1 > CP2 ? CP1 : CP2;
+            constexpr bool TRM = RING < 0 && AFFINE && NQ2 > 0; // per-thread ring of whole mass rows (contract_mass_tring)
+            constexpr bool TRG = RING < 0 && !TRM;              // per-thread ring of chunks, any phase (contract_phase_ring<TR>)
+            constexpr int CHUNK_PAIRS = TRM ? NPR2 : (CP1 > CP2 ? CP1 : CP2);
             // patch buffers in rotation: 3 (fill i+1 | compute i | assemble i-1 at the same time), or 2 for the deep-ring heavy
             // instances, where one unit of compute is long enough for the helper to assemble i-1 and THEN refill the same buffer
-            constexpr int NBUF = RING > 2 ? 2 : 3;
+            constexpr int NBUF = (RING > 2 || RING < 0) ? 2 : 3;
+            constexpr int RSLOTS = RING < 0 ? -RING : RING; // RING < 0: per-thread cp.async ring of -RING mass rows (contract_mass_tring)
 
             extern __shared__ __align__(16) unsigned char smem_raw[];
             double * bufs = reinterpret_cast<double *>(smem_raw); // [NBUF][NB2][PE]
             int * gints = reinterpret_cast<int *>(bufs + NBUF * BUF); // [NBUF][NI][PE] global DOFs of the element-interior nodes
             double2 * ring = reinterpret_cast<double2 *>(gints + NBUF * NI * PE);                        // [RING][CHUNK_PAIRS][PE]
-            unsigned long long * mbars = reinterpret_cast<unsigned long long *>(ring + RING * CHUNK_PAIRS * PE); // [RING]
+            unsigned long long * mbars = reinterpret_cast<unsigned long long *>(ring + RSLOTS * CHUNK_PAIRS * PE); // [RING]
 
             const int wg = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 7), 0); // warp-uniform by construction
             const int t = threadIdx.x & 127;
@@ -630,8 +794,11 @@
                 named_sync(HELPER, 128);
                 named_arrive(FULL + 0, 256);
                 for (int i = 0; i < n_iter; ++i) {
-                    if (NF > 1)
-                        cluster_sync_all(); // both CTAs of the pair (all 512 threads) start patch i together
+                    if (NF > 1) { // the CTAs of a pair stay within one patch of each other (split cluster barrier)
+                        if (i > 0)
+                            cluster_wait();
+                        cluster_arrive();
+                    }
                     if (NBUF >= 3 && i + 1 < n_iter)
                         issue_gather(i + 1);
                     if (i >= 1) {
@@ -650,6 +817,8 @@
                 }
                 named_sync(READY + (n_iter - 1) % NBUF, 256);
                 assemble(n_iter - 1);
+                if (NF > 1)
+                    cluster_wait();
             }
             else {
                 // =========================== compute warpgroup: one element per thread ===========================
@@ -689,6 +858,45 @@
                         }
                     }
                 };
+                // per-thread ring of chunks (TRG): the same cursor, advanced by every thread; one cp.async group per chunk (an empty
+                // group once the stream is exhausted, so that wait_group keeps counting chunks)
+                unsigned trg_dst = smem_u32(ring + e);
+                if constexpr (TRG)
+                    asm volatile("" : "+r"(trg_dst));
+                auto issue_tr = [&](const int slot) {
+                    if (cur_i < n_iter) {
+                        const int p = cta + cur_i * stride;
+                        const int npr = cur_ph == 0 ? NPR1 : NPR2, cp = cur_ph == 0 ? CP1 : CP2;
+                        const double2 * src = (cur_ph == 0 ? args.G1 + (size_t)p * g_patch1 : args.G2 + (size_t)p * g_patch2) +
+                                              (size_t)(cur_r * npr + cur_h * cp) * PE + e;
+                        const int pairs = min(cp, npr - cur_h * cp);
+                        const unsigned dst = trg_dst + (unsigned)slot * (unsigned)(CHUNK_PAIRS * PE * sizeof(double2));
+#pragma unroll
+                        for (int m = 0; m < CHUNK_PAIRS; ++m)
+                            if (m < pairs)
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (unsigned)(m * PE * sizeof(double2))),
+                                             "l"(src + m * PE)
+                                             : "memory");
+                        const int nh = cur_ph == 0 ? ring_nh(NPR1) : ring_nh(NPR2 > 0 ? NPR2 : 1);
+                        const int nq = cur_ph == 0 ? NQ : NQ2;
+                        if (++cur_h == nh) {
+                            cur_h = 0;
+                            if (++cur_r == nq) {
+                                cur_r = 0;
+                                if (++cur_ph == (NQ2 > 0 ? 2 : 1)) {
+                                    cur_ph = FIRST_PH;
+                                    ++cur_i;
+                                }
+                            }
+                        }
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                };
+                if constexpr (TRG) {
+#pragma unroll
+                    for (int k = 0; k < RSLOTS; ++k)
+                        issue_tr(k);
+                }
                 if constexpr (RING > 0) {
                     if (t == 0) {
                         for (int k = 0; k < RING; ++k)
@@ -712,31 +920,96 @@
                         g1[2 * m + 1] = w.y;
                     }
                 }
+                // per-thread ring (RING < 0): request cursor (patch iteration, row) and consumer slot; one cp.async group per row, an
+                // empty group once the stream is exhausted so that wait_group keeps counting rows
+                // Source pointer, patch skip and ring address live in registers (made opaque to ptxas, which otherwise rebuilds them
+                // from the constant bank and SR_TID at every request: long-scoreboard samples on the uniform datapath).
+                int tr_i = 0, tr_r = 0, tr_slot = 0;
+                const double2 * tr_src = TRM ? args.G2 + (size_t)cta * g_patch2 + e : nullptr; // rows of a patch are contiguous
+                int tr_skip = (stride - 1) * (int)g_patch2;                                          // last row of a patch -> next patch of this CTA
+                unsigned tr_dst = smem_u32(ring + e);
+                if constexpr (TRM)
+                    asm volatile("" : "+l"(tr_src), "+r"(tr_skip), "+r"(tr_dst));
+                auto tr_request = [&](const int slot) {
+                    if constexpr (TRM) {
+                        if (tr_i < n_iter) {
+                            const unsigned dst = tr_dst + (unsigned)slot * (unsigned)(NPR2 * PE * sizeof(double2));
+#pragma unroll
+                            for (int m = 0; m < NPR2; ++m)
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (unsigned)(m * PE * sizeof(double2))),
+                                             "l"(tr_src + m * PE)
+                                             : "memory");
+                            tr_src += NPR2 * PE;
+                            if (++tr_r == NQ2) {
+                                tr_r = 0;
+                                ++tr_i;
+                                tr_src += tr_skip;
+                            }
+                        }
+                        asm volatile("cp.async.commit_group;" ::: "memory");
+                    }
+                };
+                if constexpr (TRM) {
+#pragma unroll
+                    for (int k = 0; k < -RING; ++k)
+                        tr_request(k);
+                }
                 for (int i = 0; i < n_iter; ++i) {
                     const int p = cta + i * stride;
                     double * b = bufs + (i % NBUF) * BUF + e;
                     // first phase of the next patch of this CTA (at the very end this one again: a harmless reload)
                     const int pn = (i + 1 < n_iter) ? p + stride : p;
-                    if (NF > 1)
-                        cluster_sync_all();
+                    if (NF > 1) {
+                        if (i > 0)
+                            cluster_wait();
+                        cluster_arrive();
+                    }
                     const double2 * gp1 = args.G1 + (size_t)p * g_patch1 + e;
                     const double2 * gp1_next = args.G1 + (size_t)pn * g_patch1 + e;
+                    // AFFINE: metric constants of this thread's element, requested before the wait for the patch buffer
+                    double gA = 0.0, gB = 0.0, gC = 0.0;
+                    if constexpr (AFFINE) {
+                        const double * gc = args.Gc + (size_t)p * (3 * PE) + e;
+                        gA = __ldg(gc);
+                        gB = __ldg(gc + PE);
+                        gC = __ldg(gc + 2 * PE);
+                    }
                     named_sync(FULL + i % NBUF, 256);
                     double out[NB2];
 #pragma unroll
                     for (int k = 0; k < NB2; ++k)
                         out[k] = 0.0;
                     if constexpr (AFFINE) {
-                        // metric constants of this thread's element; U in registers for both phases
-                        const double * gc = args.Gc + (size_t)p * (3 * PE) + e;
-                        const double gA = __ldg(gc), gB = __ldg(gc + PE), gC = __ldg(gc + 2 * PE);
+                        // U in registers for both phases
                         double U[NB2];
 #pragma unroll
                         for (int k = 0; k < NB2; ++k)
                             U[k] = b[k * PE];
-                        contract_stiff_affine<NB, NQ>(tab, U, gA, gB, gC, out, args.zero);
-                        if constexpr (NQ2 > 0)
-                            contract_phase_ring<NB, NQ2, false, PE, RING, CHUNK_PAIRS>(tab2, U, rs, e, out, args.msc, args.zero, t == 0, issue);
+                        if constexpr (NQ2 > 0 && RING < 0) {
+                            contract_stiff_affine<NB, NQ>(tab, U, gA, gB, gC, out, args.zero);
+                            contract_mass_tring<NB, NQ2, PE, -RING>(tab2, U, ring + e, tr_slot, out, args.msc, args.zero, tr_request);
+                        }
+                        else if constexpr (NQ2 > 0 && RING == 0) {
+                            // mass rows 0 and 1 of this patch: requested now, used after the stiffness phase
+                            constexpr int KR2 = Cfg2::KR;
+                            double m0[KR2], m1[KR2];
+                            const double2 * gp2 = args.G2 + (size_t)p * g_patch2 + e;
+#pragma unroll
+                            for (int m = 0; m < KR2 / 2; ++m) {
+                                const double2 v = ld_metric_pair(gp2 + m * PE), w = ld_metric_pair(gp2 + (KR2 / 2 + m) * PE);
+                                m0[2 * m] = v.x;
+                                m0[2 * m + 1] = v.y;
+                                m1[2 * m] = w.x;
+                                m1[2 * m + 1] = w.y;
+                            }
+                            contract_stiff_affine<NB, NQ>(tab, U, gA, gB, gC, out, args.zero);
+                            contract_mass_direct<NB, NQ2, PE>(tab2, U, m0, m1, gp2, out, args.msc, args.zero);
+                        }
+                        else {
+                            contract_stiff_affine<NB, NQ>(tab, U, gA, gB, gC, out, args.zero);
+                            if constexpr (NQ2 > 0)
+                                contract_phase_ring<NB, NQ2, false, PE, RING, CHUNK_PAIRS>(tab2, U, rs, e, out, args.msc, args.zero, t == 0, issue);
+                        }
                     }
                     else if constexpr (RING > 0) {
                         // the ring leaves room in the register file: U stays in registers for all rows of both phases
@@ -747,6 +1020,16 @@
                         contract_phase_ring<NB, NQ, STIFF, PE, RING, CHUNK_PAIRS>(tab, U, rs, e, out, 1.0, args.zero, t == 0, issue);
                         if constexpr (NQ2 > 0)
                             contract_phase_ring<NB, NQ2, false, PE, RING, CHUNK_PAIRS>(tab2, U, rs, e, out, args.msc, args.zero, t == 0, issue);
+                    }
+                    else if constexpr (TRG) {
+                        double U[NB2];
+#pragma unroll
+                        for (int k = 0; k < NB2; ++k)
+                            U[k] = b[k * PE];
+                        if constexpr (!AFFINE)
+                            contract_phase_ring<NB, NQ, STIFF, PE, RSLOTS, CHUNK_PAIRS, true>(tab, U, rs, e, out, 1.0, args.zero, false, issue_tr);
+                        if constexpr (NQ2 > 0)
+                            contract_phase_ring<NB, NQ2, false, PE, RSLOTS, CHUNK_PAIRS, true>(tab2, U, rs, e, out, args.msc, args.zero, false, issue_tr);
                     }
                     else if constexpr (NQ2 > 0) {
                         const double2 * gp2 = args.G2 + (size_t)p * g_patch2 + e;
@@ -783,6 +1066,8 @@
                     }
                     named_arrive(READY + i % NBUF, 256);
                 }
+                if (NF > 1)
+                    cluster_wait();
             }
         }
 

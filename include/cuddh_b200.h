@@ -139,7 +139,8 @@ int64_t cuddh_b200_operator_bytes(cuddh_operator_t op);
 int64_t cuddh_b200_operator_bytes_moved(cuddh_operator_t op);
 int cuddh_b200_operator_is_affine(cuddh_operator_t op);
 /* which kernel family serves this handle: 0 = lane-per-row patch kernel / generic, 1 = warp-specialised thread-per-element
- * kernel (n_basis <= 5), 2 = Helmholtz handle on the fused S - w^2 M path; -1 = not a volume operator */
+ * kernel (n_basis <= 5), 2 = Helmholtz handle on the fused S - w^2 M path, 3 = warp-specialised thread-pair-per-element kernel
+ * (n_basis 6-9); -1 = not a volume operator */
 int cuddh_b200_operator_kernel_kind(cuddh_operator_t op);
 
 /* ---- linalg: include/linalg.hpp:16-54 (double and float) ---------------------------------------- */

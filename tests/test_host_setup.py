@@ -2,6 +2,7 @@
 golden fixtures from the reference and against the oracle; and the ABI itself (every symbol the header
 declares is exported)."""
 import ctypes
+import os
 import re
 
 import numpy as np
@@ -342,3 +343,13 @@ def test_assembly_plan_hashes_pinned():
         assert fem.check_plan(int(k))["hash"] == h, key
         checked += 1
     assert checked >= 40
+
+
+def test_thread_pair_algebra_matches_direct_formulas():
+    """host replay of the mirrored-frame thread-pair split of volume_action_pair (csrc/volume_pair.cuh) against the direct
+    sum-factorised formulas of source/StiffnessMatrix.cpp:132-182 / source/MassMatrix.cpp:170-205, every (n_basis, n_quad) rule"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("check_pair_algebra", os.path.join(os.path.dirname(__file__), "..", "scripts", "check_pair_algebra.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.main() < 1e-13
