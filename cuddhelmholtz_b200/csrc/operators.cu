@@ -1379,7 +1379,8 @@ namespace cb200
                 return &launch_ws<5, 6, true, 9, 2>;
             if (nb == 5 && nqs == 6 && nqm == 9 && ring == 5)
                 return &launch_ws<5, 6, true, 9, 5>;
-            static const int ring4 = env_int("CUDDH_B200_RING4", 5);
+            // n_basis 4: per-thread chunk ring (measured 0.437 -> 0.388 ms; at n_basis 5 the two rings tie, 0.720 / 0.717 ms)
+            static const int ring4 = env_int("CUDDH_B200_RING4F", -5);
             if (nb == 4 && nqs == 5 && nqm == 8 && ring4 == -5)
                 return &launch_ws<4, 5, true, 8, -5>;
             if (nb == 4 && nqs == 5 && nqm == 8 && ring4 == 2)

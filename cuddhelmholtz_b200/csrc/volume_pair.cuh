@@ -74,6 +74,10 @@
             constexpr int NI = (NB - 2) * (NB - 2);             // element-interior nodes
             constexpr size_t g_patch = (size_t)NQ * NPR * Cfg::NT; // double2 per patch
             constexpr int FULL = 1, READY = 4, HELPER = 7;      // named barrier ids
+            // U (own columns) in registers for all rows where the register file allows it; otherwise re-read from the patch buffer
+            // every row (ncu at n_basis 8: the compute warps then sit on the MIO queue / short scoreboard - LDS + SHFL - 45 % of the time)
+            // (measured at 1024^2: n_basis 6 stiffness 0.371 -> 0.355 ms; the n_basis 8 mass kernel fits but loses, 0.94 -> 0.995 ms)
+            constexpr bool UREG = NB <= 6;
             static_assert(!AFFINE || STIFF, "AFFINE is a property of the stiffness operator");
             static_assert(NB >= 3, "pair kernel: n_basis >= 3");
 
@@ -284,6 +288,14 @@
                     for (int k = 0; k < NB * JA; ++k)
                         out[k] = 0.0;
                     const double * bc = b + col0;
+                    double U[UREG ? NB * JA : 1];
+                    if constexpr (UREG) {
+#pragma unroll
+                        for (int jj = 0; jj < JA; ++jj)
+#pragma unroll
+                            for (int ii = 0; ii < NB; ++ii)
+                                U[ii + NB * jj] = bc[jj * cstep + ii * PE];
+                    }
 #pragma unroll 1
                     for (int tx = 0; tx < NQ; ++tx) {
                         const int z = tx * zero; // 0 at run time; keeps the tt-indexed table loads inside the rolled loop
@@ -294,7 +306,11 @@
                             double s0 = 0.0, s1 = 0.0;
 #pragma unroll
                             for (int ii = 0; ii < NB; ++ii) {
-                                const double u = bc[jj * cstep + ii * PE];
+                                double u;
+                                if constexpr (UREG)
+                                    u = U[ii + NB * jj];
+                                else
+                                    u = bc[jj * cstep + ii * PE];
                                 s0 = fma(tab.Prow[tx][ii], u, s0);
                                 if (STIFF)
                                     s1 = fma(tab.Drow[tx][ii], u, s1);

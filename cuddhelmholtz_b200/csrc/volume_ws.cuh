@@ -618,6 +618,11 @@
 
             // shared-memory metric ring (RING > 0): chunk = CHUNK_PAIRS x PE 16-byte pairs
             constexpr int CP1 = ring_cp(NPR1), CP2 = NQ2 > 0 ? ring_cp(NPR2) : 0;
+            // fused instances: split cluster barrier (the CTAs of a pair may drift by one patch) for the per-thread rings, lockstep
+            // for the TMA rings (measured 0.61 -> 0.81 ms with the split barrier there: the second CTA outruns the first one's L2
+            // prefetches). Compile-time on purpose: a run-time choice between the two aligned barrier forms costs ptxas the
+            // uniformity of the row loops (table loads fall from LDCU to LDC: 0.72 -> 1.17 ms on the stored-metric instance).
+            constexpr bool CSPLIT = RING < 0;
             constexpr bool TRM = RING < 0 && AFFINE && NQ2 > 0; // per-thread ring of whole mass rows (contract_mass_tring)
             constexpr bool TRG = RING < 0 && !TRM;              // per-thread ring of chunks, any phase (contract_phase_ring<TR>)
             constexpr int CHUNK_PAIRS = TRM ? NPR2 : (CP1 > CP2 ? CP1 : CP2);
@@ -794,10 +799,14 @@
                 named_sync(HELPER, 128);
                 named_arrive(FULL + 0, 256);
                 for (int i = 0; i < n_iter; ++i) {
-                    if (NF > 1) { // the CTAs of a pair stay within one patch of each other (split cluster barrier)
-                        if (i > 0)
-                            cluster_wait();
-                        cluster_arrive();
+                    if (NF > 1) { // the CTAs of a pair stay within one patch of each other (split cluster barrier) or in lockstep
+                        if constexpr (!CSPLIT)
+                            cluster_sync_all();
+                        else {
+                            if (i > 0)
+                                cluster_wait();
+                            cluster_arrive();
+                        }
                     }
                     if (NBUF >= 3 && i + 1 < n_iter)
                         issue_gather(i + 1);
@@ -817,7 +826,7 @@
                 }
                 named_sync(READY + (n_iter - 1) % NBUF, 256);
                 assemble(n_iter - 1);
-                if (NF > 1)
+                if (CSPLIT && NF > 1)
                     cluster_wait();
             }
             else {
@@ -960,9 +969,13 @@
                     // first phase of the next patch of this CTA (at the very end this one again: a harmless reload)
                     const int pn = (i + 1 < n_iter) ? p + stride : p;
                     if (NF > 1) {
-                        if (i > 0)
-                            cluster_wait();
-                        cluster_arrive();
+                        if constexpr (!CSPLIT)
+                            cluster_sync_all();
+                        else {
+                            if (i > 0)
+                                cluster_wait();
+                            cluster_arrive();
+                        }
                     }
                     const double2 * gp1 = args.G1 + (size_t)p * g_patch1 + e;
                     const double2 * gp1_next = args.G1 + (size_t)pn * g_patch1 + e;
@@ -1066,7 +1079,7 @@
                     }
                     named_arrive(READY + i % NBUF, 256);
                 }
-                if (NF > 1)
+                if (CSPLIT && NF > 1)
                     cluster_wait();
             }
         }

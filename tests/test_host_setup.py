@@ -353,3 +353,37 @@ def test_thread_pair_algebra_matches_direct_formulas():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.main() < 1e-13
+
+
+def test_sass_table_operands_stay_uniform():
+    """SASS of the built library: in the compute branch (after USETMAXREG.TRY_ALLOC) of every warp-specialised volume kernel the 1-D
+    table operands must come through the uniform datapath (LDCU), not through per-thread constant loads (LDC): a change that costs
+    ptxas the uniformity of the quadrature-row loop (seen once with a run-time choice between two aligned cluster-barrier forms)
+    turns ~200 LDCU.64 into LDC.64, spills, and slows the kernel by 30-60 % without changing a single result."""
+    import shutil, subprocess
+    so = os.path.join(os.path.dirname(cb.__file__), "lib", "libcuddh_b200.so")
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe) or not os.path.exists(so):
+        pytest.skip("cuobjdump or the built library is not available")
+    text = subprocess.run([exe, "-sass", so], capture_output=True, text=True, timeout=600).stdout
+    # the default instances behind the bench numbers: fused Helmholtz (affine / stored metric) n_basis 5 and 4, stand-alone
+    # stiffness / weighted mass n_basis 5, thread-pair kernels n_basis 8
+    wanted = ["volume_action_wsILi5ELi6ELb1ELi9ELin4ELb1E", "volume_action_wsILi4ELi5ELb1ELi8ELin4ELb1E", "volume_action_wsILi5ELi6ELb1ELi9ELi5ELb0E",
+              "volume_action_wsILi4ELi5ELb1ELi8ELin5ELb0E", "volume_action_wsILi5ELi6ELb1ELi0ELi0ELb1E", "volume_action_wsILi5ELi6ELb1ELi0ELi5ELb0E",
+              "volume_action_wsILi5ELi9ELb0ELi0ELi5ELb0E", "volume_action_pairILi8ELi9ELb1ELb1E", "volume_action_pairILi8ELi9ELb1ELb0E",
+              "volume_action_pairILi8ELi14ELb0ELb0E"]
+    checked = set()
+    for block in text.split("Function : ")[1:]:
+        name = block.split("\n", 1)[0]
+        key = next((w for w in wanted if w in name), None)
+        if key is None:
+            continue
+        assert "USETMAXREG.TRY_ALLOC" in block, name
+        compute = block.split("USETMAXREG.TRY_ALLOC", 1)[1]
+        n_dfma = len(re.findall(r"\bDFMA\b", compute))
+        n_ldc = len(re.findall(r"\bLDC\.64\b", compute))
+        n_ldcu = len(re.findall(r"\bLDCU\.(?:64|128)\b", compute))
+        n_spill = len(re.findall(r"\bSTL\b", compute))
+        assert n_dfma >= 140 and n_ldc <= 32 and n_ldcu >= n_dfma // 4 and n_spill <= 4, (name, n_dfma, n_ldc, n_ldcu, n_spill)
+        checked.add(key)
+    assert checked == set(wanted), sorted(set(wanted) - checked)
