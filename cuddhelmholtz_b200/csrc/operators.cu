@@ -64,6 +64,8 @@ namespace cb200
             // rows scaled by the quadrature weight, PWrow[q][k] = w_q P(q,k): back-contractions of the affine stiffness phase
             double PWrow[STIFF ? NQ : 1][NBP];
             double DWrow[STIFF ? NQ : 1][NBP];
+            // mass: msc * P(q,k), the phase scale (1, or -omega^2 inside the Helmholtz composite) folded into the last back-contraction
+            double PSrow[STIFF ? 1 : NQ][NBP];
         };
 
         // Padded layout of the per-element transpose scratch: element stride S, row stride RS, offset HALF of the second
@@ -1090,11 +1092,13 @@ namespace cb200
         }
 
         template <int NB, int NQ, bool STIFF>
-        void fill_tables(Tables<NB, NQ, STIFF> & tab, const VolumeOp & op)
+        void fill_tables(Tables<NB, NQ, STIFF> & tab, const VolumeOp & op, const double msc = 1.0)
         {
             std::memset(&tab, 0, sizeof(tab));
             for (int q = 0; q < NQ; ++q)
                 for (int k = 0; k < NB; ++k) {
+                    if (!STIFF)
+                        tab.PSrow[q][k] = msc * op.P[q + NQ * k];
                     tab.Prow[q][k] = op.P[q + NQ * k];
                     tab.Pcol[k][q] = op.P[q + NQ * k];
                     if (STIFF) {
@@ -1125,7 +1129,7 @@ namespace cb200
             typename Phase2<NB, NQ2>::type tab2;
             std::memset(&tab2, 0, sizeof(tab2));
             if constexpr (NQ2 > 0)
-                fill_tables(tab2, *op2);
+                fill_tables(tab2, *op2, args.msc);
             auto kern = volume_action_ws<NB, NQ, STIFF, NQ2, RING, AFFINE>;
             // one wave of resident CTAs, cached per device (function attributes are per device too)
             static int grid_of_device[MAX_DEVICES] = {};
@@ -1204,13 +1208,27 @@ namespace cb200
         }
 
         // thread-pair-per-element kernel (volume_pair.cuh): n_basis 6-9
+        // depth of the per-thread metric ring of a thread-pair instance: the (short-row) mass operator where two CTAs per SM still
+        // fit with 3 rows of ring; 0 = registers, one row ahead
+        template <int NB, int NQ, bool STIFF, bool AFFINE>
+        constexpr int pair_ring_depth()
+        {
+            if (STIFF || AFFINE)
+                return 0;
+            constexpr int NI = (NB - 2) * (NB - 2), TA = (NQ + 1) / 2, NPR = ((TA + 1) & ~1) / 2;
+            constexpr size_t base = sizeof(double) * 2 * (size_t)NB * NB * 64 + sizeof(int) * 2 * (size_t)NI * 64 + 16;
+            return (base + 3 * (size_t)NPR * 128 * 16 + 1024) * 2 <= 233472 ? 3 : 0;
+        }
+
         template <int NB, int NQ, bool STIFF, bool AFFINE = false>
         void launch_volume_pair(VolumeOp & op, const PlanDev & pd, const Plan & plan, double c, int accumulate, const double * x, double * y,
                                 cudaStream_t s)
         {
             CB_REQUIRE(plan.PE == 64, "thread-pair kernel: patches must hold 64 elements");
             constexpr int NI = (NB - 2) * (NB - 2);
-            const size_t smem = sizeof(double) * 2 * (size_t)NB * NB * 64 + sizeof(int) * 2 * (size_t)NI * 64 + 16;
+            constexpr int RD = pair_ring_depth<NB, NQ, STIFF, AFFINE>();
+            constexpr int NPR = PairCfg<NB, NQ, STIFF>::NPR;
+            const size_t smem = sizeof(double) * 2 * (size_t)NB * NB * 64 + sizeof(int) * 2 * (size_t)NI * 64 + (size_t)RD * NPR * 128 * 16 + 16;
             PairTables<NB, NQ, STIFF> tab;
             std::memset(&tab, 0, sizeof(tab));
             for (int q = 0; q < NQ; ++q)
@@ -1224,7 +1242,7 @@ namespace cb200
                         }
                     }
                 }
-            auto kern = volume_action_pair<NB, NQ, STIFF, AFFINE>;
+            auto kern = volume_action_pair<NB, NQ, STIFF, AFFINE, RD>;
             static int grid_of_device[MAX_DEVICES] = {};
             int dev = 0;
             cudaGetDevice(&dev);
@@ -1357,12 +1375,12 @@ namespace cb200
         {
             if (affine) {
                 // mass rows through the shared-memory ring (5) or straight from global memory into registers (0)
-                static const int aring = env_int("CUDDH_B200_AFFINE_RING", -4);
+                static const int aring = env_int("CUDDH_B200_AFFINE_RING", -5);
                 // (negative: per-thread cp.async ring of that many rows)
                 if (nb == 5 && nqs == 6 && nqm == 9)
                     return aring == 0 ? &launch_ws<5, 6, true, 9, 0, true> : aring == -3 ? &launch_ws<5, 6, true, 9, -3, true>
-                         : aring == -5 ? &launch_ws<5, 6, true, 9, -5, true> : aring == 5 ? &launch_ws<5, 6, true, 9, 5, true>
-                         : &launch_ws<5, 6, true, 9, -4, true>;
+                         : aring == -4 ? &launch_ws<5, 6, true, 9, -4, true> : aring == 5 ? &launch_ws<5, 6, true, 9, 5, true>
+                         : &launch_ws<5, 6, true, 9, -5, true>;
                 if (nb == 4 && nqs == 5 && nqm == 8)
                     return aring == 0 ? &launch_ws<4, 5, true, 8, 0, true> : aring == 5 ? &launch_ws<4, 5, true, 8, 5, true>
                          : &launch_ws<4, 5, true, 8, -4, true>;

@@ -61,7 +61,11 @@
             int accumulate, n_patches, zero;
         };
 
-        template <int NB, int NQ, bool STIFF, bool AFFINE>
+        // RD > 0: the metric rows come through a PER-THREAD shared-memory ring of RD rows (16-byte cp.async of the thread's own
+        // pairs, cp.async.wait_group, no barrier - as contract_mass_tring in volume_ws.cuh) instead of through registers one row
+        // ahead: the rows of the mass operator are short (176 DFMA per thread at n_basis 8), one row of lead does not cover an
+        // L2 / DRAM round trip (ncu: 3.8 long-scoreboard warps per issued instruction).
+        template <int NB, int NQ, bool STIFF, bool AFFINE, int RD = 0>
         __global__ void __launch_bounds__(256, 2)
         volume_action_pair(const __grid_constant__ PairTables<NB, NQ, STIFF> tab, const PlanDev plan, const __grid_constant__ PairArgs args)
         {
@@ -76,14 +80,17 @@
             constexpr int FULL = 1, READY = 4, HELPER = 7;      // named barrier ids
             // U (own columns) in registers for all rows where the register file allows it; otherwise re-read from the patch buffer
             // every row (ncu at n_basis 8: the compute warps then sit on the MIO queue / short scoreboard - LDS + SHFL - 45 % of the time)
-            // (measured at 1024^2: n_basis 6 stiffness 0.371 -> 0.355 ms; the n_basis 8 mass kernel fits but loses, 0.94 -> 0.995 ms)
-            constexpr bool UREG = NB <= 6;
+            // (measured at 1024^2: n_basis 6 stiffness 0.371 -> 0.355 ms; the mass kernels gain only together with the metric ring)
+            constexpr bool UREG = STIFF ? (NB <= 6) : (NB <= 8 && RD > 0);
             static_assert(!AFFINE || STIFF, "AFFINE is a property of the stiffness operator");
             static_assert(NB >= 3, "pair kernel: n_basis >= 3");
 
             extern __shared__ __align__(16) unsigned char smem_raw[];
             double * bufs = reinterpret_cast<double *>(smem_raw);     // [NBUF][NB2][PE]
             int * gints = reinterpret_cast<int *>(bufs + NBUF * BUF); // [NBUF][NI][PE] global DOFs of the element-interior nodes
+            double2 * mring = reinterpret_cast<double2 *>(gints + NBUF * NI * PE); // [RD][NPR][128] per-thread metric ring
+            static_assert(RD == 0 || !AFFINE, "the metric ring serves the stored-metric instances");
+            static_assert((NBUF * NI * PE) % 4 == 0, "ring alignment");
 
             const int wg = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 7), 0);
             const int t = threadIdx.x & 127;
@@ -259,7 +266,35 @@
                 const int zero = args.zero;
 
                 double g[AFFINE ? 2 : KR]; // metric values of the current quadrature row (stored-metric instances)
-                if constexpr (!AFFINE) {
+                // per-thread ring: running source pointer (rows of a patch are contiguous), patch skip, ring address - in registers
+                const double2 * tr_src = args.G + (size_t)cta * g_patch + t;
+                int tr_skip = (stride - 1) * (int)g_patch, tr_i = 0, tr_r = 0, tr_slot = 0;
+                unsigned tr_dst = (unsigned)__cvta_generic_to_shared(mring + t);
+                if constexpr (RD > 0)
+                    asm volatile("" : "+l"(tr_src), "+r"(tr_skip), "+r"(tr_dst));
+                auto tr_request = [&](const int slot) {
+                    if (tr_i < n_iter) {
+                        const unsigned dst = tr_dst + (unsigned)slot * (unsigned)(NPR * Cfg::NT * sizeof(double2));
+#pragma unroll
+                        for (int m = 0; m < NPR; ++m)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (unsigned)(m * Cfg::NT * sizeof(double2))),
+                                         "l"(tr_src + m * Cfg::NT)
+                                         : "memory");
+                        tr_src += NPR * Cfg::NT;
+                        if (++tr_r == NQ) {
+                            tr_r = 0;
+                            ++tr_i;
+                            tr_src += tr_skip;
+                        }
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                };
+                if constexpr (RD > 0) {
+#pragma unroll
+                    for (int k = 0; k < RD; ++k)
+                        tr_request(k);
+                }
+                if constexpr (!AFFINE && RD == 0) {
                     const double2 * gp0 = args.G + (size_t)cta * g_patch + t;
 #pragma unroll
                     for (int m = 0; m < NPR; ++m) {
@@ -341,6 +376,16 @@
                                 a1o[q] = a1n[q] = 0.0;
                         }
                         const double2 * gnext = (tx + 1 < NQ) ? gp + (size_t)(tx + 1) * (NPR * Cfg::NT) : gp_next;
+                        if constexpr (RD > 0) { // this row's pairs out of the ring (the oldest of the RD groups in flight)
+                            asm volatile("cp.async.wait_group %0;" ::"n"(RD - 1) : "memory");
+                            const double2 * src = mring + (size_t)tr_slot * (NPR * Cfg::NT) + t;
+#pragma unroll
+                            for (int m = 0; m < NPR; ++m) {
+                                const double2 v = src[m * Cfg::NT];
+                                g[2 * m] = v.x;
+                                g[2 * m + 1] = v.y;
+                            }
+                        }
 #pragma unroll
                         for (int tt = 0; tt < TA; ++tt) {
                             const bool dead = (NQ % 2) && tt == TA - 1 && mirrored; // the middle quadrature column belongs to thread 0
@@ -401,7 +446,7 @@
                                 }
                             }
                             // metric pairs that are no longer needed: fetch the same pairs of the next row (or of the next patch)
-                            if constexpr (!AFFINE) {
+                            if constexpr (!AFFINE && RD == 0) {
 #pragma unroll
                                 for (int m = pairs_done<TA, NKI, KR>(tt - 1); m < pairs_done<TA, NKI, KR>(tt); ++m) {
                                     const double2 v = ld_metric_pair(gnext + m * Cfg::NT);
@@ -409,6 +454,11 @@
                                     g[2 * m + 1] = v.y;
                                 }
                             }
+                        }
+                        if constexpr (RD > 0) { // the row's values have been consumed: refill its slot with the row RD further on
+                            tr_request(tr_slot);
+                            if (++tr_slot == RD)
+                                tr_slot = 0;
                         }
                         // ---- 4b. the partner's share of the own output columns ----
 #pragma unroll

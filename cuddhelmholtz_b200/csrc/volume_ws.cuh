@@ -80,7 +80,8 @@
         // (conflict-free, element-fastest) and accumulates into out[]. The metric values of two rows (even / odd) sit in g0 / g1;
         // every 16-byte pair is replaced, as soon as it has been used, by the pair of the NEXT ROW OF THE SAME PARITY: row
         // tx + 2 of this phase, or row (tx & 1) of the phase that follows (gp_next, NPN pairs per row) - two row iterations
-        // ahead of its use. Mass values are scaled by msc (Helmholtz: -omega^2).
+        // ahead of its use. The scale msc of a mass phase (Helmholtz: -omega^2) is folded into the table of its last back-contraction
+        // (Tables::PSrow = msc * P): one DMUL per quadrature point less than scaling the metric value.
         template <int NB, int NQ, bool STIFF, int GK, int NPN, int PE>
         __device__ __forceinline__ void contract_phase(const Tables<NB, NQ, STIFF> & tab, const double * b, double (&g0)[GK], double (&g1)[GK],
                                                        const double2 * gp, const double2 * gp_next, double (&out)[NB * NB],
@@ -156,7 +157,7 @@
 #pragma unroll
                         for (int l = 0; l < NB; ++l)
                             ppu = fma(tab.Prow[ty + z][l], pu[l], ppu);
-                        const double val = (g[ty] * msc) * ppu;
+                        const double val = g[ty] * ppu; // the phase scale msc sits in PSrow
 #pragma unroll
                         for (int q = 0; q < NB; ++q)
                             a0[q] = fma(tab.Prow[ty + z][q], val, a0[q]);
@@ -176,7 +177,7 @@
                         if (STIFF)
                             out[ii + NB * q] = fma(tab.Drow[tx][ii], a0[q], fma(tab.Prow[tx][ii], a1[q], out[ii + NB * q]));
                         else
-                            out[ii + NB * q] = fma(tab.Prow[tx][ii], a0[q], out[ii + NB * q]);
+                            out[ii + NB * q] = fma(tab.PSrow[tx][ii], a0[q], out[ii + NB * q]);
                     }
             };
 #pragma unroll 1
@@ -305,7 +306,7 @@
 #pragma unroll
                         for (int l = 0; l < NB; ++l)
                             ppu = fma(tab.Prow[ty + z][l], pu[l], ppu);
-                        const double val = (g[ty] * msc) * ppu;
+                        const double val = g[ty] * ppu; // the phase scale msc sits in PSrow
 #pragma unroll
                         for (int q = 0; q < NB; ++q)
                             a0[q] = fma(tab.Prow[ty + z][q], val, a0[q]);
@@ -318,7 +319,7 @@
                         if (STIFF)
                             out[ii + NB * q] = fma(tab.Drow[tx][ii], a0[q], fma(tab.Prow[tx][ii], a1[q], out[ii + NB * q]));
                         else
-                            out[ii + NB * q] = fma(tab.Prow[tx][ii], a0[q], out[ii + NB * q]);
+                            out[ii + NB * q] = fma(tab.PSrow[tx][ii], a0[q], out[ii + NB * q]);
                     }
             };
 #pragma unroll 1
@@ -471,7 +472,7 @@
 #pragma unroll
                     for (int l = 0; l < NB; ++l)
                         ppu = fma(tab.Prow[ty + z][l], pu[l], ppu);
-                    const double val = (g[ty] * msc) * ppu;
+                    const double val = g[ty] * ppu; // the phase scale msc sits in PSrow
 #pragma unroll
                     for (int q = 0; q < NB; ++q)
                         a0[q] = fma(tab.Prow[ty + z][q], val, a0[q]);
@@ -487,7 +488,7 @@
                 for (int q = 0; q < NB; ++q)
 #pragma unroll
                     for (int ii = 0; ii < NB; ++ii)
-                        out[ii + NB * q] = fma(tab.Prow[tx][ii], a0[q], out[ii + NB * q]);
+                        out[ii + NB * q] = fma(tab.PSrow[tx][ii], a0[q], out[ii + NB * q]);
             };
 #pragma unroll 1
             for (int tx = 0; tx < NQ; tx += 2) {
@@ -550,7 +551,7 @@
 #pragma unroll
                     for (int l = 0; l < NB; ++l)
                         ppu = fma(tab.Prow[ty + z][l], pu[l], ppu);
-                    const double val = (g[ty] * msc) * ppu;
+                    const double val = g[ty] * ppu; // the phase scale msc sits in PSrow
 #pragma unroll
                     for (int q = 0; q < NB; ++q)
                         a0[q] = fma(tab.Prow[ty + z][q], val, a0[q]);
@@ -563,7 +564,7 @@
                 for (int q = 0; q < NB; ++q)
 #pragma unroll
                     for (int ii = 0; ii < NB; ++ii)
-                        out[ii + NB * q] = fma(tab.Prow[tx][ii], a0[q], out[ii + NB * q]);
+                        out[ii + NB * q] = fma(tab.PSrow[tx][ii], a0[q], out[ii + NB * q]);
             }
         }
 
