@@ -639,6 +639,10 @@ def extras(args, cb, torch, slab, x, y):
         out["n_basis_8"] = high_order_ops(cb, torch, args.nx, 8, peak)
     except Exception as e:
         out["n_basis_8"] = "failed: %r" % (e,)
+    try:
+        out["n_basis_9"] = high_order_ops(cb, torch, args.nx, 9, peak)
+    except Exception as e:
+        out["n_basis_9"] = "failed: %r" % (e,)
     try:  # BASELINE configs[4] order on one GPU: n_basis 8 DDH action, the reference's block 16 and the config's block 32
         out["ddh_n_basis_8"] = ddh_high_order(cb, torch, drv if os.path.exists(drv) else None)
     except Exception as e:
@@ -661,15 +665,27 @@ def high_order_ops(cb, torch, nx, nb, peak):
     xx = torch.rand(n, dtype=torch.float64, device="cuda") - 0.5
     yy = torch.empty_like(xx)
     aa = torch.rand(n, dtype=torch.float64, device="cuda") + 0.5
-    res = {"ndof": n, "nx": nx}
-    for name, mk in (("stiffness", lambda: cb.StiffnessMatrix(fem)), ("mass_weighted", lambda: cb.MassMatrix(aa, fem))):
+    res = {"ndof": n, "nx": nx, "kernel": "volume_action_pair (thread pair per element, kernel_kind 3)",
+           "hbm_frac_patch_kernel": "SURVEY 8(d) bytes of the reference's stored-metric formulation / patch-kernel time / measured HBM peak"}
+
+    def one(mk):
         op = mk()
         op.action(xx, yy)
         pms, sms = op.time_phases(xx, yy, 10)
-        res[name] = {"ms": pms + sms, "gdofs": n / ((pms + sms) * 1e-3) / 1e9, "kernel_kind": op.kernel_kind(),
-                     "hbm_frac_patch_kernel": op.algorithmic_bytes() / (pms * 1e-3) / 1e9 / peak}
+        r = {"ms": pms + sms, "kernel_ms": pms, "gdofs": n / ((pms + sms) * 1e-3) / 1e9, "kernel_kind": op.kernel_kind(),
+             "affine": op.is_affine(), "hbm_frac_patch_kernel": op.algorithmic_bytes() / (pms * 1e-3) / 1e9 / peak}
         del op
         torch.cuda.empty_cache()
+        return r
+
+    res["stiffness"] = one(lambda: cb.StiffnessMatrix(fem))
+    if res["stiffness"]["affine"] and "CUDDH_B200_AFFINE" not in os.environ:  # the stored-metric instance on the same data
+        os.environ["CUDDH_B200_AFFINE"] = "0"
+        try:
+            res["stiffness_stored_metric"] = one(lambda: cb.StiffnessMatrix(fem))
+        finally:
+            del os.environ["CUDDH_B200_AFFINE"]
+    res["mass_weighted"] = one(lambda: cb.MassMatrix(aa, fem))
     return res
 
 

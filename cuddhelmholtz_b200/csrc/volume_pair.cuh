@@ -81,7 +81,8 @@
             // U (own columns) in registers for all rows where the register file allows it; otherwise re-read from the patch buffer
             // every row (ncu at n_basis 8: the compute warps then sit on the MIO queue / short scoreboard - LDS + SHFL - 45 % of the time)
             // (measured at 1024^2: n_basis 6 stiffness 0.371 -> 0.355 ms; the mass kernels gain only together with the metric ring)
-            constexpr bool UREG = STIFF ? (NB <= 6) : (NB <= 8 && RD > 0);
+            constexpr bool ILP2 = STIFF && AFFINE && NB >= 7 && NB <= 8;
+            constexpr bool UREG = STIFF ? (NB <= 6 || ILP2) : (NB <= 8 && RD > 0);
             static_assert(!AFFINE || STIFF, "AFFINE is a property of the stiffness operator");
             static_assert(NB >= 3, "pair kernel: n_basis >= 3");
 
@@ -386,20 +387,49 @@
                                 g[2 * m + 1] = v.y;
                             }
                         }
+                        // ILP2 (affine stiffness): all second-index sums first - pu / du are dead before the back-contraction accumulators
+                        // come alive, which is what lets U stay in registers at n_basis 8 (for the stored-metric and mass instances the
+                        // same order cost ptxas the uniform table loads, LDCU -> LDC, and was slower: 0.94 -> 1.32 ms)
+                        double DxA[ILP2 ? TA : 1], DyA[ILP2 ? TA : 1];
+                        if constexpr (ILP2) {
+#pragma unroll
+                            for (int tt = 0; tt < TA; ++tt)
+                                DxA[tt] = DyA[tt] = 0.0;
+#pragma unroll
+                            for (int jj = 0; jj < JA; ++jj)
+#pragma unroll
+                                for (int tt = 0; tt < TA; ++tt) {
+                                    DxA[tt] = fma(tab.Prow[tt + z][jj], du[jj], DxA[tt]);
+                                    DyA[tt] = fma(tab.Drow[tt + z][jj], pu[jj], DyA[tt]);
+                                }
+#pragma unroll
+                            for (int jj = 0; jj < JA; ++jj)
+#pragma unroll
+                                for (int tt = 0; tt < TA; ++tt) {
+                                    DxA[tt] = fma(tab.Prow[tt + z][NB - 1 - jj], duo[jj], DxA[tt]);
+                                    DyA[tt] = fma(tab.Drow[tt + z][NB - 1 - jj], puo[jj], DyA[tt]);
+                                }
+                        }
 #pragma unroll
                         for (int tt = 0; tt < TA; ++tt) {
                             const bool dead = (NQ % 2) && tt == TA - 1 && mirrored; // the middle quadrature column belongs to thread 0
                             if (STIFF) {
                                 double Dx = 0.0, Dy = 0.0;
-#pragma unroll
-                                for (int jj = 0; jj < JA; ++jj) {
-                                    Dx = fma(tab.Prow[tt + z][jj], du[jj], Dx);
-                                    Dy = fma(tab.Drow[tt + z][jj], pu[jj], Dy);
+                                if constexpr (ILP2) {
+                                    Dx = DxA[tt];
+                                    Dy = DyA[tt];
                                 }
+                                else {
 #pragma unroll
-                                for (int jj = 0; jj < JA; ++jj) {
-                                    Dx = fma(tab.Prow[tt + z][NB - 1 - jj], duo[jj], Dx);
-                                    Dy = fma(tab.Drow[tt + z][NB - 1 - jj], puo[jj], Dy);
+                                    for (int jj = 0; jj < JA; ++jj) {
+                                        Dx = fma(tab.Prow[tt + z][jj], du[jj], Dx);
+                                        Dy = fma(tab.Drow[tt + z][jj], pu[jj], Dy);
+                                    }
+#pragma unroll
+                                    for (int jj = 0; jj < JA; ++jj) {
+                                        Dx = fma(tab.Prow[tt + z][NB - 1 - jj], duo[jj], Dx);
+                                        Dy = fma(tab.Drow[tt + z][NB - 1 - jj], puo[jj], Dy);
+                                    }
                                 }
                                 double F0, F1;
                                 if constexpr (AFFINE) {
