@@ -1287,6 +1287,10 @@ namespace cb200
         }                                                                                                              \
         return &launch_volume_pair<NB_, NQ_, STIFF, false>;                                                            \
     }
+            // the stored-metric stiffness at n_basis 9 spills its result tile in this kernel (2.73 ms at 1024^2 against 2.11 ms of the
+            // lane-per-row kernel): only the affine instance is offered there
+            if (STIFF && nb == 9 && !affine)
+                return nullptr;
             // default rules nq = nb + 1 (reference StiffnessMatrix.cpp:45, MassMatrix.cpp:74)
             CB_CASE(6, 7) CB_CASE(7, 8) CB_CASE(8, 9) CB_CASE(9, 10)
             if constexpr (!STIFF) { // weighted mass: nq = 1 + 3nb/2 + 1 (MassMatrix.cpp:108)
@@ -1480,10 +1484,11 @@ namespace cb200
             op.nk = (stiff ? 3 : 1) * nq;
             op.affine = want_affine && stiff && op.tpe && find_affine_instance(op.nb, nq) != nullptr && env_int("CUDDH_B200_AFFINE", 1) != 0 &&
                         fem->all_affine();
-            LaunchFn fp = stiff ? find_pair_instance<true>(op.nb, nq) : find_pair_instance<false>(op.nb, nq);
+            const bool pair_affine = want_affine && stiff && env_int("CUDDH_B200_AFFINE", 1) != 0 && op.nb >= 6 && fem->all_affine();
+            LaunchFn fp = stiff ? find_pair_instance<true>(op.nb, nq, pair_affine) : find_pair_instance<false>(op.nb, nq);
             op.pair = !op.generic && !op.tpe && fp != nullptr && env_int("CUDDH_B200_PAIR", 1) != 0;
             if (op.pair) { // thread-pair layout: [row][pair of metric values][thread slot], see volume_action_pair / metric_index_pair
-                op.affine = want_affine && stiff && env_int("CUDDH_B200_AFFINE", 1) != 0 && fem->all_affine();
+                op.affine = pair_affine;
                 op.plan = &fem->get_plan_tpe();
                 CB_REQUIRE(op.plan->PE == 64, "thread-pair kernel: the node-major plan must have 64-element patches");
                 op.epw = -1;

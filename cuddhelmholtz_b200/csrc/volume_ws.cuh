@@ -871,14 +871,17 @@
                 // per-thread ring of chunks (TRG): the same cursor, advanced by every thread; one cp.async group per chunk (an empty
                 // group once the stream is exhausted, so that wait_group keeps counting chunks)
                 unsigned trg_dst = smem_u32(ring + e);
+                // the element slot as an opaque register for the requests: ptxas otherwise rebuilds it from SR_TID (an S2R round trip) at
+                // every request. Only here: the same trick applied to `e` everywhere costs the default instances 1 % (register allocation).
+                int e_op = e;
                 if constexpr (TRG)
-                    asm volatile("" : "+r"(trg_dst));
+                    asm volatile("" : "+r"(trg_dst), "+r"(e_op));
                 auto issue_tr = [&](const int slot) {
                     if (cur_i < n_iter) {
                         const int p = cta + cur_i * stride;
                         const int npr = cur_ph == 0 ? NPR1 : NPR2, cp = cur_ph == 0 ? CP1 : CP2;
                         const double2 * src = (cur_ph == 0 ? args.G1 + (size_t)p * g_patch1 : args.G2 + (size_t)p * g_patch2) +
-                                              (size_t)(cur_r * npr + cur_h * cp) * PE + e;
+                                              (size_t)(cur_r * npr + cur_h * cp) * PE + e_op;
                         const int pairs = min(cp, npr - cur_h * cp);
                         const unsigned dst = trg_dst + (unsigned)slot * (unsigned)(CHUNK_PAIRS * PE * sizeof(double2));
 #pragma unroll
