@@ -95,43 +95,63 @@ namespace cb200
         }
 
         tm.lap("ensemble elems+faces");
-        // subspace DOF numbering: first touch over (el, j, i) (:142-175)
+        // subspace DOF numbering: first touch over (el, j, i) (:142-175). The subspaces are independent: one thread per range of
+        // subspaces, each with a small open-addressing table global DOF -> local id (a subspace touches at most mx_elems * nb^2
+        // DOFs) instead of one ndof-sized scratch array walked serially.
         sI.assign((size_t)nb2 * mx_elems * n_spaces, -1);
         s_dof.assign(n_spaces, 0);
-        std::vector<int> local((size_t)fem.ndof, -1);
         std::vector<std::vector<int>> s2g(n_spaces);
-        for (int p = 0; p < n_spaces; ++p) {
-            auto & lst = s2g[p];
-            for (int el = 0; el < s_elems[p]; ++el) {
-                const int g_el = elems[(size_t)el + (size_t)mx_elems * p];
-                const int * Ie = &fem.I[(size_t)nb2 * g_el];
-                int * sIe = &sI[(size_t)nb2 * (el + (size_t)mx_elems * p)];
-                for (int t = 0; t < nb2; ++t) {
-                    const int g = Ie[t];
-                    if (local[g] < 0) {
-                        local[g] = (int)lst.size();
-                        lst.push_back(g);
+        {
+            size_t cap = 64;
+            while (cap < (size_t)4 * mx_elems * nb2)
+                cap <<= 1;
+            parallel_for(n_spaces, [&](int64_t pb, int64_t pe, int) {
+                std::vector<int> key(cap, -1), val(cap, 0);
+                std::vector<size_t> used;
+                used.reserve((size_t)mx_elems * nb2);
+                for (int64_t p = pb; p < pe; ++p) {
+                    auto & lst = s2g[p];
+                    lst.reserve((size_t)s_elems[p] * nb2);
+                    for (int el = 0; el < s_elems[p]; ++el) {
+                        const int g_el = elems[(size_t)el + (size_t)mx_elems * p];
+                        const int * Ie = &fem.I[(size_t)nb2 * g_el];
+                        int * sIe = &sI[(size_t)nb2 * (el + (size_t)mx_elems * p)];
+                        for (int t = 0; t < nb2; ++t) {
+                            const int g = Ie[t];
+                            size_t h = ((size_t)(uint32_t)g * 2654435761u) & (cap - 1);
+                            while (key[h] != -1 && key[h] != g)
+                                h = (h + 1) & (cap - 1);
+                            if (key[h] == -1) {
+                                key[h] = g;
+                                val[h] = (int)lst.size();
+                                lst.push_back(g);
+                                used.push_back(h);
+                            }
+                            sIe[t] = val[h];
+                        }
                     }
-                    sIe[t] = local[g];
+                    s_dof[p] = (int)lst.size();
+                    for (size_t h : used)
+                        key[h] = -1;
+                    used.clear();
                 }
-            }
-            s_dof[p] = (int)lst.size();
-            for (int g : lst)
-                local[g] = -1;
+            });
         }
         mx_ndof = *std::max_element(s_dof.begin(), s_dof.end());
         gI.assign((size_t)mx_ndof * n_spaces, -1);
-        for (int p = 0; p < n_spaces; ++p)
-            std::copy(s2g[p].begin(), s2g[p].end(), gI.begin() + (size_t)mx_ndof * p);
+        parallel_for(n_spaces, [&](int64_t pb, int64_t pe, int) {
+            for (int64_t p = pb; p < pe; ++p)
+                std::copy(s2g[p].begin(), s2g[p].end(), gI.begin() + (size_t)mx_ndof * p);
+        });
 
         tm.lap("ensemble dof numbering");
-        // face-space numbering: first touch over (face, i), reversed on side 1 of a flipped edge (:193-234)
+        // face-space numbering: first touch over (face, i), reversed on side 1 of a flipped edge (:193-234); per subspace, threaded
         fI.assign((size_t)nb * mx_faces * n_spaces, -1);
         s_fdof.assign(n_spaces, 0);
         std::vector<std::vector<int>> f2s(n_spaces);
-        {
+        parallel_for(n_spaces, [&](int64_t pb, int64_t pe, int) {
             std::vector<int> flocal((size_t)mx_ndof, -1);
-            for (int p = 0; p < n_spaces; ++p) {
+            for (int64_t p = pb; p < pe; ++p) {
                 auto & lst = f2s[p];
                 for (int f = 0; f < s_faces[p]; ++f) {
                     const size_t at = (size_t)f + (size_t)mx_faces * p;
@@ -157,7 +177,7 @@ namespace cb200
                 for (int idx : lst)
                     flocal[idx] = -1;
             }
-        }
+        });
         mx_fdof = *std::max_element(s_fdof.begin(), s_fdof.end());
         pI.assign((size_t)mx_fdof * n_spaces, -1);
         for (int p = 0; p < n_spaces; ++p)
@@ -165,8 +185,35 @@ namespace cb200
 
         tm.lap("ensemble face numbering");
         // connectivity map: one entry per unique shared face DOF per subspace pair (:254-286); 64-bit keys
-        std::unordered_set<uint64_t> seen;
-        seen.reserve(shared_faces.size() * (size_t)nb * 2);
+        // (a flat open-addressing set: the insertion order - which IS the output order - stays the serial one)
+        struct FlatSet
+        {
+            std::vector<uint64_t> slot;
+            size_t mask;
+            explicit FlatSet(size_t n)
+            {
+                size_t cap = 64;
+                while (cap < 2 * n + 16)
+                    cap <<= 1;
+                slot.assign(cap, ~uint64_t(0));
+                mask = cap - 1;
+            }
+            bool insert(uint64_t k) // true if new; keys never equal ~0
+            {
+                uint64_t z = k + 0x9e3779b97f4a7c15ull;
+                z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+                z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+                size_t h = (size_t)(z ^ (z >> 31)) & mask;
+                while (slot[h] != ~uint64_t(0)) {
+                    if (slot[h] == k)
+                        return false;
+                    h = (h + 1) & mask;
+                }
+                slot[h] = k;
+                return true;
+            }
+        } seen(shared_faces.size() * (size_t)nb);
+        cmap.reserve(shared_faces.size() * (size_t)nb * 4);
         for (auto & sf : shared_faces) {
             const uint64_t lo = (uint64_t)std::min(sf.S0, sf.S1), hi = (uint64_t)std::max(sf.S0, sf.S1);
             const uint64_t pair_key = lo + (uint64_t)n_spaces * hi;
@@ -174,7 +221,7 @@ namespace cb200
                 const int j0 = fI[(size_t)i + nb * (sf.l0 + (size_t)mx_faces * sf.S0)];
                 const int j1 = fI[(size_t)i + nb * (sf.l1 + (size_t)mx_faces * sf.S1)];
                 const uint64_t lkey = (uint64_t)((sf.S0 < sf.S1) ? j0 : j1);
-                if (seen.insert(pair_key * (uint64_t)(mx_fdof + 1) + lkey).second) {
+                if (seen.insert(pair_key * (uint64_t)(mx_fdof + 1) + lkey)) {
                     const int rec[4] = {sf.S0, sf.S1, j0, j1};
                     cmap.insert(cmap.end(), rec, rec + 4);
                 }

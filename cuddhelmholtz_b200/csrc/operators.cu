@@ -1382,8 +1382,7 @@ namespace cb200
                 static const int aring = env_int("CUDDH_B200_AFFINE_RING", -5);
                 // (negative: per-thread cp.async ring of that many rows)
                 if (nb == 5 && nqs == 6 && nqm == 9)
-                    return aring == 0 ? &launch_ws<5, 6, true, 9, 0, true> : aring == -3 ? &launch_ws<5, 6, true, 9, -3, true>
-                         : aring == -4 ? &launch_ws<5, 6, true, 9, -4, true> : aring == 5 ? &launch_ws<5, 6, true, 9, 5, true>
+                    return aring == 0 ? &launch_ws<5, 6, true, 9, 0, true> : aring == 5 ? &launch_ws<5, 6, true, 9, 5, true>
                          : &launch_ws<5, 6, true, 9, -5, true>;
                 if (nb == 4 && nqs == 5 && nqm == 8)
                     return aring == 0 ? &launch_ws<4, 5, true, 8, 0, true> : aring == 5 ? &launch_ws<4, 5, true, 8, 5, true>

@@ -115,8 +115,6 @@
                         int4 idx[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            constexpr int dummy = 0;
-                            (void)dummy;
                             const int gq = H * NGH + c0 + u;
                             if (c0 + u < NGH && gq < NG)
                                 idx[u] = __ldg(ig + gq * PE);

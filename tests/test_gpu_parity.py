@@ -834,6 +834,30 @@ def test_affine_and_stored_metric_paths_agree(nb, monkeypatch):
     assert rel(got[True][0], got[False][0]) < 1e-14 and rel(got[True][1], got[False][1]) < 1e-14
 
 
+@pytest.mark.parametrize("nb", [5, 4])
+def test_metric_ring_variants_are_bitwise_equal(nb):
+    """the fused Helmholtz kernel feeds its metric data through a per-thread cp.async ring (default), a TMA ring with mbarriers or
+    straight through registers - the instance is fixed per process (environment), so each variant runs in its own process
+    (scripts/fused_variant.py) and reports a hash of [Au; Av] at 256^2: the variants only move data differently and must agree
+    bit for bit, on the affine and on the stored-metric path."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    def run(env):
+        e = dict(os.environ)
+        for k in [k for k in e if k.startswith("CUDDH_B200_")]:
+            del e[k]
+        e.update(env)
+        out = subprocess.run([sys.executable, os.path.join(root, "scripts", "fused_variant.py"), "256", str(nb)], env=e, capture_output=True,
+                             text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        return json.loads(out.stdout.strip().splitlines()[-1])["sha1"]
+    affine = {v: run({"CUDDH_B200_AFFINE_RING": v}) for v in ("-5", "5", "0")}
+    assert len(set(affine.values())) == 1, affine
+    rk = "CUDDH_B200_RING" if nb == 5 else "CUDDH_B200_RING4F"
+    stored = {v: run({"CUDDH_B200_AFFINE": "0", rk: v}) for v in ("-5", "5")}
+    assert len(set(stored.values())) == 1, stored
+
+
 def test_full_size_properties():
     # BASELINE config 2 size (uniform_rect(1024), n_basis 5): size-independent properties of the operators
     nx, nb = 1024, 5
