@@ -1220,20 +1220,15 @@ namespace cb200
             return (base + 3 * (size_t)NPR * 128 * 16 + 1024) * 2 <= 233472 ? 3 : 0;
         }
 
-        template <int NB, int NQ, bool STIFF, bool AFFINE = false>
-        void launch_volume_pair(VolumeOp & op, const PlanDev & pd, const Plan & plan, double c, int accumulate, const double * x, double * y,
-                                cudaStream_t s)
+        template <int NB, int NQ, bool STIFF>
+        void fill_pair_tables(PairTables<NB, NQ, STIFF> & tab, const VolumeOp & op, const double msc = 1.0)
         {
-            CB_REQUIRE(plan.PE == 64, "thread-pair kernel: patches must hold 64 elements");
-            constexpr int NI = (NB - 2) * (NB - 2);
-            constexpr int RD = pair_ring_depth<NB, NQ, STIFF, AFFINE>();
-            constexpr int NPR = PairCfg<NB, NQ, STIFF>::NPR;
-            const size_t smem = sizeof(double) * 2 * (size_t)NB * NB * 64 + sizeof(int) * 2 * (size_t)NI * 64 + (size_t)RD * NPR * 128 * 16 + 16;
-            PairTables<NB, NQ, STIFF> tab;
             std::memset(&tab, 0, sizeof(tab));
             for (int q = 0; q < NQ; ++q)
                 for (int k = 0; k < NB; ++k) {
                     tab.Prow[q][k] = op.P[q + NQ * k];
+                    if (!STIFF)
+                        tab.PSrow[q][k] = msc * op.P[q + NQ * k];
                     if (STIFF) {
                         tab.Drow[q][k] = op.D[q + NQ * k];
                         if (!op.wq.empty()) {
@@ -1242,7 +1237,27 @@ namespace cb200
                         }
                     }
                 }
-            auto kern = volume_action_pair<NB, NQ, STIFF, AFFINE, RD>;
+        }
+
+        // one launch of the thread-pair kernel: a single operator (NQ2 == 0, op2 == nullptr) or the fused S + msc * M of one field
+        template <int NB, int NQ, bool STIFF, bool AFFINE, int NQ2>
+        void launch_pair(const VolumeOp & op, const VolumeOp * op2, const PlanDev & pd, const Plan & plan, PairArgs a, cudaStream_t s)
+        {
+            CB_REQUIRE(plan.PE == 64, "thread-pair kernel: patches must hold 64 elements");
+            constexpr int NI = (NB - 2) * (NB - 2);
+            constexpr int RD = pair_ring_depth<NB, NQ, STIFF, AFFINE>();
+            constexpr int RD2 = NQ2 > 0 ? pair_ring_depth<NB, (NQ2 > 0 ? NQ2 : 1), false, false>() : 0;
+            static_assert(NQ2 == 0 || RD2 > 0, "fused thread-pair instances need the metric ring for their mass phase");
+            constexpr int NPRR = RD > 0 ? PairCfg<NB, NQ, STIFF>::NPR : PairCfg<NB, (NQ2 > 0 ? NQ2 : 1), false>::NPR;
+            constexpr int RDR = RD > 0 ? RD : RD2;
+            const size_t smem = sizeof(double) * 2 * (size_t)NB * NB * 64 + sizeof(int) * 2 * (size_t)NI * 64 + (size_t)RDR * NPRR * 128 * 16 + 16;
+            PairTables<NB, NQ, STIFF> tab;
+            fill_pair_tables(tab, op);
+            PairTables<NB, (NQ2 > 0 ? NQ2 : 1), false> tab2;
+            std::memset(&tab2, 0, sizeof(tab2));
+            if constexpr (NQ2 > 0)
+                fill_pair_tables(tab2, *op2, a.msc);
+            auto kern = volume_action_pair<NB, NQ, STIFF, AFFINE, RD, NQ2, RD2>;
             static int grid_of_device[MAX_DEVICES] = {};
             int dev = 0;
             cudaGetDevice(&dev);
@@ -1256,8 +1271,22 @@ namespace cb200
                 CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
                 grid = std::max(1, occ) * sms;
             }
+            a.n_patches = (int)plan.n_patches;
+            a.zero = 0;
+            const int cap = max_persistent_ctas();
+            const int wave = cap > 0 ? std::min(grid, cap) : grid;
+            const int g = (int)std::min<int64_t>(wave, plan.n_patches);
+            kern<<<g, 256, smem, s>>>(tab, tab2, pd, a);
+            CB_LAUNCHED();
+        }
+
+        template <int NB, int NQ, bool STIFF, bool AFFINE = false>
+        void launch_volume_pair(VolumeOp & op, const PlanDev & pd, const Plan & plan, double c, int accumulate, const double * x, double * y,
+                                cudaStream_t s)
+        {
             PairArgs a{};
             a.G = reinterpret_cast<const double2 *>(op.d_G.p);
+            a.G2 = nullptr;
             a.Gc = op.d_Gc.p;
             a.x = x;
             a.y = y;
@@ -1265,13 +1294,21 @@ namespace cb200
             a.c = c;
             a.msc = 1.0;
             a.accumulate = accumulate;
-            a.n_patches = (int)plan.n_patches;
-            a.zero = 0;
-            const int cap = max_persistent_ctas();
-            const int wave = cap > 0 ? std::min(grid, cap) : grid;
-            const int g = (int)std::min<int64_t>(wave, plan.n_patches);
-            kern<<<g, 256, smem, s>>>(tab, pd, a);
-            CB_LAUNCHED();
+            launch_pair<NB, NQ, STIFF, AFFINE, 0>(op, nullptr, pd, plan, a, s);
+        }
+
+        // fused S + msc * M of one field (Helmholtz composite at n_basis 6-8): stiffness rule nq = nb + 1, weighted-mass rule 1 + 3nb/2 + 1
+        using FusedPairFn = void (*)(const VolumeOp &, const VolumeOp *, const PlanDev &, const Plan &, PairArgs, cudaStream_t);
+        FusedPairFn find_fused_pair_instance(int nb, int nqs, int nqm, bool affine)
+        {
+            if (!affine) // stored-metric meshes keep the per-operator launches (see volume_action_pair)
+                return nullptr;
+#define CB_CASE(NB_, NQS_, NQM_)                                                                                       \
+    if (nb == NB_ && nqs == NQS_ && nqm == NQM_)                                                                       \
+        return &launch_pair<NB_, NQS_, true, true, NQM_>;
+            CB_CASE(6, 7, 11) CB_CASE(7, 8, 12) CB_CASE(8, 9, 14)
+#undef CB_CASE
+            return nullptr;
         }
 
         using LaunchFn = void (*)(VolumeOp &, const PlanDev &, const Plan &, double, int, const double *, double *, cudaStream_t);
@@ -1949,6 +1986,11 @@ namespace cb200
         op->fused = op->S->tpe && op->M->tpe && op->S->plan == op->M->plan &&
                     find_fused_instance(op->S->nb, op->S->nq, op->M->nq, op->S->affine) != nullptr &&
                     env_int("CUDDH_B200_FUSED", 1) != 0;
+        // n_basis 6-8: the thread-pair kernel runs S - w^2 M of one field per launch (two launches per apply)
+        op->fused_pair = op->S->pair && op->M->pair && op->S->plan == op->M->plan &&
+                         find_fused_pair_instance(op->S->nb, op->S->nq, op->M->nq, op->S->affine) != nullptr &&
+                         env_int("CUDDH_B200_FUSED", 1) != 0;
+        op->fused = op->fused || op->fused_pair;
         if (op->fused)
             op->d_partial2.alloc(2 * (size_t)std::max<int64_t>(op->S->plan->n_slots_total, 1));
         return op;
@@ -1984,8 +2026,24 @@ namespace cb200
             a.accumulate = 0;
             a.n_patches = (int)plan.n_patches;
             a.n_fields = 2;
-            if (phases & 1)
+            if ((phases & 1) && !fused_pair)
                 find_fused_instance(S->nb, S->nq, M->nq, S->affine)(*S, M.get(), pd, plan, a, s);
+            if ((phases & 1) && fused_pair) {
+                FusedPairFn fn = find_fused_pair_instance(S->nb, S->nq, M->nq, S->affine);
+                for (int f = 0; f < 2; ++f) {
+                    PairArgs pa{};
+                    pa.G = reinterpret_cast<const double2 *>(S->d_G.p);
+                    pa.G2 = reinterpret_cast<const double2 *>(M->d_G.p);
+                    pa.Gc = S->d_Gc.p;
+                    pa.x = x + f * n;
+                    pa.y = y + f * n;
+                    pa.partial = d_partial2.p + f * a.partial_stride;
+                    pa.c = a.c[f];
+                    pa.msc = a.msc;
+                    pa.accumulate = 0;
+                    fn(*S, M.get(), pd, plan, pa, s);
+                }
+            }
             if (!(phases & 2))
                 return;
             if (plan.n_shared > 0) {

@@ -122,7 +122,8 @@ namespace cb200
         std::unique_ptr<VolumeOp> S, M;
         std::unique_ptr<FaceMassOp> H;
         DevBuf<double> d_partial2;    // fused path: partial sums of patch-boundary DOFs for both fields
-        bool fused = false;           // S - omega^2 M on u and v in one warp-specialised kernel (n_basis <= 5)
+        bool fused = false;           // S - omega^2 M on u and v in one warp-specialised kernel (n_basis <= 5), or per field (fused_pair)
+        bool fused_pair = false;      // n_basis 6-8: the thread-pair kernel with both phases, one launch per field
         // phases (fused path only): bit 0 = the fused volume kernel, bit 1 = shared-DOF assembly + face terms
         void apply(const double * x, double * y, cudaStream_t s, int phases = 3);
         // the apply of one slab of a partitioned mesh: local apply, interface rows packed inside the face-mass launch,

@@ -48,11 +48,13 @@
             double Drow[STIFF ? NQ : 1][NBP];   // D(q, k)
             double PWrow[STIFF ? NQ : 1][NBP];  // w_q P(q, k): back-contractions of the affine stiffness
             double DWrow[STIFF ? NQ : 1][NBP];
+            double PSrow[STIFF ? 1 : NQ][NBP];  // mass: msc * P(q, k), the phase scale folded into the last back-contraction
         };
 
         struct PairArgs
         {
             const double2 * G; // [patch][row tx][pair][thread slot 128]
+            const double2 * G2; // fused instances: the same for the mass phase
             const double * Gc; // AFFINE: per patch (3, 64) gA, gB, gC
             const double * x;
             double * y;
@@ -61,13 +63,220 @@
             int accumulate, n_patches, zero;
         };
 
+        // The quadrature rows of ONE operator for the element of this thread pair, accumulated into out[] (see the header of this file
+        // for the five steps). g: metric values of the current row (stored-metric instances without ring: loaded one row ahead, the
+        // last row fetches row 0 of the next patch from gp_next); RD > 0: the rows come out of the per-thread ring at ring_t.
+        template <int NB, int NQ, bool STIFF, bool AFFINE, int RD, bool UREG, bool ILP2, int GN, class Tab, class RequestFn>
+        __device__ __forceinline__ void pair_rows(const Tab & tab, const double * bc, const int cstep, double (&out)[NB * ((NB + 1) / 2)],
+                                                  double (&g)[GN], const double2 * gp, const double2 * gp_next, const double gA,
+                                                  const double gB, const double gC, const bool mirrored, const int zero,
+                                                  const double2 * ring_t, int & tr_slot, RequestFn tr_request)
+        {
+            using Cfg = PairCfg<NB, NQ, STIFF>;
+            constexpr int PE = Cfg::PE, JA = Cfg::JA, TA = Cfg::TA, NKI = Cfg::NKI, KR = Cfg::KR, NPR = Cfg::NPR;
+            static_assert(GN >= (AFFINE ? 1 : KR), "metric register buffer too small");
+            double U[UREG ? NB * JA : 1];
+            if constexpr (UREG) {
+#pragma unroll
+                for (int jj = 0; jj < JA; ++jj)
+#pragma unroll
+                    for (int ii = 0; ii < NB; ++ii)
+                        U[ii + NB * jj] = bc[jj * cstep + ii * PE];
+            }
+#pragma unroll 1
+            for (int tx = 0; tx < NQ; ++tx) {
+                const int z = tx * zero; // 0 at run time; keeps the tt-indexed table loads inside the rolled loop
+                // ---- 1. first-index contraction of the own columns ----
+                double pu[JA], du[STIFF ? JA : 1];
+#pragma unroll
+                for (int jj = 0; jj < JA; ++jj) {
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int ii = 0; ii < NB; ++ii) {
+                        double u;
+                        if constexpr (UREG)
+                            u = U[ii + NB * jj];
+                        else
+                            u = bc[jj * cstep + ii * PE];
+                        s0 = fma(tab.Prow[tx][ii], u, s0);
+                        if (STIFF)
+                            s1 = fma(tab.Drow[tx][ii], u, s1);
+                    }
+                    pu[jj] = s0;
+                    if (STIFF)
+                        du[jj] = s1;
+                }
+                if (NB % 2) { // the middle column belongs to the natural-frame thread
+                    pu[JA - 1] = mirrored ? 0.0 : pu[JA - 1];
+                    if (STIFF)
+                        du[JA - 1] = mirrored ? 0.0 : du[JA - 1];
+                }
+                // ---- 2. the partner's columns ----
+                double puo[JA], duo[STIFF ? JA : 1];
+#pragma unroll
+                for (int jj = 0; jj < JA; ++jj) {
+                    puo[jj] = __shfl_xor_sync(0xffffffffu, pu[jj], 16);
+                    if (STIFF)
+                        duo[jj] = __shfl_xor_sync(0xffffffffu, du[jj], 16);
+                }
+                // ---- 2-4. own quadrature columns: second-index contraction, metric, partial back-contraction ----
+                double a0o[JA], a0n[JA], a1o[STIFF ? JA : 1], a1n[STIFF ? JA : 1];
+#pragma unroll
+                for (int q = 0; q < JA; ++q) {
+                    a0o[q] = a0n[q] = 0.0;
+                    if (STIFF)
+                        a1o[q] = a1n[q] = 0.0;
+                }
+                const double2 * gnext = (tx + 1 < NQ) ? gp + (size_t)(tx + 1) * (NPR * Cfg::NT) : gp_next;
+                if constexpr (RD > 0) { // this row's pairs out of the ring (the oldest of the RD groups in flight)
+                    asm volatile("cp.async.wait_group %0;" ::"n"(RD - 1) : "memory");
+                    const double2 * src = ring_t + (size_t)tr_slot * (NPR * Cfg::NT);
+#pragma unroll
+                    for (int m = 0; m < NPR; ++m) {
+                        const double2 v = src[m * Cfg::NT];
+                        g[2 * m] = v.x;
+                        g[2 * m + 1] = v.y;
+                    }
+                }
+                // ILP2 (affine stiffness): all second-index sums first - pu / du are dead before the back-contraction accumulators
+                // come alive, which is what lets U stay in registers at n_basis 8 (for the stored-metric and mass instances the
+                // same order cost ptxas the uniform table loads, LDCU -> LDC, and was slower: 0.94 -> 1.32 ms)
+                double DxA[ILP2 ? TA : 1], DyA[ILP2 ? TA : 1];
+                if constexpr (ILP2) {
+#pragma unroll
+                    for (int tt = 0; tt < TA; ++tt)
+                        DxA[tt] = DyA[tt] = 0.0;
+#pragma unroll
+                    for (int jj = 0; jj < JA; ++jj)
+#pragma unroll
+                        for (int tt = 0; tt < TA; ++tt) {
+                            DxA[tt] = fma(tab.Prow[tt + z][jj], du[jj], DxA[tt]);
+                            DyA[tt] = fma(tab.Drow[tt + z][jj], pu[jj], DyA[tt]);
+                        }
+#pragma unroll
+                    for (int jj = 0; jj < JA; ++jj)
+#pragma unroll
+                        for (int tt = 0; tt < TA; ++tt) {
+                            DxA[tt] = fma(tab.Prow[tt + z][NB - 1 - jj], duo[jj], DxA[tt]);
+                            DyA[tt] = fma(tab.Drow[tt + z][NB - 1 - jj], puo[jj], DyA[tt]);
+                        }
+                }
+#pragma unroll
+                for (int tt = 0; tt < TA; ++tt) {
+                    const bool dead = (NQ % 2) && tt == TA - 1 && mirrored; // the middle quadrature column belongs to thread 0
+                    if (STIFF) {
+                        double Dx = 0.0, Dy = 0.0;
+                        if constexpr (ILP2) {
+                            Dx = DxA[tt];
+                            Dy = DyA[tt];
+                        }
+                        else {
+#pragma unroll
+                            for (int jj = 0; jj < JA; ++jj) {
+                                Dx = fma(tab.Prow[tt + z][jj], du[jj], Dx);
+                                Dy = fma(tab.Drow[tt + z][jj], pu[jj], Dy);
+                            }
+#pragma unroll
+                            for (int jj = 0; jj < JA; ++jj) {
+                                Dx = fma(tab.Prow[tt + z][NB - 1 - jj], duo[jj], Dx);
+                                Dy = fma(tab.Drow[tt + z][NB - 1 - jj], puo[jj], Dy);
+                            }
+                        }
+                        double F0, F1;
+                        if constexpr (AFFINE) {
+                            F0 = gA * Dx + gB * Dy;
+                            F1 = gB * Dx + gC * Dy;
+                            if ((NQ % 2) && tt == TA - 1) {
+                                F0 = dead ? 0.0 : F0;
+                                F1 = dead ? 0.0 : F1;
+                            }
+#pragma unroll
+                            for (int q = 0; q < JA; ++q) {
+                                a0o[q] = fma(tab.PWrow[tt + z][q], F0, a0o[q]);
+                                a0n[q] = fma(tab.PWrow[tt + z][NB - 1 - q], F0, a0n[q]);
+                                a1o[q] = fma(tab.DWrow[tt + z][q], F1, a1o[q]);
+                                a1n[q] = fma(tab.DWrow[tt + z][NB - 1 - q], F1, a1n[q]);
+                            }
+                        }
+                        else {
+                            const double A = g[3 * tt], B = g[3 * tt + 1], C = g[3 * tt + 2]; // B sign-flipped, dead column zeroed in the layout
+                            F0 = A * Dx + B * Dy;
+                            F1 = B * Dx + C * Dy;
+#pragma unroll
+                            for (int q = 0; q < JA; ++q) {
+                                a0o[q] = fma(tab.Prow[tt + z][q], F0, a0o[q]);
+                                a0n[q] = fma(tab.Prow[tt + z][NB - 1 - q], F0, a0n[q]);
+                                a1o[q] = fma(tab.Drow[tt + z][q], F1, a1o[q]);
+                                a1n[q] = fma(tab.Drow[tt + z][NB - 1 - q], F1, a1n[q]);
+                            }
+                        }
+                    }
+                    else {
+                        double ppu = 0.0;
+#pragma unroll
+                        for (int jj = 0; jj < JA; ++jj)
+                            ppu = fma(tab.Prow[tt + z][jj], pu[jj], ppu);
+#pragma unroll
+                        for (int jj = 0; jj < JA; ++jj)
+                            ppu = fma(tab.Prow[tt + z][NB - 1 - jj], puo[jj], ppu);
+                        const double val = g[tt] * ppu; // the phase scale sits in PSrow
+#pragma unroll
+                        for (int q = 0; q < JA; ++q) {
+                            a0o[q] = fma(tab.Prow[tt + z][q], val, a0o[q]);
+                            a0n[q] = fma(tab.Prow[tt + z][NB - 1 - q], val, a0n[q]);
+                        }
+                    }
+                    // metric pairs that are no longer needed: fetch the same pairs of the next row (or of the next patch)
+                    if constexpr (!AFFINE && RD == 0) {
+#pragma unroll
+                        for (int m = pairs_done<TA, NKI, KR>(tt - 1); m < pairs_done<TA, NKI, KR>(tt); ++m) {
+                            const double2 v = ld_metric_pair(gnext + m * Cfg::NT);
+                            g[2 * m] = v.x;
+                            g[2 * m + 1] = v.y;
+                        }
+                    }
+                }
+                if constexpr (RD > 0) { // the row's values have been consumed: refill its slot with the row RD further on
+                    tr_request(tr_slot);
+                    if (++tr_slot == RD)
+                        tr_slot = 0;
+                }
+                // ---- 4b. the partner's share of the own output columns ----
+#pragma unroll
+                for (int q = 0; q < JA; ++q) {
+                    a0o[q] += __shfl_xor_sync(0xffffffffu, a0n[q], 16);
+                    if (STIFF)
+                        a1o[q] += __shfl_xor_sync(0xffffffffu, a1n[q], 16);
+                }
+                // ---- 5. first-index back-contraction into the own output columns ----
+#pragma unroll
+                for (int q = 0; q < JA; ++q)
+#pragma unroll
+                    for (int ii = 0; ii < NB; ++ii) {
+                        if (STIFF) {
+                            if constexpr (AFFINE)
+                                out[ii + NB * q] = fma(tab.DWrow[tx][ii], a0o[q], fma(tab.PWrow[tx][ii], a1o[q], out[ii + NB * q]));
+                            else
+                                out[ii + NB * q] = fma(tab.Drow[tx][ii], a0o[q], fma(tab.Prow[tx][ii], a1o[q], out[ii + NB * q]));
+                        }
+                        else
+                            out[ii + NB * q] = fma(tab.PSrow[tx][ii], a0o[q], out[ii + NB * q]);
+                    }
+            }
+
+        }
+
         // RD > 0: the metric rows come through a PER-THREAD shared-memory ring of RD rows (16-byte cp.async of the thread's own
         // pairs, cp.async.wait_group, no barrier - as contract_mass_tring in volume_ws.cuh) instead of through registers one row
         // ahead: the rows of the mass operator are short (176 DFMA per thread at n_basis 8), one row of lead does not cover an
         // L2 / DRAM round trip (ncu: 3.8 long-scoreboard warps per issued instruction).
-        template <int NB, int NQ, bool STIFF, bool AFFINE, int RD = 0>
+        // NQ2 > 0: a weighted-mass phase (n_quad NQ2, metric args.G2 through the per-thread ring of RD2 rows, scale folded into
+        // tab2.PSrow) follows the stiffness phase on the same element data and accumulates into the same registers: the Helmholtz
+        // composite S - omega^2 M of one field in one launch (one gather, one assembly instead of two).
+        template <int NB, int NQ, bool STIFF, bool AFFINE, int RD = 0, int NQ2 = 0, int RD2 = 0>
         __global__ void __launch_bounds__(256, 2)
-        volume_action_pair(const __grid_constant__ PairTables<NB, NQ, STIFF> tab, const PlanDev plan, const __grid_constant__ PairArgs args)
+        volume_action_pair(const __grid_constant__ PairTables<NB, NQ, STIFF> tab, const __grid_constant__ PairTables<NB, (NQ2 > 0 ? NQ2 : 1), false> tab2,
+                           const PlanDev plan, const __grid_constant__ PairArgs args)
         {
             using Cfg = PairCfg<NB, NQ, STIFF>;
             constexpr int PE = Cfg::PE, NB2 = NB * NB, JA = Cfg::JA, TA = Cfg::TA, NKI = Cfg::NKI, KR = Cfg::KR, NPR = Cfg::NPR;
@@ -83,6 +292,16 @@
             // (measured at 1024^2: n_basis 6 stiffness 0.371 -> 0.355 ms; the mass kernels gain only together with the metric ring)
             constexpr bool ILP2 = STIFF && AFFINE && NB >= 7 && NB <= 8;
             constexpr bool UREG = STIFF ? (NB <= 6 || ILP2) : (NB <= 8 && RD > 0);
+            constexpr bool UREG2 = NB <= 8; // second (mass) phase, always fed from the ring
+            // the ONE per-thread metric ring of the kernel serves the phase that has a depth: the mass operator of a stand-alone mass
+            // instance (RD) or the mass phase of a fused instance (RD2)
+            using Cfg2 = PairCfg<NB, (NQ2 > 0 ? NQ2 : 1), false>;
+            constexpr int RDR = RD > 0 ? RD : RD2, NQR = RD > 0 ? NQ : NQ2, NPRR = RD > 0 ? NPR : Cfg2::NPR;
+            constexpr size_t g_patchR = (size_t)NQR * NPRR * Cfg::NT;
+            // (a stored-metric stiffness phase in front of the mass phase was tried: its row buffer stays live across the second phase,
+            // ptxas spills ~800 bytes and the tables fall to LDC at n_basis 8 - the fused form is offered on affine meshes only)
+            static_assert(NQ2 == 0 || (STIFF && AFFINE && RD == 0 && RD2 > 0), "fused instances: affine stiffness phase, mass phase with ring");
+            static_assert(RD2 == 0 || NQ2 > 0, "RD2 is the ring depth of the second phase");
             static_assert(!AFFINE || STIFF, "AFFINE is a property of the stiffness operator");
             static_assert(NB >= 3, "pair kernel: n_basis >= 3");
 
@@ -91,6 +310,7 @@
             int * gints = reinterpret_cast<int *>(bufs + NBUF * BUF); // [NBUF][NI][PE] global DOFs of the element-interior nodes
             double2 * mring = reinterpret_cast<double2 *>(gints + NBUF * NI * PE); // [RD][NPR][128] per-thread metric ring
             static_assert(RD == 0 || !AFFINE, "the metric ring serves the stored-metric instances");
+            (void)tab2;
             static_assert((NBUF * NI * PE) % 4 == 0, "ring alignment");
 
             const int wg = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 7), 0);
@@ -266,21 +486,22 @@
 
                 double g[AFFINE ? 2 : KR]; // metric values of the current quadrature row (stored-metric instances)
                 // per-thread ring: running source pointer (rows of a patch are contiguous), patch skip, ring address - in registers
-                const double2 * tr_src = args.G + (size_t)cta * g_patch + t;
-                int tr_skip = (stride - 1) * (int)g_patch, tr_i = 0, tr_r = 0, tr_slot = 0;
+                const double2 * ringG = RD > 0 ? args.G : args.G2;
+                const double2 * tr_src = ringG + (size_t)cta * g_patchR + t;
+                int tr_skip = (stride - 1) * (int)g_patchR, tr_i = 0, tr_r = 0, tr_slot = 0;
                 unsigned tr_dst = (unsigned)__cvta_generic_to_shared(mring + t);
-                if constexpr (RD > 0)
+                if constexpr (RDR > 0)
                     asm volatile("" : "+l"(tr_src), "+r"(tr_skip), "+r"(tr_dst));
                 auto tr_request = [&](const int slot) {
                     if (tr_i < n_iter) {
-                        const unsigned dst = tr_dst + (unsigned)slot * (unsigned)(NPR * Cfg::NT * sizeof(double2));
+                        const unsigned dst = tr_dst + (unsigned)slot * (unsigned)(NPRR * Cfg::NT * sizeof(double2));
 #pragma unroll
-                        for (int m = 0; m < NPR; ++m)
+                        for (int m = 0; m < NPRR; ++m)
                             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (unsigned)(m * Cfg::NT * sizeof(double2))),
                                          "l"(tr_src + m * Cfg::NT)
                                          : "memory");
-                        tr_src += NPR * Cfg::NT;
-                        if (++tr_r == NQ) {
+                        tr_src += NPRR * Cfg::NT;
+                        if (++tr_r == NQR) {
                             tr_r = 0;
                             ++tr_i;
                             tr_src += tr_skip;
@@ -288,9 +509,9 @@
                     }
                     asm volatile("cp.async.commit_group;" ::: "memory");
                 };
-                if constexpr (RD > 0) {
+                if constexpr (RDR > 0) {
 #pragma unroll
-                    for (int k = 0; k < RD; ++k)
+                    for (int k = 0; k < RDR; ++k)
                         tr_request(k);
                 }
                 if constexpr (!AFFINE && RD == 0) {
@@ -322,193 +543,12 @@
                     for (int k = 0; k < NB * JA; ++k)
                         out[k] = 0.0;
                     const double * bc = b + col0;
-                    double U[UREG ? NB * JA : 1];
-                    if constexpr (UREG) {
-#pragma unroll
-                        for (int jj = 0; jj < JA; ++jj)
-#pragma unroll
-                            for (int ii = 0; ii < NB; ++ii)
-                                U[ii + NB * jj] = bc[jj * cstep + ii * PE];
-                    }
-#pragma unroll 1
-                    for (int tx = 0; tx < NQ; ++tx) {
-                        const int z = tx * zero; // 0 at run time; keeps the tt-indexed table loads inside the rolled loop
-                        // ---- 1. first-index contraction of the own columns ----
-                        double pu[JA], du[STIFF ? JA : 1];
-#pragma unroll
-                        for (int jj = 0; jj < JA; ++jj) {
-                            double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                            for (int ii = 0; ii < NB; ++ii) {
-                                double u;
-                                if constexpr (UREG)
-                                    u = U[ii + NB * jj];
-                                else
-                                    u = bc[jj * cstep + ii * PE];
-                                s0 = fma(tab.Prow[tx][ii], u, s0);
-                                if (STIFF)
-                                    s1 = fma(tab.Drow[tx][ii], u, s1);
-                            }
-                            pu[jj] = s0;
-                            if (STIFF)
-                                du[jj] = s1;
-                        }
-                        if (NB % 2) { // the middle column belongs to the natural-frame thread
-                            pu[JA - 1] = mirrored ? 0.0 : pu[JA - 1];
-                            if (STIFF)
-                                du[JA - 1] = mirrored ? 0.0 : du[JA - 1];
-                        }
-                        // ---- 2. the partner's columns ----
-                        double puo[JA], duo[STIFF ? JA : 1];
-#pragma unroll
-                        for (int jj = 0; jj < JA; ++jj) {
-                            puo[jj] = __shfl_xor_sync(0xffffffffu, pu[jj], 16);
-                            if (STIFF)
-                                duo[jj] = __shfl_xor_sync(0xffffffffu, du[jj], 16);
-                        }
-                        // ---- 2-4. own quadrature columns: second-index contraction, metric, partial back-contraction ----
-                        double a0o[JA], a0n[JA], a1o[STIFF ? JA : 1], a1n[STIFF ? JA : 1];
-#pragma unroll
-                        for (int q = 0; q < JA; ++q) {
-                            a0o[q] = a0n[q] = 0.0;
-                            if (STIFF)
-                                a1o[q] = a1n[q] = 0.0;
-                        }
-                        const double2 * gnext = (tx + 1 < NQ) ? gp + (size_t)(tx + 1) * (NPR * Cfg::NT) : gp_next;
-                        if constexpr (RD > 0) { // this row's pairs out of the ring (the oldest of the RD groups in flight)
-                            asm volatile("cp.async.wait_group %0;" ::"n"(RD - 1) : "memory");
-                            const double2 * src = mring + (size_t)tr_slot * (NPR * Cfg::NT) + t;
-#pragma unroll
-                            for (int m = 0; m < NPR; ++m) {
-                                const double2 v = src[m * Cfg::NT];
-                                g[2 * m] = v.x;
-                                g[2 * m + 1] = v.y;
-                            }
-                        }
-                        // ILP2 (affine stiffness): all second-index sums first - pu / du are dead before the back-contraction accumulators
-                        // come alive, which is what lets U stay in registers at n_basis 8 (for the stored-metric and mass instances the
-                        // same order cost ptxas the uniform table loads, LDCU -> LDC, and was slower: 0.94 -> 1.32 ms)
-                        double DxA[ILP2 ? TA : 1], DyA[ILP2 ? TA : 1];
-                        if constexpr (ILP2) {
-#pragma unroll
-                            for (int tt = 0; tt < TA; ++tt)
-                                DxA[tt] = DyA[tt] = 0.0;
-#pragma unroll
-                            for (int jj = 0; jj < JA; ++jj)
-#pragma unroll
-                                for (int tt = 0; tt < TA; ++tt) {
-                                    DxA[tt] = fma(tab.Prow[tt + z][jj], du[jj], DxA[tt]);
-                                    DyA[tt] = fma(tab.Drow[tt + z][jj], pu[jj], DyA[tt]);
-                                }
-#pragma unroll
-                            for (int jj = 0; jj < JA; ++jj)
-#pragma unroll
-                                for (int tt = 0; tt < TA; ++tt) {
-                                    DxA[tt] = fma(tab.Prow[tt + z][NB - 1 - jj], duo[jj], DxA[tt]);
-                                    DyA[tt] = fma(tab.Drow[tt + z][NB - 1 - jj], puo[jj], DyA[tt]);
-                                }
-                        }
-#pragma unroll
-                        for (int tt = 0; tt < TA; ++tt) {
-                            const bool dead = (NQ % 2) && tt == TA - 1 && mirrored; // the middle quadrature column belongs to thread 0
-                            if (STIFF) {
-                                double Dx = 0.0, Dy = 0.0;
-                                if constexpr (ILP2) {
-                                    Dx = DxA[tt];
-                                    Dy = DyA[tt];
-                                }
-                                else {
-#pragma unroll
-                                    for (int jj = 0; jj < JA; ++jj) {
-                                        Dx = fma(tab.Prow[tt + z][jj], du[jj], Dx);
-                                        Dy = fma(tab.Drow[tt + z][jj], pu[jj], Dy);
-                                    }
-#pragma unroll
-                                    for (int jj = 0; jj < JA; ++jj) {
-                                        Dx = fma(tab.Prow[tt + z][NB - 1 - jj], duo[jj], Dx);
-                                        Dy = fma(tab.Drow[tt + z][NB - 1 - jj], puo[jj], Dy);
-                                    }
-                                }
-                                double F0, F1;
-                                if constexpr (AFFINE) {
-                                    F0 = gA * Dx + gB * Dy;
-                                    F1 = gB * Dx + gC * Dy;
-                                    if ((NQ % 2) && tt == TA - 1) {
-                                        F0 = dead ? 0.0 : F0;
-                                        F1 = dead ? 0.0 : F1;
-                                    }
-#pragma unroll
-                                    for (int q = 0; q < JA; ++q) {
-                                        a0o[q] = fma(tab.PWrow[tt + z][q], F0, a0o[q]);
-                                        a0n[q] = fma(tab.PWrow[tt + z][NB - 1 - q], F0, a0n[q]);
-                                        a1o[q] = fma(tab.DWrow[tt + z][q], F1, a1o[q]);
-                                        a1n[q] = fma(tab.DWrow[tt + z][NB - 1 - q], F1, a1n[q]);
-                                    }
-                                }
-                                else {
-                                    const double A = g[3 * tt], B = g[3 * tt + 1], C = g[3 * tt + 2]; // B sign-flipped, dead column zeroed in the layout
-                                    F0 = A * Dx + B * Dy;
-                                    F1 = B * Dx + C * Dy;
-#pragma unroll
-                                    for (int q = 0; q < JA; ++q) {
-                                        a0o[q] = fma(tab.Prow[tt + z][q], F0, a0o[q]);
-                                        a0n[q] = fma(tab.Prow[tt + z][NB - 1 - q], F0, a0n[q]);
-                                        a1o[q] = fma(tab.Drow[tt + z][q], F1, a1o[q]);
-                                        a1n[q] = fma(tab.Drow[tt + z][NB - 1 - q], F1, a1n[q]);
-                                    }
-                                }
-                            }
-                            else {
-                                double ppu = 0.0;
-#pragma unroll
-                                for (int jj = 0; jj < JA; ++jj)
-                                    ppu = fma(tab.Prow[tt + z][jj], pu[jj], ppu);
-#pragma unroll
-                                for (int jj = 0; jj < JA; ++jj)
-                                    ppu = fma(tab.Prow[tt + z][NB - 1 - jj], puo[jj], ppu);
-                                const double val = (g[tt] * args.msc) * ppu;
-#pragma unroll
-                                for (int q = 0; q < JA; ++q) {
-                                    a0o[q] = fma(tab.Prow[tt + z][q], val, a0o[q]);
-                                    a0n[q] = fma(tab.Prow[tt + z][NB - 1 - q], val, a0n[q]);
-                                }
-                            }
-                            // metric pairs that are no longer needed: fetch the same pairs of the next row (or of the next patch)
-                            if constexpr (!AFFINE && RD == 0) {
-#pragma unroll
-                                for (int m = pairs_done<TA, NKI, KR>(tt - 1); m < pairs_done<TA, NKI, KR>(tt); ++m) {
-                                    const double2 v = ld_metric_pair(gnext + m * Cfg::NT);
-                                    g[2 * m] = v.x;
-                                    g[2 * m + 1] = v.y;
-                                }
-                            }
-                        }
-                        if constexpr (RD > 0) { // the row's values have been consumed: refill its slot with the row RD further on
-                            tr_request(tr_slot);
-                            if (++tr_slot == RD)
-                                tr_slot = 0;
-                        }
-                        // ---- 4b. the partner's share of the own output columns ----
-#pragma unroll
-                        for (int q = 0; q < JA; ++q) {
-                            a0o[q] += __shfl_xor_sync(0xffffffffu, a0n[q], 16);
-                            if (STIFF)
-                                a1o[q] += __shfl_xor_sync(0xffffffffu, a1n[q], 16);
-                        }
-                        // ---- 5. first-index back-contraction into the own output columns ----
-#pragma unroll
-                        for (int q = 0; q < JA; ++q)
-#pragma unroll
-                            for (int ii = 0; ii < NB; ++ii) {
-                                if (STIFF) {
-                                    if constexpr (AFFINE)
-                                        out[ii + NB * q] = fma(tab.DWrow[tx][ii], a0o[q], fma(tab.PWrow[tx][ii], a1o[q], out[ii + NB * q]));
-                                    else
-                                        out[ii + NB * q] = fma(tab.Drow[tx][ii], a0o[q], fma(tab.Prow[tx][ii], a1o[q], out[ii + NB * q]));
-                                }
-                                else
-                                    out[ii + NB * q] = fma(tab.Prow[tx][ii], a0o[q], out[ii + NB * q]);
-                            }
+                    pair_rows<NB, NQ, STIFF, AFFINE, RD, UREG, ILP2>(tab, bc, cstep, out, g, gp, gp_next, gA, gB, gC, mirrored, zero, mring + t,
+                                                                   tr_slot, tr_request);
+                    if constexpr (NQ2 > 0) { // weighted-mass phase of the fused composite, scale in tab2.PSrow
+                        double g2[Cfg2::KR];
+                        pair_rows<NB, NQ2, false, false, RD2, UREG2, false>(tab2, bc, cstep, out, g2, nullptr, nullptr, 0.0, 0.0, 0.0, mirrored,
+                                                                            zero, mring + t, tr_slot, tr_request);
                     }
 
                     // ---- results: element-interior nodes straight to y (one contributor), the rest back into the buffer ----
