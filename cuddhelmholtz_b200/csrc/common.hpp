@@ -174,6 +174,8 @@ namespace cb200
     struct Plan
     {
         int nb = 0, PE = 0;
+        bool interior_affine = false;      // node-major plans: in every element the ids of the nodes strictly inside it are base + (i-1) + (j-1) * stride
+                                           // (true for the first-touch numbering of H1Space on any mesh; the thread-pair kernel hands over 2 ids per element)
         bool node_major = false;           // L / cent laid out (PE, nb*nb) per patch instead of (nb*nb, PE): thread-per-element kernels
         int64_t n_patches = 0, n_slots_total = 0, n_shared = 0;
         int max_pdof = 0, max_nsh = 0;   // largest patch: DOFs, shared DOFs

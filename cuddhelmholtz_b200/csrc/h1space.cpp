@@ -363,6 +363,20 @@ namespace cb200
         }
         const int64_t np = (int64_t)pel.size();
         plan.n_patches = np;
+        if (tpe && nb >= 4) { // element-interior ids an affine function of (i, j)? (first-touch numbering: always; checked, not assumed)
+            bool ok = true;
+            for (int64_t el = 0; el < nel && ok; ++el) {
+                const int * Ie = &fem.I[(size_t)nb2 * el];
+                const int base = Ie[1 + nb], stride = Ie[1 + 2 * nb] - base;
+                for (int j = 1; j < nb - 1 && ok; ++j)
+                    for (int i = 1; i < nb - 1; ++i)
+                        if (Ie[i + nb * j] != base + (i - 1) + (j - 1) * stride) {
+                            ok = false;
+                            break;
+                        }
+            }
+            plan.interior_affine = ok;
+        }
 
         // 2. element slots of each patch (patch order = element order of the lists above)
         plan.hdr.resize(np);

@@ -1215,7 +1215,7 @@ namespace cb200
         {
             if (STIFF || AFFINE)
                 return 0;
-            constexpr int NI = (NB - 2) * (NB - 2), TA = (NQ + 1) / 2, NPR = ((TA + 1) & ~1) / 2;
+            constexpr int NI = 2, TA = (NQ + 1) / 2, NPR = ((TA + 1) & ~1) / 2; // NI: ids handed over per element (see volume_action_pair)
             constexpr size_t base = sizeof(double) * 2 * (size_t)NB * NB * 64 + sizeof(int) * 2 * (size_t)NI * 64 + 16;
             return (base + 3 * (size_t)NPR * 128 * 16 + 1024) * 2 <= 233472 ? 3 : 0;
         }
@@ -1243,8 +1243,8 @@ namespace cb200
         template <int NB, int NQ, bool STIFF, bool AFFINE, int NQ2>
         void launch_pair(const VolumeOp & op, const VolumeOp * op2, const PlanDev & pd, const Plan & plan, PairArgs a, cudaStream_t s)
         {
-            CB_REQUIRE(plan.PE == 64, "thread-pair kernel: patches must hold 64 elements");
-            constexpr int NI = (NB - 2) * (NB - 2);
+            CB_REQUIRE(plan.PE == 64 && plan.interior_affine, "thread-pair kernel: needs 64-element patches and affine element-interior ids");
+            constexpr int NI = 2;
             constexpr int RD = pair_ring_depth<NB, NQ, STIFF, AFFINE>();
             constexpr int RD2 = NQ2 > 0 ? pair_ring_depth<NB, (NQ2 > 0 ? NQ2 : 1), false, false>() : 0;
             static_assert(NQ2 == 0 || RD2 > 0, "fused thread-pair instances need the metric ring for their mass phase");
@@ -1306,7 +1306,7 @@ namespace cb200
 #define CB_CASE(NB_, NQS_, NQM_)                                                                                       \
     if (nb == NB_ && nqs == NQS_ && nqm == NQM_)                                                                       \
         return &launch_pair<NB_, NQS_, true, true, NQM_>;
-            CB_CASE(6, 7, 11) CB_CASE(7, 8, 12) CB_CASE(8, 9, 14)
+            CB_CASE(6, 7, 11) CB_CASE(7, 8, 12) CB_CASE(8, 9, 14) CB_CASE(9, 10, 15)
 #undef CB_CASE
             return nullptr;
         }
@@ -1528,6 +1528,12 @@ namespace cb200
                 op.affine = pair_affine;
                 op.plan = &fem->get_plan_tpe();
                 CB_REQUIRE(op.plan->PE == 64, "thread-pair kernel: the node-major plan must have 64-element patches");
+                if (!op.plan->interior_affine) { // never with H1Space's own numbering; the lane-per-row kernel serves such a plan
+                    op.pair = false;
+                    op.affine = false;
+                }
+            }
+            if (op.pair) {
                 op.epw = -1;
                 op.lw = 0;
                 op.n_pass = 0;

@@ -284,7 +284,8 @@
             constexpr int NBUF = 2;                             // assemble i-1, refill the same buffer for i+1, while i is computed
             constexpr int NG = (NB2 + 3) / 4;                   // groups of four nodes in the global index map
             constexpr int NGH = (NG + 1) / 2;                   // groups per helper half
-            constexpr int NI = (NB - 2) * (NB - 2);             // element-interior nodes
+            constexpr int NI = 2;                               // ids handed over per element: nodes (1,1) and (1,2) - the ids of the nodes strictly
+                                                                // inside an element are base + (i-1) + (j-1) * stride (Plan::interior_affine)
             constexpr size_t g_patch = (size_t)NQ * NPR * Cfg::NT; // double2 per patch
             constexpr int FULL = 1, READY = 4, HELPER = 7;      // named barrier ids
             // U (own columns) in registers for all rows where the register file allows it; otherwise re-read from the patch buffer
@@ -307,7 +308,7 @@
 
             extern __shared__ __align__(16) unsigned char smem_raw[];
             double * bufs = reinterpret_cast<double *>(smem_raw);     // [NBUF][NB2][PE]
-            int * gints = reinterpret_cast<int *>(bufs + NBUF * BUF); // [NBUF][NI][PE] global DOFs of the element-interior nodes
+            int * gints = reinterpret_cast<int *>(bufs + NBUF * BUF); // [NBUF][2][PE] global DOFs of the interior nodes (1,1) and (1,2) of every element
             double2 * mring = reinterpret_cast<double2 *>(gints + NBUF * NI * PE); // [RD][NPR][128] per-thread metric ring
             static_assert(RD == 0 || !AFFINE, "the metric ring serves the stored-metric instances");
             (void)tab2;
@@ -349,9 +350,10 @@
                                     if (k < NB2) {
                                         const int gi = w == 0 ? idx[u].x : w == 1 ? idx[u].y : w == 2 ? idx[u].z : idx[u].w;
                                         cp_async8(b + k * PE, args.x + gi);
-                                        const int ki = k % NB, kj = k / NB;
-                                        if (ki > 0 && ki < NB - 1 && kj > 0 && kj < NB - 1)
-                                            gs[((ki - 1) + (NB - 2) * (kj - 1)) * PE] = (he < n_el) ? gi : -1;
+                                        if (k == 1 + NB)
+                                            gs[0] = (he < n_el) ? gi : -1;
+                                        if (k == 1 + 2 * NB)
+                                            gs[PE] = gi;
                                     }
                                 }
                             }
@@ -479,9 +481,6 @@
                 // node (i, own column jj) sits at b[col0 + jj * cstep + i * PE]
                 const int col0 = mirrored ? (NB - 1) * NB * PE : 0;
                 const int cstep = mirrored ? -NB * PE : NB * PE;
-                // interior node (ii, own column qq >= 1): gints[gcol0 + (qq - 1) * gstep + (ii - 1) * PE]
-                const int gcol0 = mirrored ? (NB - 2) * (NB - 3) * PE : 0;
-                const int gstep = mirrored ? -(NB - 2) * PE : (NB - 2) * PE;
                 const int zero = args.zero;
 
                 double g[AFFINE ? 2 : KR]; // metric values of the current quadrature row (stored-metric instances)
@@ -554,15 +553,18 @@
                     // ---- results: element-interior nodes straight to y (one contributor), the rest back into the buffer ----
                     double * y = args.y;
                     const double c = args.c;
-                    const int * gi_base = gints + (i % NBUF) * (NI * PE) + e + gcol0;
+                    // interior node (ii, j): id = base + (ii - 1) + (j - 1) * stride, with j - 1 = q - 1 (natural frame) or nb - 2 - q (mirrored)
+                    const int * gi_p = gints + (i % NBUF) * (NI * PE) + e;
+                    const int gi_b = gi_p[0], gi_s = gi_p[PE] - gi_b;
+                    const int gi_col0 = gi_b + (mirrored ? (NB - 2) * gi_s : -gi_s), gi_cstep = mirrored ? -gi_s : gi_s; // id of (1, column q) = gi_col0 + q * gi_cstep
 #pragma unroll
                     for (int q = 0; q < JA; ++q) {
                         const bool own = !((NB % 2) && q == JA - 1) || !mirrored; // odd n_basis: the middle column is thread 0's
 #pragma unroll
                         for (int ii = 0; ii < NB; ++ii) {
                             if (ii > 0 && ii < NB - 1 && q > 0) {
-                                const int gi = gi_base[(q - 1) * gstep + (ii - 1) * PE];
-                                if (gi >= 0 && own) {
+                                const int gi = gi_col0 + q * gi_cstep + (ii - 1);
+                                if (gi_b >= 0 && own) {
                                     const double v = c * out[ii + NB * q];
                                     if (accumulate)
                                         asm volatile("red.global.add.f64 [%0], %1;" ::"l"(y + gi), "d"(v) : "memory");

@@ -176,9 +176,9 @@ def test_helmholtz_composite(kind, nb):
     # n_basis <= 5 runs the fused warp-specialised kernel (S - w^2 M on u and v in one launch, a cluster of two CTAs per patch
     # sequence), larger orders the per-operator composition: both must agree with the same composition done operator by
     # operator through the public API, and both are bitwise reproducible
-    # 2: fused kernels (n_basis <= 5; n_basis 6-8 on affine meshes: thread-pair kernel with both phases, one launch per field),
+    # 2: fused kernels (n_basis <= 5; n_basis 6-9 on affine meshes: thread-pair kernel with both phases, one launch per field),
     # 3: thread-pair kernels per operator
-    assert A.kernel_kind() == (2 if (nb <= 5 or (kind == "rect" and nb <= 8)) else 3)
+    assert A.kernel_kind() == (2 if (nb <= 5 or kind == "rect") else 3)
     y2 = torch.empty_like(y)
     A.action(dev(x), y2)
     assert torch.equal(y, y2)
@@ -789,7 +789,7 @@ def test_steady_state_against_oracle(nb, nx, cap):
         assert torch.equal(AX, AX2)
 
 
-@pytest.mark.parametrize("nb", [4, 5, 6, 7, 8])
+@pytest.mark.parametrize("nb", [4, 5, 6, 7, 8, 9])
 def test_affine_and_stored_metric_paths_agree(nb, monkeypatch):
     """uniform (all-parallelogram) meshes run the stiffness phase from three per-element constants with the quadrature weights
     folded into the tables; CUDDH_B200_AFFINE=0 forces the stored-metric kernels. Both against the oracle (1e-12) and against
@@ -825,9 +825,10 @@ def test_affine_and_stored_metric_paths_agree(nb, monkeypatch):
             Sp.action(-0.75, dX[n:], dy)
             assert rel(host(dy), O.StiffnessMatrix(ofem).action(X[n:], y0.copy(), -0.75)) < TOL
             A = cb.Helmholtz(7.0, a2, af, fem, fs)
-            # n_basis 6-8: the thread-pair kernel runs both phases per field in one launch on affine meshes (kind 2), the
+            # n_basis 6-9: the thread-pair kernel runs both phases per field in one launch on affine meshes (kind 2), the
             # per-operator launches (kind 3) on stored-metric meshes
-            assert A.kernel_kind() == (2 if (nb <= 5 or affine) else 3) and A.is_affine() == affine
+            # (n_basis 9 stored metric: the stiffness runs the lane-per-row kernel, kind 0)
+            assert A.kernel_kind() == (2 if (nb <= 5 or affine) else 0 if nb == 9 else 3) and A.is_affine() == affine
             AX = torch.empty(2 * n, dtype=torch.float64, device="cuda")
             A.action(dX, AX)
             assert rel(host(AX[:n]), want_A[:n]) < TOL and rel(host(AX[n:]), want_A[n:]) < TOL
