@@ -5,6 +5,9 @@ data differently must agree bit for bit), the result norm and the kernel time (m
 import hashlib, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, cuddhelmholtz_b200 as cb
+if os.environ.get("CUDDH_B200_LIBPATH"):  # experiments: an alternative build of the library (scripts only, not a product knob)
+    from cuddhelmholtz_b200 import capi as _capi
+    _capi.LIB_PATH = os.environ["CUDDH_B200_LIBPATH"]
 nx, nb = int(sys.argv[1]), int(sys.argv[2])
 mesh = cb.Mesh2D.uniform_rect(nx, -1.0, 1.0, nx, -1.0, 1.0)
 fem = cb.H1Space(mesh, cb.Basis(nb))
