@@ -25,8 +25,12 @@
 // Around it the same machinery as volume_action_ws: persistent CTAs of 256 threads, 2 per SM; a helper warpgroup gathers x for
 // the next patch (64 elements, node-major plan) with cp.async, assembles the previous patch's element-boundary DOFs in the
 // plan's CSR order (bitwise reproducible) and prefetches lists and metric blocks into L2; two patch buffers rotate. Stored
-// metric data streams through registers one quadrature row ahead (a row is ~1200 issue cycles long at this order: deeper than
-// an L2 round trip), laid out [row][pair][thread] so that every load of a warp is one contiguous 512-byte run.
+// metric data is laid out [row][pair][thread] so that every load of a warp is one contiguous 512-byte run; the stiffness streams it
+// through registers one quadrature row ahead (a row is ~1200 issue cycles long at this order: deeper than an L2 round trip), the
+// mass operator (short rows) through a per-thread cp.async ring of three rows. The element-interior results go straight to y: their
+// ids are base + (i-1) + (j-1) * stride under H1Space's first-touch numbering (Plan::interior_affine), so the helper hands over
+// two ids per element. With NQ2 > 0 the weighted-mass phase follows the (affine) stiffness phase on the same element data:
+// the Helmholtz composite S - omega^2 M of one field in one launch.
 #pragma once
         template <int NB, int NQ, bool STIFF>
         struct PairCfg
