@@ -32,42 +32,39 @@ namespace cuddh
         virtual ~Edge() = default;
     };
 
+    // A straight segment between two mesh vertices. Only the segment itself is stored (start point, end - start, its length and
+    // whether the outward normal of the first element is the left or the right normal of the direction of travel); normal,
+    // measure and coordinates are evaluated from that on request - the values the reference's StraightEdge returns
+    // (include/Edge.hpp:95-157), which is also what the C ABI's edge records carry (cuddh_b200_mesh_edges: end points, first
+    // element, side).
     struct StraightEdge : public Edge
     {
     private:
-        double n[2];
-        double meas;
-        double x[2];
-        double dx[2];
+        double a_[2];  // start point
+        double d_[2];  // end point - start point
+        double len_;   // |d_|
+        bool flip_;    // sides 2 and 3 of the first element are traversed against the element's orientation
 
     public:
-        /// end points x0 -> x1; `side` of the first element fixes the sign of the outward normal
         StraightEdge(const double * x0, const double * x1, int side)
+            : a_{x0[0], x0[1]}, d_{x1[0] - x0[0], x1[1] - x0[1]}, len_(std::hypot(x1[0] - x0[0], x1[1] - x0[1])), flip_(side == 2 || side == 3)
         {
-            x[0] = x0[0];
-            x[1] = x0[1];
-            dx[0] = x1[0] - x0[0];
-            dx[1] = x1[1] - x0[1];
-            const double s = std::hypot(dx[0], dx[1]);
-            const double sgn = (side == 2 || side == 3) ? -1 : 1;
-            n[0] = sgn * dx[1] / s;
-            n[1] = -sgn * dx[0] / s;
-            meas = s / 2;
         }
 
-        void normal(const double, double * n_) const override
+        void normal(const double, double * n_) const override // d_ rotated by -90 degrees, unit length, flipped for sides 2 / 3
         {
-            n_[0] = n[0];
-            n_[1] = n[1];
+            const double o = flip_ ? -1.0 : 1.0;
+            n_[0] = o * d_[1] / len_;
+            n_[1] = -o * d_[0] / len_;
         }
-        double measure(const double) const override { return meas; }
+        double measure(const double) const override { return len_ / 2; } // d(x)/d(xi) on xi in [-1, 1]
         void physical_coordinates(const double xi, double * x_) const override
         {
             const double t = 0.5 * (xi + 1.0);
-            x_[0] = x[0] + dx[0] * t;
-            x_[1] = x[1] + dx[1] * t;
+            x_[0] = a_[0] + d_[0] * t;
+            x_[1] = a_[1] + d_[1] * t;
         }
-        double length() const override { return 2.0 * meas; }
+        double length() const override { return len_; }
     };
 } // namespace cuddh
 
