@@ -1527,8 +1527,9 @@ namespace cb200
             if (op.pair) { // thread-pair layout: [row][pair of metric values][thread slot], see volume_action_pair / metric_index_pair
                 op.affine = pair_affine;
                 op.plan = &fem->get_plan_tpe();
-                CB_REQUIRE(op.plan->PE == 64, "thread-pair kernel: the node-major plan must have 64-element patches");
-                if (!op.plan->interior_affine) { // never with H1Space's own numbering; the lane-per-row kernel serves such a plan
+                // never with H1Space's own numbering and the default patch shape (the CUDDH_B200_TPE_PX / PY experiment knobs can change
+                // the latter): the lane-per-row kernel serves such a plan
+                if (op.plan->PE != 64 || !op.plan->interior_affine) {
                     op.pair = false;
                     op.affine = false;
                 }
